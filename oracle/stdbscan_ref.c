@@ -1,0 +1,194 @@
+/*
+ * CPU oracle (plain C) for ST-DBSCAN labels — TEST INFRASTRUCTURE ONLY.
+ *
+ * Restates the RESULT of the reference's sequential ST-DBSCAN
+ * (PointCloudWork/4_temporal_object_tracker.py:469-506, twins
+ * 3_stdbscan_point_clouds.py:101-136 and radar_pipeline/processors/clustering.py:49-115)
+ * in its order-free form (note N4):
+ *   neighbour(p,q)  <=>  sum_d (double(p_d)-double(q_d))^2 <= eps*eps   (scikit-learn BallTree,
+ *                        float64, inclusive, self included; T4:474-475)
+ *                    and |t_p - t_q| <= eps_time in float32               (T4:485-486)
+ *   core(p)         <=>  |N(p)| >= min_samples                            (T4:488)
+ *   clusters         =   connected components of core points; id = rank of the component's
+ *                        smallest core index (discovery order of the loop at T4:479,506)
+ *   border(p)        =   smallest cluster id among p's core neighbours    (T4:503-504)
+ * It exists so that parity cases too large for the Python oracle (its neighbour lists and
+ * per-element loops) still have an independent CPU answer. tests/test_oracle_golden.py pins it
+ * against labels produced by the unmodified reference (tests/golden/).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline leg may load this library.
+ * Build: gcc -O2 -ffp-contract=off -shared -fPIC (see oracle/build.py). No fast-math.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct { int64_t key; int64_t idx; } keyed_t;
+
+static int cmp_keyed(const void* a, const void* b) {
+    const keyed_t* x = (const keyed_t*)a; const keyed_t* y = (const keyed_t*)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return x->idx < y->idx ? -1 : (x->idx > y->idx);
+}
+
+typedef struct {
+    const float* xyz; const float* t; int dim; int64_t n;
+    double eps2; float eps_t;
+    double lo[3]; double cell; int64_t nc[3];
+    keyed_t* sorted;      /* points sorted by cell key */
+    int64_t* ukeys; int64_t* ustart; int64_t nu;
+} grid_t;
+
+static int64_t find_cell(const grid_t* g, int64_t key) {
+    int64_t lo = 0, hi = g->nu - 1;
+    while (lo <= hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (g->ukeys[mid] == key) return mid;
+        if (g->ukeys[mid] < key) lo = mid + 1; else hi = mid - 1;
+    }
+    return -1;
+}
+
+static inline int is_neighbour(const grid_t* g, int64_t p, int64_t q) {
+    float dt = g->t[q] - g->t[p];
+    if (fabsf(dt) > g->eps_t) return 0;
+    if (!(fabsf(dt) <= g->eps_t)) return 0;          /* NaN times never match */
+    double d = 0.0;
+    for (int k = 0; k < g->dim; ++k) {
+        double tmp = (double)g->xyz[p * g->dim + k] - (double)g->xyz[q * g->dim + k];
+        d += tmp * tmp;
+    }
+    return d <= g->eps2;
+}
+
+typedef void (*visit_fn)(int64_t p, int64_t q, void* ctx);
+
+static void for_each_neighbour(const grid_t* g, int64_t p, visit_fn fn, void* ctx) {
+    int64_t c[3] = {0, 0, 0};
+    for (int k = 0; k < g->dim; ++k)
+        c[k] = (int64_t)floor(((double)g->xyz[p * g->dim + k] - g->lo[k]) / g->cell);
+    int64_t z0 = g->dim > 2 ? c[2] - 1 : 0, z1 = g->dim > 2 ? c[2] + 1 : 0;
+    int64_t y0 = g->dim > 1 ? c[1] - 1 : 0, y1 = g->dim > 1 ? c[1] + 1 : 0;
+    for (int64_t cx = c[0] - 1; cx <= c[0] + 1; ++cx) {
+        if (cx < 0 || cx >= g->nc[0]) continue;
+        for (int64_t cy = y0; cy <= y1; ++cy) {
+            if (cy < 0 || cy >= g->nc[1]) continue;
+            for (int64_t cz = z0; cz <= z1; ++cz) {
+                if (cz < 0 || cz >= g->nc[2]) continue;
+                int64_t u = find_cell(g, (cx * g->nc[1] + cy) * g->nc[2] + cz);
+                if (u < 0) continue;
+                for (int64_t s = g->ustart[u]; s < g->ustart[u + 1]; ++s) {
+                    int64_t q = g->sorted[s].idx;
+                    if (is_neighbour(g, p, q)) fn(p, q, ctx);
+                }
+            }
+        }
+    }
+}
+
+typedef struct { int64_t* count; } count_ctx;
+static void visit_count(int64_t p, int64_t q, void* v) { (void)q; ((count_ctx*)v)->count[p]++; }
+
+typedef struct { int64_t* parent; const unsigned char* core; } union_ctx;
+static int64_t uf_find(int64_t* parent, int64_t a) {
+    while (parent[a] != a) { parent[a] = parent[parent[a]]; a = parent[a]; }
+    return a;
+}
+static void visit_union(int64_t p, int64_t q, void* v) {
+    union_ctx* u = (union_ctx*)v;
+    if (!u->core[q]) return;
+    int64_t a = uf_find(u->parent, p), b = uf_find(u->parent, q);
+    if (a == b) return;
+    if (a < b) u->parent[b] = a; else u->parent[a] = b;
+}
+
+typedef struct { const int* labels; const unsigned char* core; int best; } border_ctx;
+static void visit_border(int64_t p, int64_t q, void* v) {
+    (void)p;
+    border_ctx* b = (border_ctx*)v;
+    if (b->core[q] && (b->best < 0 || b->labels[q] < b->best)) b->best = b->labels[q];
+}
+
+/* Returns number of clusters, or -1 on allocation failure / bad arguments. */
+int64_t oracle_stdbscan(const float* xyz, int dim, const float* times, int64_t n,
+                        double eps_space, float eps_time, int min_samples,
+                        int* labels, unsigned char* core_out) {
+    if (dim < 1 || dim > 3 || n < 0) return -1;
+    for (int64_t i = 0; i < n; ++i) labels[i] = -1;
+    if (core_out) memset(core_out, 0, (size_t)n);
+    if (n == 0) return 0;
+
+    grid_t g; memset(&g, 0, sizeof g);
+    g.xyz = xyz; g.t = times; g.dim = dim; g.n = n;
+    g.eps2 = eps_space * eps_space; g.eps_t = eps_time;
+    double hi[3] = {0, 0, 0};
+    for (int k = 0; k < 3; ++k) { g.lo[k] = 0; g.nc[k] = 1; }
+    for (int k = 0; k < dim; ++k) {
+        g.lo[k] = hi[k] = xyz[k];
+        for (int64_t i = 1; i < n; ++i) {
+            double v = xyz[i * dim + k];
+            if (v < g.lo[k]) g.lo[k] = v;
+            if (v > hi[k]) hi[k] = v;
+        }
+    }
+    g.cell = eps_space > 0 ? eps_space * (1.0 + 1e-9) : 1.0;
+    for (;;) {                                   /* coarsen until the key fits comfortably */
+        int ok = 1;
+        for (int k = 0; k < dim; ++k) {
+            g.nc[k] = (int64_t)floor((hi[k] - g.lo[k]) / g.cell) + 1;
+            if (g.nc[k] > (1 << 20)) ok = 0;
+        }
+        if (ok) break;
+        g.cell *= 2.0;
+    }
+
+    g.sorted = (keyed_t*)malloc(sizeof(keyed_t) * (size_t)n);
+    g.ukeys = (int64_t*)malloc(sizeof(int64_t) * (size_t)n);
+    g.ustart = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n + 1));
+    int64_t* count = (int64_t*)calloc((size_t)n, sizeof(int64_t));
+    int64_t* parent = (int64_t*)malloc(sizeof(int64_t) * (size_t)n);
+    unsigned char* core = (unsigned char*)calloc((size_t)n, 1);
+    if (!g.sorted || !g.ukeys || !g.ustart || !count || !parent || !core) return -1;
+
+    for (int64_t i = 0; i < n; ++i) {
+        int64_t c[3] = {0, 0, 0};
+        for (int k = 0; k < dim; ++k)
+            c[k] = (int64_t)floor(((double)xyz[i * dim + k] - g.lo[k]) / g.cell);
+        g.sorted[i].key = (c[0] * g.nc[1] + c[1]) * g.nc[2] + c[2];
+        g.sorted[i].idx = i;
+    }
+    qsort(g.sorted, (size_t)n, sizeof(keyed_t), cmp_keyed);
+    g.nu = 0;
+    for (int64_t s = 0; s < n; ++s) {
+        if (s == 0 || g.sorted[s].key != g.sorted[s - 1].key) {
+            g.ukeys[g.nu] = g.sorted[s].key; g.ustart[g.nu] = s; g.nu++;
+        }
+    }
+    g.ustart[g.nu] = n;
+
+    count_ctx cc = {count};
+    for (int64_t p = 0; p < n; ++p) for_each_neighbour(&g, p, visit_count, &cc);
+    for (int64_t p = 0; p < n; ++p) { core[p] = count[p] >= min_samples; parent[p] = p; }
+
+    union_ctx uc = {parent, core};
+    for (int64_t p = 0; p < n; ++p) if (core[p]) for_each_neighbour(&g, p, visit_union, &uc);
+
+    int64_t n_clusters = 0;
+    int* root_id = (int*)malloc(sizeof(int) * (size_t)n);
+    if (!root_id) return -1;
+    for (int64_t p = 0; p < n; ++p)
+        root_id[p] = (core[p] && uf_find(parent, p) == p) ? (int)n_clusters++ : -1;
+    for (int64_t p = 0; p < n; ++p) if (core[p]) labels[p] = root_id[uf_find(parent, p)];
+    for (int64_t p = 0; p < n; ++p) {
+        if (core[p]) continue;
+        border_ctx bc = {labels, core, -1};
+        for_each_neighbour(&g, p, visit_border, &bc);
+        labels[p] = bc.best;
+    }
+    if (core_out) memcpy(core_out, core, (size_t)n);
+
+    free(root_id); free(core); free(parent); free(count);
+    free(g.ustart); free(g.ukeys); free(g.sorted);
+    return n_clusters;
+}
