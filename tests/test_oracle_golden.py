@@ -94,7 +94,7 @@ def test_cluster_records_vs_reference(tag, eps_s, eps_t, ms):
         csv = csv[np.lexsort((csv[:, 1], csv[:, 0]))]
         # to_csv prints the float32 centroids with their shortest round-trip repr
         assert np.array_equal(csv.astype(np.float32), rec.astype(np.float32))
-        assert np.array_equal(csv[:, :3], rec[:, :3]) and np.array_equal(csv[:, 5], rec[:, 5])
+        assert np.array_equal(csv[:, :3], rec[:, :3])   # (pandas' CSV float parser is 1 ulp inexact in f64)
 
 
 def test_random_stdbscan_vs_reference():
