@@ -1,0 +1,180 @@
+/*
+ * radarb200 — C ABI of the B200-native per-frame detection hot path
+ * (spoke-to-point -> land/stationary persistence filter -> temporal ST-DBSCAN).
+ *
+ * The reference (SamuelCancilla2/radar-point-cloud-tracking) has no FFI/plugin interface: its
+ * boundary for this path is the Python function surface of
+ *   PointCloudWork/4_temporal_object_tracker.py            ("T4")
+ *   PointCloudWork/3_stdbscan_point_clouds.py               ("T3")
+ *   PointCloudWork/5_gain_fusion_ply_builder.py             ("T5")
+ *   radar-pipeline/src/radar_pipeline/{core,processors}     ("PKG")
+ * Each entry point below names the reference lines it replaces; INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only. Every data pointer is a DEVICE pointer unless
+ *     the parameter comment says "host". The caller owns all buffers; the library owns only the
+ *     scratch inside rb_ctx (grown on demand, freed by rb_destroy).
+ *   - All work is enqueued on the caller's stream (`stream` is a cudaStream_t passed as void*;
+ *     NULL = legacy default stream). A call synchronises that stream only where its comment says
+ *     "syncs" (a count or a bound has to reach the host).
+ *   - Return value: 0 = ok, negative = error (rb_last_error() gives the text). Nothing throws.
+ *   - One rb_ctx per device and per host thread; a ctx is not thread safe.
+ *   - There is no CPU fallback: without a CUDA device rb_create fails.
+ */
+#ifndef RADARB200_H
+#define RADARB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB_OK 0
+#define RB_ERR_CUDA (-1)        /* a CUDA runtime call failed                     */
+#define RB_ERR_ARG (-2)         /* bad argument                                   */
+#define RB_ERR_CAPACITY (-3)    /* caller-provided output capacity too small      */
+#define RB_ERR_NOMEM (-4)       /* scratch allocation failed                      */
+#define RB_ERR_NCCL (-5)        /* collective layer failure (reserved)            */
+
+typedef struct rb_ctx rb_ctx;
+
+/* ---- context ----------------------------------------------------------------------------- */
+int rb_version(void);                               /* ABI version, currently 1 */
+const char* rb_last_error(void);                    /* thread-local text of the last failure */
+int rb_create(int device, rb_ctx** out);            /* fails without a usable CUDA device */
+void rb_destroy(rb_ctx* ctx);
+int rb_device_info(rb_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_bytes);
+
+/* ---- a1 + a2: spoke-to-point with threshold, stride and multi-gain concat fusion ------------
+ * Replaces the numeric part of load_radar_csv (T4:200-232; twins PKG/core/transforms.py:13-79,
+ * T5:97-121) for a whole batch of sweeps in ONE launch, and the concatenation of build_frame
+ * (T4:322-344): sweeps are laid out frame-major / ascending-gain-minor, so the output of a frame
+ * is exactly np.concatenate over its gains.
+ *
+ *   echo       [W][S][E] float32, row major (W = frames x gains sweeps)
+ *   cos_tab    [W][S]  float32  np.cos(deg2rad(Angle.f32*360/8196)) computed by the HOST with
+ *   sin_tab    [W][S]  float32  numpy (bit-exactness of trig is a host contract)
+ *   range_res  [W][S]  float32  Scale.f32 / E                                   (T4:213)
+ *   ranges     [W][S][E] float32, OPTIONAL (NULL = use range_res*j): explicit range of every cell,
+ *              for callers that hold a RadarSweep.ranges array (PKG/core/transforms.py:63); only
+ *              the cells that are written are read.
+ *   sweep_gain [W]     int32    gain label written for every point of the sweep (T4:333)
+ * For sweep w, element (s, j) survives when echo > threshold (strict, T4:221); survivors are
+ * ranked in row-major order and every `stride`-th one (rank % stride == 0, T4:227-230) is written:
+ *   x = fl32(fl32(range_res*j) * cos), y = fl32(fl32(range_res*j) * sin), intensity = echo.
+ * Outputs (capacity `cap` points each): x, y, inten float32; gain int32;
+ *   sweep_base [W+1] int64: output offset of every sweep; sweep_base[W] = total points.
+ * If the total exceeds `cap`, points beyond `cap` are dropped (never written) and sweep_base
+ * still holds the true sizes, so the caller can detect it after its own sync. Does not sync.
+ */
+int rb_spoke_to_points(rb_ctx* ctx, const float* echo, const float* cos_tab, const float* sin_tab,
+                       const float* range_res, const float* ranges, const int32_t* sweep_gain,
+                       int64_t n_sweeps, int n_spokes, int n_bins,
+                       float threshold, int stride,
+                       float* x, float* y, float* inten, int32_t* gain, int64_t cap,
+                       int64_t* sweep_base, void* stream);
+
+/* polar_to_cartesian on a full grid (PKG/core/transforms.py:13-34): x = ranges*cos[:,None],
+ * y = ranges*sin[:,None]; ranges/x/y float32 [n_rows][n_cols], cos/sin float32 [n_rows] from the
+ * host's numpy. No sync. */
+int rb_polar_to_cartesian(rb_ctx* ctx, const float* ranges, const float* cos_tab, const float* sin_tab,
+                          int64_t n_rows, int n_cols, float* x, float* y, void* stream);
+
+/* frame_off[f] = sweep_base[f*gains_per_frame], f = 0..n_frames (int64, device). No sync. */
+int rb_frame_offsets(rb_ctx* ctx, const int64_t* sweep_base, int64_t n_frames, int gains_per_frame,
+                     int64_t* frame_off, void* stream);
+
+/* times[i] = frame_ids[f] for frame_off[f] <= i < frame_off[f+1]  (T4:460,467: float32 frame
+ * ids per point). frame_ids float32[n_frames] device. No sync. */
+int rb_expand_frame_times(rb_ctx* ctx, const int64_t* frame_off, const float* frame_ids,
+                          int64_t n_frames, int64_t n_points, float* times, void* stream);
+
+/* ---- a3: max fusion on a grid (T5:222-273 fuse_gains_max) --------------------------------------
+ * Pools n points on a grid anchored at (x_min, y_min): cell = trunc((v - v_min)/res) in float32
+ * (T5:258-259), keeps the max intensity per cell (T5:263) and emits occupied cells in y-major
+ * order (T5:267): cell_ix, cell_iy int32 and max intensity float32, capacity cap_cells. The cell
+ * centres x_min + ix*res + res/2 are float64 host arithmetic (T5:269-270) and stay in Python.
+ * x_min / y_min / nx / ny are the host's float32 numpy values (T5:251-256). n_cells_out: host
+ * int64. Syncs. */
+int rb_fuse_max(rb_ctx* ctx, const float* x, const float* y, const float* inten, int64_t n,
+                float x_min, float y_min, float resolution, int nx, int ny,
+                int32_t* cell_ix, int32_t* cell_iy, float* cell_max, int64_t cap_cells,
+                int64_t* n_cells_out, void* stream);
+
+/* ---- a4-a6: land / stationary persistence filter --------------------------------------------- */
+/* Global bounds (T4:365-369): out4 = device float32 {x_min, x_max, y_min, y_max}. No sync. */
+int rb_bounds(rb_ctx* ctx, const float* x, const float* y, int64_t n, float* out4, void* stream);
+
+/* build_occupancy_grid accumulation (T4:378-389): for every point
+ *   ix = clip(searchsorted_right(x_edges, (double)x) - 1, 0, n_x_edges - 2)      (T4:384)
+ *   count[ix][iy] += 1 (int32);  isum[ix][iy] += intensity (float64)            (T4:388-389)
+ * x_edges / y_edges are the float64 np.arange edges computed on the host (T4:372-373) and copied
+ * to the device. count/isum must be zeroed by the caller; the call accumulates. No sync. */
+int rb_land_accumulate(rb_ctx* ctx, const float* x, const float* y, const float* inten, int64_t n,
+                       const double* x_edges, int n_x_edges, const double* y_edges, int n_y_edges,
+                       int32_t* count, double* isum, void* stream);
+
+/* identify_land_cells (T4:394-410) in float64 on the device:
+ *   land = (count / max(num_frames,1) >= persistence) & ((count>0 ? isum/count : 0) >= min_intensity)
+ * land = uint8[n_cells]. No sync. */
+int rb_land_cells(rb_ctx* ctx, const int32_t* count, const double* isum, int64_t n_cells,
+                  int64_t num_frames, double persistence, double min_intensity,
+                  uint8_t* land, void* stream);
+
+/* filter_land_from_frame for all frames at once (T4:413-436): order-preserving removal of points
+ * whose cell is land; frame_off_out[f] = new start of frame f. Outputs have capacity n.
+ * keep_mask (optional, may be NULL) receives the uint8 keep flag per input point. No sync. */
+int rb_land_filter(rb_ctx* ctx, const float* x, const float* y, const float* inten,
+                   const int32_t* gain, int64_t n, const int64_t* frame_off, int64_t n_frames,
+                   const double* x_edges, int n_x_edges, const double* y_edges, int n_y_edges,
+                   const uint8_t* land,
+                   float* x_out, float* y_out, float* inten_out, int32_t* gain_out,
+                   int64_t* frame_off_out, uint8_t* keep_mask, void* stream);
+
+/* ---- a7: temporal ST-DBSCAN ------------------------------------------------------------------
+ * Replaces st_dbscan (T4:443-506 label computation; T3:101-136; PKG/processors/clustering.py:
+ * 49-115; native precedent radar-pipeline-rs/src/processors/clustering.rs:209-325).
+ *   neighbour(p,q) <=> sum_d (double(p_d)-double(q_d))^2 <= eps_space^2  (float64, inclusive,
+ *                      self included: sklearn BallTree semantics, T4:474-475)
+ *                  and |t_p - t_q| <= (float)eps_time in float32          (T4:485-486)
+ *   core <=> |N| >= min_samples; clusters = connected components of cores;
+ *   labels are the reference's own numbering: id = rank of the component's smallest core index;
+ *   border points take the smallest id among their core neighbours; noise = -1.
+ * Coordinates: component d of point i is at x[i*stride], y[i*stride], z[i*stride] (z NULL = 2-D),
+ * so both SoA (stride 1) and a row-major [N][D] array (x=base, y=base+1, z=base+2, stride D) work.
+ *   times  float32[n];  labels int32[n] out;  core uint8[n] out (optional, may be NULL)
+ *   n_clusters: host int64 out (optional).  Syncs (grid dimensions are chosen on the host).
+ */
+int rb_stdbscan(rb_ctx* ctx, const float* x, const float* y, const float* z, int64_t stride,
+                const float* times, int64_t n, double eps_space, float eps_time, int min_samples,
+                int32_t* labels, uint8_t* core, int64_t* n_clusters, void* stream);
+
+/* Work counters of the last rb_stdbscan on this ctx (host): pair tests per neighbour sweep, grid
+ * cells, cell size. For bench/roofline reporting only. */
+typedef struct rb_dbscan_stats {
+    int64_t n_points, n_cells, n_core, n_clusters;
+    int64_t pair_tests_count, pair_tests_union, pair_tests_border;
+    double cell_size, time_bin;
+    int32_t dims[4];            /* nx, ny, nz, nt */
+    int32_t time_radius;
+} rb_dbscan_stats;
+int rb_stdbscan_last_stats(rb_ctx* ctx, rb_dbscan_stats* out);
+
+/* ---- test/bench infrastructure (not part of the reference surface) ---------------------------
+ * Device twin of radar_point_cloud_tracking_b200.synthetic.synth_echo: fills echo[W][S][E] for
+ * sweeps w0 .. w0+n_sweeps-1 of the data set. sweep_keys uint32[n_sweeps], clutter_thr
+ * uint32[n_sweeps], rects int32[n_rects][10], rect_off int32[n_frames+1] (all device). */
+int rb_synth_echo(rb_ctx* ctx, float* echo, int64_t n_sweeps, int n_spokes, int n_bins,
+                  int gains_per_frame, int64_t first_frame,
+                  const uint32_t* sweep_keys, const uint32_t* clutter_thr,
+                  const int32_t* rects, const int32_t* rect_off, void* stream);
+
+/* Number of kernels this library has launched on this ctx since creation (bench "gpu_launches"). */
+int64_t rb_launch_count(rb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RADARB200_H */

@@ -1,0 +1,141 @@
+"""ctypes binding of ``libradarb200.so`` (the C ABI declared in ``include/radarb200.h``).
+
+There is no fallback: if the shared library is missing or no CUDA device is present, every
+entry point raises. PyTorch is used only to allocate device memory and to provide the current
+stream; all compute is in the hand-written kernels behind this ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from pathlib import Path
+from typing import Dict, Optional
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libradarb200.so"
+
+c_i32, c_i64, c_f32, c_f64, c_vp = C.c_int, C.c_int64, C.c_float, C.c_double, C.c_void_p
+
+
+class DbscanStats(C.Structure):
+    _fields_ = [("n_points", c_i64), ("n_cells", c_i64), ("n_core", c_i64), ("n_clusters", c_i64),
+                ("pair_tests_count", c_i64), ("pair_tests_union", c_i64), ("pair_tests_border", c_i64),
+                ("cell_size", c_f64), ("time_bin", c_f64), ("dims", c_i32 * 4), ("time_radius", c_i32)]
+
+
+#: name -> (restype, argtypes); must list every symbol of include/radarb200.h
+SIGNATURES = {
+    "rb_version": (c_i32, []),
+    "rb_last_error": (C.c_char_p, []),
+    "rb_create": (c_i32, [c_i32, C.POINTER(c_vp)]),
+    "rb_destroy": (None, [c_vp]),
+    "rb_device_info": (c_i32, [c_vp, C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i64)]),
+    "rb_spoke_to_points": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_f32, c_i32,
+                                   c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "rb_polar_to_cartesian": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp]),
+    "rb_frame_offsets": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),
+    "rb_expand_frame_times": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "rb_fuse_max": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_i32, c_i32,
+                            c_vp, c_vp, c_vp, c_i64, C.POINTER(c_i64), c_vp]),
+    "rb_bounds": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "rb_land_accumulate": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp]),
+    "rb_land_cells": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_f64, c_f64, c_vp, c_vp]),
+    "rb_land_filter": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i32, c_vp, c_i32,
+                               c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "rb_stdbscan": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_f64, c_f32, c_i32,
+                            c_vp, c_vp, C.POINTER(c_i64), c_vp]),
+    "rb_stdbscan_last_stats": (c_i32, [c_vp, C.POINTER(DbscanStats)]),
+    "rb_synth_echo": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "rb_launch_count": (c_i64, [c_vp]),
+}
+
+_lib: Optional[C.CDLL] = None
+_lock = threading.Lock()
+
+
+class RadarB200Error(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the shared library and bind every declared symbol (no compute, works without a GPU)."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not LIB_PATH.exists():
+            raise RadarB200Error(
+                f"{LIB_PATH} is missing: build it with `python -m radar_point_cloud_tracking_b200.build` "
+                "(there is no CPU fallback for this path)")
+        lib = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().rb_last_error()
+        raise RadarB200Error(f"{what} failed (rc={rc}): {msg.decode() if msg else '?'}")
+
+
+class Context:
+    """One ``rb_ctx`` per CUDA device (per thread of use)."""
+
+    def __init__(self, device: int):
+        lib = load()
+        h = c_vp()
+        check(lib.rb_create(int(device), C.byref(h)), "rb_create")
+        self.handle = h
+        self.device = int(device)
+        self.lib = lib
+        sm, maj, mnr, l2 = c_i32(), c_i32(), c_i32(), c_i64()
+        check(lib.rb_device_info(h, C.byref(sm), C.byref(maj), C.byref(mnr), C.byref(l2)), "rb_device_info")
+        self.sm_count, self.cc, self.l2_bytes = sm.value, (maj.value, mnr.value), l2.value
+
+    def launch_count(self) -> int:
+        return int(self.lib.rb_launch_count(self.handle))
+
+    def close(self) -> None:
+        if self.handle:
+            self.lib.rb_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_contexts: Dict[int, Context] = {}
+
+
+def context(device: Optional[int] = None) -> Context:
+    """Context of ``device`` (default: torch's current CUDA device). Raises without a GPU."""
+    import torch
+
+    if not torch.cuda.is_available():
+        raise RadarB200Error("no CUDA device: the radar-b200 detection path is GPU only (no CPU fallback)")
+    if device is None:
+        device = torch.cuda.current_device()
+    ctx = _contexts.get(device)
+    if ctx is None:
+        ctx = _contexts[device] = Context(device)
+    return ctx
+
+
+def stream_ptr() -> int:
+    import torch
+
+    return int(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t) -> Optional[int]:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return int(t.data_ptr())

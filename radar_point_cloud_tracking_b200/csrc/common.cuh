@@ -1,0 +1,133 @@
+// Shared host/device helpers for libradarb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "radarb200.h"
+
+#define RB_WARP 32
+
+struct rb_scratch {
+    void* ptr = nullptr;
+    size_t cap = 0;
+};
+
+// Named scratch slots; each grows on demand and is reused across calls.
+enum rb_slot {
+    RB_S_TILE_STATUS = 0,   // spoke: decoupled look-back tile descriptors
+    RB_S_SWEEP_FLAGS,       // spoke: per-sweep ready flags + ticket
+    RB_S_REDUCE,            // bounds partials
+    RB_S_KEEP,              // land filter keep flags
+    RB_S_BLOCKSUM,          // scan block sums
+    RB_S_BLOCKSUM2,
+    RB_S_CELL_ID,           // dbscan: cell id per point
+    RB_S_CELL_START,        // dbscan: cell start table
+    RB_S_CELL_FILL,
+    RB_S_SORT_IDX,
+    RB_S_SX, RB_S_SY, RB_S_SZ, RB_S_ST,
+    RB_S_CORE,
+    RB_S_PARENT,
+    RB_S_MINORIG,
+    RB_S_FLAGS,
+    RB_S_RANK,
+    RB_S_SLABEL,
+    RB_S_STATS,
+    RB_S_MISC,
+    RB_S_FUSE_GRID,
+    RB_S_COUNT
+};
+
+struct rb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    int64_t l2_bytes = 0;
+    int64_t launches = 0;
+    rb_scratch slots[RB_S_COUNT];
+    void* pinned = nullptr;          // small pinned staging buffer (host)
+    size_t pinned_cap = 0;
+    rb_dbscan_stats last_stats;
+};
+
+void rb_set_error(const char* fmt, ...);
+int rb_scratch_get(rb_ctx* ctx, rb_slot slot, size_t bytes, void** out);
+
+#define RB_CUDA(call)                                                                      \
+    do {                                                                                   \
+        cudaError_t _e = (call);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            rb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+            return RB_ERR_CUDA;                                                            \
+        }                                                                                  \
+    } while (0)
+
+#define RB_LAUNCH_CHECK(ctx)                                                               \
+    do {                                                                                   \
+        (ctx)->launches++;                                                                 \
+        cudaError_t _e = cudaGetLastError();                                               \
+        if (_e != cudaSuccess) {                                                           \
+            rb_set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return RB_ERR_CUDA;                                                            \
+        }                                                                                  \
+    } while (0)
+
+#define RB_REQUIRE(cond, msg)                                                              \
+    do {                                                                                   \
+        if (!(cond)) {                                                                     \
+            rb_set_error("%s:%d: %s", __FILE__, __LINE__, msg);                            \
+            return RB_ERR_ARG;                                                             \
+        }                                                                                  \
+    } while (0)
+
+#define RB_TRY(expr)                                                                       \
+    do {                                                                                   \
+        int _rc = (expr);                                                                  \
+        if (_rc != RB_OK) return _rc;                                                      \
+    } while (0)
+
+static inline int64_t rb_div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- device helpers ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned rb_lane() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned rb_lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+// streaming 128-bit load: read-only path, do not allocate in L1
+__device__ __forceinline__ float4 rb_ld_stream4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ unsigned long long rb_ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void rb_st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ int rb_ld_acquire_s32(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void rb_st_release_s32(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int rb_ld_relaxed_s32(const int* p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+#endif
+
+// device-wide exclusive scan of int32 -> int32 (n < 2^31); total written to *total_out (device, optional)
+int rb_exclusive_scan_i32(rb_ctx* ctx, const int32_t* in, int32_t* out, int64_t n,
+                          int32_t* total_out, cudaStream_t stream);

@@ -1,0 +1,306 @@
+"""Device-resident stages of the detection path: thin, typed wrappers over the C ABI.
+
+Everything here takes and returns CUDA ``torch`` tensors (torch = allocator + stream only) and
+launches the hand-written kernels of ``libradarb200.so`` on torch's current stream. No stage has a
+CPU implementation; calling one without a GPU raises :class:`RadarB200Error`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import RadarB200Error, check, context, ptr, stream_ptr
+
+
+def _dev(t: torch.Tensor, dtype: torch.dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RadarB200Error(f"{name} must be a CUDA tensor")
+    if t.dtype != dtype:
+        raise RadarB200Error(f"{name} must be {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+#: bench hook: when a list, (start, end) CUDA events around every spoke-to-point launch are appended
+SPOKE_EVENTS = None
+
+
+@dataclass
+class PointBatch:
+    """Points of a batch of frames, SoA on the device, frames concatenated in order.
+
+    ``frame_off`` (int64[F+1], device) delimits the frames; ``n`` is the number of valid points
+    (host int). The tensors may be longer than ``n`` (capacity)."""
+    x: torch.Tensor
+    y: torch.Tensor
+    inten: torch.Tensor
+    gain: torch.Tensor
+    frame_off: torch.Tensor
+    n: int
+
+    def trimmed(self) -> "PointBatch":
+        n = self.n
+        return PointBatch(self.x[:n], self.y[:n], self.inten[:n], self.gain[:n], self.frame_off, n)
+
+
+# --------------------------------------------------------------------------------------- a1 + a2
+def spoke_to_points_raw(echo: torch.Tensor, cos_tab: torch.Tensor, sin_tab: torch.Tensor,
+                        range_res: Optional[torch.Tensor], sweep_gain: torch.Tensor, threshold: float, stride: int,
+                        cap: int, out: Optional[Tuple[torch.Tensor, ...]] = None,
+                        ranges: Optional[torch.Tensor] = None):
+    """One launch over ``echo[W,S,E]``; returns ``(x, y, inten, gain, sweep_base)`` without syncing.
+    ``sweep_base[W]`` (device) is the true total, which may exceed ``cap`` (then points were dropped)."""
+    ctx = context(echo.device.index)
+    echo = _dev(echo, torch.float32, "echo")
+    if echo.dim() != 3:
+        raise RadarB200Error("echo must be [sweeps, spokes, bins]")
+    W, S, E = echo.shape
+    cos_tab = _dev(cos_tab, torch.float32, "cos_tab")
+    sin_tab = _dev(sin_tab, torch.float32, "sin_tab")
+    if range_res is not None:
+        range_res = _dev(range_res, torch.float32, "range_res")
+    if ranges is not None:
+        ranges = _dev(ranges, torch.float32, "ranges")
+        if ranges.numel() != W * S * E:
+            raise RadarB200Error("ranges must be [sweeps, spokes, bins]")
+    elif range_res is None:
+        raise RadarB200Error("need range_res or ranges")
+    sweep_gain = _dev(sweep_gain, torch.int32, "sweep_gain")
+    if cos_tab.numel() != W * S or sin_tab.numel() != W * S or (range_res is not None and range_res.numel() != W * S):
+        raise RadarB200Error("spoke tables must be [sweeps, spokes]")
+    if sweep_gain.numel() != W:
+        raise RadarB200Error("sweep_gain must be [sweeps]")
+    dev = echo.device
+    if out is None:
+        x = torch.empty(cap, dtype=torch.float32, device=dev)
+        y = torch.empty(cap, dtype=torch.float32, device=dev)
+        inten = torch.empty(cap, dtype=torch.float32, device=dev)
+        gain = torch.empty(cap, dtype=torch.int32, device=dev)
+        sweep_base = torch.empty(W + 1, dtype=torch.int64, device=dev)
+    else:
+        x, y, inten, gain, sweep_base = out
+        cap = min(x.numel(), y.numel(), inten.numel(), gain.numel())
+    events = SPOKE_EVENTS
+    if events is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    check(ctx.lib.rb_spoke_to_points(ctx.handle, ptr(echo), ptr(cos_tab), ptr(sin_tab), ptr(range_res),
+                                     ptr(ranges), ptr(sweep_gain), W, S, E, float(threshold), int(stride),
+                                     ptr(x), ptr(y), ptr(inten), ptr(gain), cap, ptr(sweep_base), stream_ptr()),
+          "rb_spoke_to_points")
+    if events is not None:
+        e1.record()
+        events.append((e0, e1))
+    return x, y, inten, gain, sweep_base
+
+
+def default_capacity(W: int, S: int, E: int, stride: int) -> int:
+    worst = W * ((S * E + max(stride, 1) - 1) // max(stride, 1))
+    if worst * 16 <= (1 << 30):
+        return max(worst, 1)
+    return max(worst // 8, 1 << 22)
+
+
+def spoke_to_points(echo: torch.Tensor, cos_tab: torch.Tensor, sin_tab: torch.Tensor,
+                    range_res: Optional[torch.Tensor], sweep_gain: torch.Tensor, threshold: float, stride: int,
+                    gains_per_frame: int = 1, cap: Optional[int] = None,
+                    ranges: Optional[torch.Tensor] = None) -> PointBatch:
+    """Spoke-to-point for ``echo[W,S,E]`` (W = frames x gains, frame major). Syncs once to learn the
+    point count; re-runs with a larger buffer if the capacity guess was too small."""
+    W, S, E = echo.shape
+    if W % gains_per_frame:
+        raise RadarB200Error("sweeps must be a multiple of gains_per_frame")
+    if cap is None:
+        cap = default_capacity(W, S, E, stride)
+    ctx = context(echo.device.index)
+    while True:
+        x, y, inten, gain, sweep_base = spoke_to_points_raw(echo, cos_tab, sin_tab, range_res, sweep_gain,
+                                                            threshold, stride, cap, ranges=ranges)
+        n = int(sweep_base[-1].item())
+        if n <= cap:
+            break
+        cap = n
+    F = W // gains_per_frame
+    frame_off = torch.empty(F + 1, dtype=torch.int64, device=echo.device)
+    check(ctx.lib.rb_frame_offsets(ctx.handle, ptr(sweep_base), F, gains_per_frame, ptr(frame_off), stream_ptr()),
+          "rb_frame_offsets")
+    return PointBatch(x, y, inten, gain, frame_off, n)
+
+
+def polar_to_cartesian(ranges: torch.Tensor, cos_tab: torch.Tensor, sin_tab: torch.Tensor):
+    """Full-grid ``x = ranges*cos[:,None]``, ``y = ranges*sin[:,None]`` (PKG transforms.py:13-34)."""
+    ctx = context(ranges.device.index)
+    ranges = _dev(ranges, torch.float32, "ranges")
+    n, m = ranges.shape
+    x = torch.empty_like(ranges)
+    y = torch.empty_like(ranges)
+    check(ctx.lib.rb_polar_to_cartesian(ctx.handle, ptr(ranges), ptr(_dev(cos_tab, torch.float32, "cos_tab")),
+                                        ptr(_dev(sin_tab, torch.float32, "sin_tab")), n, m, ptr(x), ptr(y),
+                                        stream_ptr()), "rb_polar_to_cartesian")
+    return x, y
+
+
+def frame_offsets(sweep_base: torch.Tensor, n_frames: int, gains_per_frame: int) -> torch.Tensor:
+    ctx = context(sweep_base.device.index)
+    frame_off = torch.empty(n_frames + 1, dtype=torch.int64, device=sweep_base.device)
+    check(ctx.lib.rb_frame_offsets(ctx.handle, ptr(sweep_base), n_frames, gains_per_frame, ptr(frame_off),
+                                   stream_ptr()), "rb_frame_offsets")
+    return frame_off
+
+
+def expand_frame_times(frame_off: torch.Tensor, frame_ids: torch.Tensor, n_points: int) -> torch.Tensor:
+    """float32 frame id per point (reference T4:460,467)."""
+    ctx = context(frame_off.device.index)
+    frame_ids = _dev(frame_ids, torch.float32, "frame_ids")
+    frame_off = _dev(frame_off, torch.int64, "frame_off")
+    times = torch.empty(max(n_points, 1), dtype=torch.float32, device=frame_off.device)[:n_points]
+    check(ctx.lib.rb_expand_frame_times(ctx.handle, ptr(frame_off), ptr(frame_ids), frame_ids.numel(), n_points,
+                                        ptr(times), stream_ptr()), "rb_expand_frame_times")
+    return times
+
+
+# --------------------------------------------------------------------------------------- a3
+def fuse_max_cells(x: torch.Tensor, y: torch.Tensor, inten: torch.Tensor, x_min: float, y_min: float,
+                   resolution: float, nx: int, ny: int):
+    """Occupied cells of the max-pooling grid in y-major order: ``(ix, iy, max_intensity)``."""
+    ctx = context(x.device.index)
+    n = x.numel()
+    cap = min(n, nx * ny)
+    ix = torch.empty(max(cap, 1), dtype=torch.int32, device=x.device)
+    iy = torch.empty(max(cap, 1), dtype=torch.int32, device=x.device)
+    mx = torch.empty(max(cap, 1), dtype=torch.float32, device=x.device)
+    n_cells = C.c_int64(0)
+    check(ctx.lib.rb_fuse_max(ctx.handle, ptr(_dev(x, torch.float32, "x")), ptr(_dev(y, torch.float32, "y")),
+                              ptr(_dev(inten, torch.float32, "inten")), n, float(x_min), float(y_min),
+                              float(resolution), int(nx), int(ny), ptr(ix), ptr(iy), ptr(mx), cap,
+                              C.byref(n_cells), stream_ptr()), "rb_fuse_max")
+    k = n_cells.value
+    return ix[:k], iy[:k], mx[:k]
+
+
+# --------------------------------------------------------------------------------------- a4-a6
+def bounds(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """Device float32 ``[x_min, x_max, y_min, y_max]`` (no sync)."""
+    ctx = context(x.device.index)
+    out = torch.empty(4, dtype=torch.float32, device=x.device)
+    check(ctx.lib.rb_bounds(ctx.handle, ptr(_dev(x, torch.float32, "x")), ptr(_dev(y, torch.float32, "y")),
+                            x.numel(), ptr(out), stream_ptr()), "rb_bounds")
+    return out
+
+
+def land_accumulate(x, y, inten, x_edges: torch.Tensor, y_edges: torch.Tensor,
+                    count: Optional[torch.Tensor] = None, isum: Optional[torch.Tensor] = None):
+    """Accumulate per-cell point counts (int32) and intensity sums (float64) — T4:378-389."""
+    ctx = context(x.device.index)
+    x_edges = _dev(x_edges, torch.float64, "x_edges")
+    y_edges = _dev(y_edges, torch.float64, "y_edges")
+    nx, ny = x_edges.numel() - 1, y_edges.numel() - 1
+    if count is None:
+        count = torch.zeros((nx, ny), dtype=torch.int32, device=x.device)
+        isum = torch.zeros((nx, ny), dtype=torch.float64, device=x.device)
+    check(ctx.lib.rb_land_accumulate(ctx.handle, ptr(_dev(x, torch.float32, "x")), ptr(_dev(y, torch.float32, "y")),
+                                     ptr(_dev(inten, torch.float32, "inten")), x.numel(), ptr(x_edges), nx + 1,
+                                     ptr(y_edges), ny + 1, ptr(count), ptr(isum), stream_ptr()), "rb_land_accumulate")
+    return count, isum
+
+
+def land_cells(count: torch.Tensor, isum: torch.Tensor, num_frames: int, persistence: float,
+               min_intensity: float) -> torch.Tensor:
+    ctx = context(count.device.index)
+    land = torch.empty(count.shape, dtype=torch.uint8, device=count.device)
+    check(ctx.lib.rb_land_cells(ctx.handle, ptr(_dev(count, torch.int32, "count")),
+                                ptr(_dev(isum, torch.float64, "isum")), count.numel(), int(num_frames),
+                                float(persistence), float(min_intensity), ptr(land), stream_ptr()), "rb_land_cells")
+    return land
+
+
+def land_filter(batch: PointBatch, x_edges: torch.Tensor, y_edges: torch.Tensor, land: torch.Tensor,
+                want_mask: bool = False, sync: bool = True):
+    """Order-preserving removal of land points for all frames at once — T4:413-436.
+    Returns a new :class:`PointBatch` (and the uint8 keep mask if asked)."""
+    ctx = context(batch.x.device.index)
+    n = batch.n
+    dev = batch.x.device
+    F = batch.frame_off.numel() - 1
+    xo = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+    yo = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+    io = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+    go = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    fo = torch.empty(F + 1, dtype=torch.int64, device=dev)
+    mask = torch.empty(max(n, 1), dtype=torch.uint8, device=dev) if want_mask else None
+    x_edges = _dev(x_edges, torch.float64, "x_edges")
+    y_edges = _dev(y_edges, torch.float64, "y_edges")
+    land = _dev(land, torch.uint8, "land")
+    check(ctx.lib.rb_land_filter(ctx.handle, ptr(batch.x), ptr(batch.y), ptr(batch.inten), ptr(batch.gain), n,
+                                 ptr(batch.frame_off), F, ptr(x_edges), x_edges.numel(), ptr(y_edges),
+                                 y_edges.numel(), ptr(land), ptr(xo), ptr(yo), ptr(io), ptr(go), ptr(fo),
+                                 ptr(mask), stream_ptr()), "rb_land_filter")
+    n_out = int(fo[-1].item()) if sync else -1
+    out = PointBatch(xo, yo, io, go, fo, n_out)
+    return (out, mask[:n]) if want_mask else out
+
+
+# --------------------------------------------------------------------------------------- a7
+def stdbscan(x: torch.Tensor, y: Optional[torch.Tensor], z: Optional[torch.Tensor], times: torch.Tensor,
+             eps_space: float, eps_time: float, min_samples: int, stride: int = 1, n: Optional[int] = None,
+             want_core: bool = False):
+    """ST-DBSCAN labels (int32, the reference's own numbering). ``x/y/z`` may be SoA tensors
+    (stride 1) or views into one row-major ``[N,D]`` tensor (stride D)."""
+    ctx = context(x.device.index)
+    if n is None:
+        n = times.numel()
+    dev = x.device
+    labels = torch.empty(max(n, 1), dtype=torch.int32, device=dev)[:n]
+    core = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)[:n] if want_core else None
+    ncl = C.c_int64(0)
+    for name, t in (("x", x), ("y", y), ("z", z), ("times", times)):
+        if t is not None and (not t.is_cuda or t.dtype != torch.float32):
+            raise RadarB200Error(f"{name} must be a float32 CUDA tensor")
+    check(ctx.lib.rb_stdbscan(ctx.handle, ptr(x), ptr(y), ptr(z), int(stride), ptr(times), int(n),
+                              float(eps_space), float(np.float32(eps_time)), int(min_samples), ptr(labels), ptr(core),
+                              C.byref(ncl), stream_ptr()), "rb_stdbscan")
+    if want_core:
+        return labels, core, ncl.value
+    return labels, ncl.value
+
+
+def stdbscan_stats(device: Optional[int] = None) -> dict:
+    ctx = context(device)
+    st = _lib.DbscanStats()
+    check(ctx.lib.rb_stdbscan_last_stats(ctx.handle, C.byref(st)), "rb_stdbscan_last_stats")
+    d = {k: getattr(st, k) for k, _ in st._fields_ if k != "dims"}
+    d["dims"] = list(st.dims)
+    return d
+
+
+# --------------------------------------------------------------------------------------- synthetic input
+def synth_echo(spec, first_frame: int = 0, n_frames: Optional[int] = None, device=None,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Device twin of :func:`synthetic.synth_echo` for frames ``first_frame .. first_frame+n_frames-1``
+    of the data set described by ``spec``: ``[F, G, S, E]`` float32 on the device."""
+    from . import synthetic as syn
+
+    if n_frames is None:
+        n_frames = spec.frames - first_frame
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    ctx = context(device.index)
+    G = len(spec.gains)
+    W = n_frames * G
+    keys = np.array([spec.sweep_key(first_frame + w // G, w % G) for w in range(W)], dtype=np.uint32)
+    thr = np.array([spec.clutter_threshold(spec.gains[w % G]) for w in range(W)], dtype=np.uint32)
+    rects, offs = syn.rects_to_array(spec, syn.build_rects(spec))
+    if len(rects) == 0:
+        rects = np.zeros((1, syn.RECT_COLS), dtype=np.int32)
+    d_keys = torch.from_numpy(keys.view(np.int32)).to(device)
+    d_thr = torch.from_numpy(thr.view(np.int32)).to(device)
+    d_rects = torch.from_numpy(rects).to(device)
+    d_offs = torch.from_numpy(offs).to(device)
+    if out is None:
+        out = torch.empty((n_frames, G, spec.spokes, spec.bins), dtype=torch.float32, device=device)
+    check(ctx.lib.rb_synth_echo(ctx.handle, ptr(out), W, spec.spokes, spec.bins, G, first_frame, ptr(d_keys),
+                                ptr(d_thr), ptr(d_rects), ptr(d_offs), stream_ptr()), "rb_synth_echo")
+    return out

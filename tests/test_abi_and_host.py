@@ -1,0 +1,116 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares, the host
+logic (tables, edges, config plumbing) matches the oracle, and the product path refuses to run
+without a GPU instead of falling back to anything."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import numpy_oracle as O
+from radar_point_cloud_tracking_b200 import _lib, synthetic as syn
+from radar_point_cloud_tracking_b200 import tracker as trk
+
+REPO = Path(__file__).resolve().parent.parent
+
+
+def header_symbols():
+    text = (REPO / "include" / "radarb200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = header_symbols()
+    assert len(names) >= 18
+    assert sorted(_lib.SIGNATURES) == names            # the binding covers the header, nothing more
+    raw = ctypes.CDLL(str(_lib.LIB_PATH))
+    for n in names:
+        assert getattr(raw, n) is not None
+    assert lib.rb_version() == 1
+
+
+def test_library_is_sm100a_only():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_gpu_is_a_hard_error():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from radar_point_cloud_tracking_b200.clustering import st_dbscan
+    from radar_point_cloud_tracking_b200.pipeline import DetectionPipeline
+    with pytest.raises(_lib.RadarB200Error):
+        st_dbscan(np.zeros((4, 2), np.float32), np.zeros(4, np.float32), 1.0, 1.0, 2)
+    with pytest.raises(_lib.RadarB200Error):
+        DetectionPipeline()
+    with pytest.raises(_lib.RadarB200Error):
+        _lib.context()
+    h = ctypes.c_void_p()
+    assert _lib.load().rb_create(0, ctypes.byref(h)) != 0 and b"no CUDA device" in _lib.load().rb_last_error()
+
+
+def test_product_package_never_imports_the_oracle():
+    for py in (REPO / "radar_point_cloud_tracking_b200").glob("*.py"):
+        src = py.read_text()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), py
+        assert "sklearn" not in src and "BallTree" not in src, py
+
+
+def test_sweep_tables_match_reference_expressions():
+    spec = syn.SweepSpec(spokes=2048, bins=1024)
+    c, s, r = trk.sweep_tables(spec.angle_units(), spec.scale(), spec.bins)
+    oc, os_, or_ = O.spoke_tables(spec.angle_units(), spec.scale(), spec.bins)
+    assert c.dtype == np.float32 and np.array_equal(c, oc) and np.array_equal(s, os_) and np.array_equal(r, or_)
+    # [W, S] batches give the same rows
+    a2 = np.stack([spec.angle_units(), spec.angle_units()[::-1]])
+    c2, s2, r2 = trk.sweep_tables(a2, np.stack([spec.scale(), spec.scale() * 2]), 1000)
+    assert np.array_equal(c2[0], c) and np.array_equal(s2[1], s[::-1])
+    assert np.array_equal(r2[1], (spec.scale() * 2 / 1000).astype(np.float32))
+
+
+def test_grid_edges_match_numpy_arange_of_float32_bounds():
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        lo, hi = np.sort(rng.normal(0, 300, 2)).astype(np.float32)
+        xe, ye = trk.grid_edges_from_bounds(np.array([lo, hi, lo, hi], np.float32), 5.0)
+        assert xe.dtype == np.float64 and np.array_equal(xe, O.grid_edges(lo, hi, 5.0)) and np.array_equal(xe, ye)
+
+
+def test_parse_timestamp_and_csv_reader(tmp_path):
+    dt, ms = trk.parse_timestamp("20250813_142602_181.csv")
+    assert (dt.year, dt.second, ms % 1000) == (2025, 2, 181)
+    with pytest.raises(ValueError):
+        trk.parse_timestamp("nope.csv")
+    spec = syn.SweepSpec(seed=1, frames=1, spokes=4, bins=1024, gains=(75,))
+    files = syn.write_csv_tree(spec, tmp_path)
+    angle, scale, echo, gain = trk.read_sweep_csv(files[0][75])
+    assert gain == 75 and echo.shape == (4, 1024) and echo.dtype == np.float32
+    assert np.array_equal(echo, syn.synth_echo(spec)[0, 0]) and np.array_equal(angle, spec.angle_units())
+    assert trk.read_sweep_csv(tmp_path / "missing.csv") is None
+
+
+def test_install_reads_reference_globals_at_call_time():
+    from types import SimpleNamespace
+    ref = SimpleNamespace(RadarFrame=trk.RadarFrame, Cluster=trk.Cluster, NUM_ECHO_COLUMNS=1024,
+                          INTENSITY_THRESHOLD=10.0, POINT_STRIDE=4, LAND_PERSISTENCE_THRESHOLD=0.8,
+                          LAND_GRID_RESOLUTION=5.0, LAND_MIN_INTENSITY=100)
+    trk.install(ref)
+    for name in ("load_radar_csv", "build_frame", "build_occupancy_grid", "identify_land_cells",
+                 "filter_land_from_frame", "st_dbscan"):
+        assert callable(getattr(ref, name))
+    ref.INTENSITY_THRESHOLD = 2.0
+    assert trk._module_config(ref).INTENSITY_THRESHOLD == 2.0
+    assert ref.st_dbscan([], 8.0, 2.0, 15) == {}
+
+
+def test_synthetic_generator_is_deterministic():
+    spec = syn.SweepSpec(seed=3, frames=2, spokes=16, bins=64)
+    a, b = syn.synth_echo(spec), syn.synth_echo(spec)
+    assert np.array_equal(a, b) and a.dtype == np.float32 and a.min() >= 0 and a.max() <= 255
+    assert np.array_equal(a, np.rint(a))

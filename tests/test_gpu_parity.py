@@ -1,0 +1,335 @@
+"""Parity of the CUDA path (through the C ABI) with the reference: golden fixtures produced by the
+unmodified reference, and the CPU oracle on seeded inputs. Bit-exact everywhere (integer / index
+work and float32 chains without reassociation); no tolerance is used in this file."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle import numpy_oracle as O
+from oracle.c_oracle import st_dbscan_c
+from radar_point_cloud_tracking_b200 import synthetic as syn
+from tests.common import (CLUSTER3D_SPEC, DBSCAN_CASES, PIPE_SPEC, SWEEP_CASES, SWEEP_SPEC, digest, golden,
+                          pipe_inputs)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device (no CPU fallback exists)")
+    torch.cuda.set_device(0)
+    from radar_point_cloud_tracking_b200 import device as dev
+    return dev
+
+
+def _tables(dev, spec, n_sweeps, d):
+    from radar_point_cloud_tracking_b200.tracker import sweep_tables
+    c, s, r = sweep_tables(spec.angle_units(), spec.scale(), spec.bins)
+    rep = lambda t: torch.from_numpy(np.ascontiguousarray(np.broadcast_to(t, (n_sweeps, len(t))))).to(d)
+    return rep(c), rep(s), rep(r)
+
+
+def _run_sweeps(dev, echo_np, spec, thr, stride, gains=None, gpf=1, cap=None):
+    d = torch.device("cuda:0")
+    W = echo_np.shape[0]
+    c, s, r = _tables(dev, spec, W, d)
+    g = torch.tensor(gains if gains is not None else [0] * W, dtype=torch.int32, device=d)
+    return dev.spoke_to_points(torch.from_numpy(echo_np).to(d), c, s, r, g, thr, stride, gains_per_frame=gpf, cap=cap)
+
+
+# ------------------------------------------------------------------------------- synthetic twin
+def test_device_generator_matches_numpy(gpu):
+    spec = syn.SweepSpec(seed=9, frames=3, spokes=40, bins=256, clutter_p=0.02, land_blobs=2, buoys=3, boats=2)
+    assert np.array_equal(gpu.synth_echo(spec).cpu().numpy(), syn.synth_echo(spec))
+    part = gpu.synth_echo(spec, first_frame=1, n_frames=2).cpu().numpy()
+    assert np.array_equal(part, syn.synth_echo(spec)[1:])
+
+
+# ------------------------------------------------------------------------------- a1: spoke-to-point
+@pytest.mark.parametrize("tag,thr,stride", SWEEP_CASES)
+def test_spoke_to_points_vs_reference_golden(gpu, tag, thr, stride):
+    g = golden("sweeps")
+    spec = syn.SweepSpec(**SWEEP_SPEC)
+    echo = syn.synth_sweep(spec, 0, 2)[None]
+    b = _run_sweeps(gpu, echo, spec, thr, stride)
+    assert b.n == int(g[f"{tag}_n"])
+    x, y, z = (t[:b.n].cpu().numpy() for t in (b.x, b.y, b.inten))
+    assert digest(x) + digest(y) + digest(z) == str(g[f"{tag}_digest"])
+
+
+@pytest.mark.parametrize("S,E,stride,thr", [(7, 100, 3, 4.0), (33, 130, 1, 8.0), (5, 1023, 5, 2.0), (1, 1, 1, -1.0),
+                                            (64, 1024, 7, 9.0), (3, 4096, 2, 0.0)])
+def test_spoke_to_points_ragged_shapes(gpu, S, E, stride, thr):
+    """Sweeps that do not fill tiles / are not multiples of the vector width; several sweeps per
+    launch so stride phases restart at each sweep and output offsets chain across sweeps."""
+    spec = syn.SweepSpec(seed=3, frames=2, spokes=S, bins=E, clutter_p=0.05, land_blobs=1, buoys=1, boats=1)
+    echo = syn.synth_echo(spec).reshape(-1, S, E)
+    b = _run_sweeps(gpu, echo, spec, thr, stride, gains=[40, 50, 75] * 2, gpf=3)
+    off = b.frame_off.cpu().numpy()
+    want = [O.sweep_to_points(echo[w], spec.angle_units(), spec.scale(), thr, stride) for w in range(6)]
+    wx = np.concatenate([w[0] for w in want])
+    assert b.n == len(wx)
+    assert np.array_equal(b.x[:b.n].cpu().numpy(), wx)
+    assert np.array_equal(b.y[:b.n].cpu().numpy(), np.concatenate([w[1] for w in want]))
+    assert np.array_equal(b.inten[:b.n].cpu().numpy(), np.concatenate([w[2] for w in want]))
+    assert np.array_equal(b.gain[:b.n].cpu().numpy(),
+                          np.concatenate([np.full(len(w[0]), [40, 50, 75][i % 3], np.int32) for i, w in enumerate(want)]))
+    assert list(off) == [0, sum(len(w[0]) for w in want[:3]), len(wx)]
+
+
+def test_spoke_to_points_empty_and_capacity(gpu):
+    spec = syn.SweepSpec(**SWEEP_SPEC)
+    echo = syn.synth_sweep(spec, 0, 0)[None]
+    b = _run_sweeps(gpu, echo, spec, 300.0, 4)            # nothing above the threshold
+    assert b.n == 0 and list(b.frame_off.cpu().numpy()) == [0, 0]
+    want = O.sweep_to_points(echo[0], spec.angle_units(), spec.scale(), 2.0, 2)
+    b = _run_sweeps(gpu, echo, spec, 2.0, 2, cap=1000)    # capacity guess too small -> re-run, same answer
+    assert b.n == len(want[0]) and np.array_equal(b.x[:b.n].cpu().numpy(), want[0])
+    z = torch.zeros((0, 4, 8), dtype=torch.float32, device="cuda:0")
+    e = torch.zeros((0, 4), dtype=torch.float32, device="cuda:0")
+    b = gpu.spoke_to_points(z, e, e, e, torch.zeros(0, dtype=torch.int32, device="cuda:0"), 1.0, 1)
+    assert b.n == 0
+
+
+def test_full_size_frame_bit_exact(gpu):
+    """One full 2048 x 1024 x 3-gain frame (BASELINE shape) against the numpy oracle."""
+    spec = syn.SweepSpec(seed=123, frames=1)
+    echo = gpu.synth_echo(spec)
+    host = echo.cpu().numpy()
+    d = echo.device
+    c, s, r = _tables(gpu, spec, 3, d)
+    for thr, stride in ((10.0, 4), (2.0, 2)):
+        b = gpu.spoke_to_points(echo.view(3, spec.spokes, spec.bins), c, s, r,
+                                torch.tensor([40, 50, 75], dtype=torch.int32, device=d), thr, stride, gains_per_frame=3)
+        per_gain = {g: O.sweep_to_points(host[0, gi], spec.angle_units(), spec.scale(), thr, stride)
+                    for gi, g in enumerate(spec.gains)}
+        pts, gains = O.fuse_concat(per_gain)
+        assert b.n == len(pts)
+        got = torch.stack([b.x[:b.n], b.y[:b.n], b.inten[:b.n]], 1).cpu().numpy()
+        assert np.array_equal(got, pts) and np.array_equal(b.gain[:b.n].cpu().numpy(), gains)
+
+
+def test_batch_properties_at_scale(gpu):
+    """Size-independent properties on a 24-sweep batch: per-sweep counts = ceil(M/stride), offsets
+    monotone, intensities above threshold, idempotent re-run."""
+    spec = syn.SweepSpec(seed=5, frames=8)
+    echo = gpu.synth_echo(spec)
+    d = echo.device
+    W = 24
+    c, s, r = _tables(gpu, spec, W, d)
+    gains = torch.tensor([40, 50, 75] * 8, dtype=torch.int32, device=d)
+    flat = echo.view(W, spec.spokes, spec.bins)
+    out1 = gpu.spoke_to_points_raw(flat, c, s, r, gains, 10.0, 4, 3_000_000)
+    out2 = gpu.spoke_to_points_raw(flat, c, s, r, gains, 10.0, 4, 3_000_000)
+    base = out1[4].cpu().numpy()
+    m = (flat > 10.0).sum(dim=(1, 2)).cpu().numpy()
+    assert np.array_equal(np.diff(base), (m + 3) // 4)
+    n = int(base[-1])
+    for a, b in zip(out1[:4], out2[:4]):
+        assert torch.equal(a[:n], b[:n])
+    assert bool((out1[2][:n] > 10.0).all())
+
+
+# ------------------------------------------------------------------------------- T4 mirror on CSV files
+def test_tracker_functions_on_csv_tree_vs_golden(gpu, tmp_path):
+    from radar_point_cloud_tracking_b200 import tracker as trk
+    g = golden("pipeline_small")
+    spec, echo = pipe_inputs()
+    files = syn.write_csv_tree(spec, tmp_path, echo)
+    x, y, z, gain = trk.load_radar_csv(files[0][50])
+    o = g["frame_offsets"]
+    frames = [trk.build_frame(ff, i) for i, ff in enumerate(files)]
+    assert gain == 50 and all(f is not None for f in frames)
+    assert np.array_equal(np.cumsum([0] + [f.num_points for f in frames]), o)
+    assert np.array_equal(np.concatenate([f.points for f in frames]), g["points"])
+    assert np.array_equal(np.concatenate([f.gains for f in frames]), g["gains"])
+    assert frames[0].points.dtype == np.float32 and frames[0].gains.dtype == np.int32
+    n40 = int((frames[0].gains == 40).sum())
+    assert np.array_equal(x, frames[0].points[n40:n40 + len(x), 0])
+
+    count, isum, (xe, ye) = trk.build_occupancy_grid(frames, trk.LAND_GRID_RESOLUTION)
+    assert np.array_equal(xe, g["x_edges"]) and np.array_equal(ye, g["y_edges"])
+    assert np.array_equal(count, g["count"]) and count.dtype == np.int32
+    assert np.array_equal(isum, g["isum"]) and isum.dtype == np.float64
+    land = trk.identify_land_cells(count, isum, len(frames))
+    assert land.dtype == bool and np.array_equal(land, g["land"])
+    filt = [trk.filter_land_from_frame(f, land, (xe, ye)) for f in frames]
+    assert np.array_equal(np.cumsum([0] + [f.num_points for f in filt]), g["filt_offsets"])
+    assert np.array_equal(np.concatenate([f.points for f in filt]), g["filt_points"])
+    assert np.array_equal(np.concatenate([f.gains for f in filt]), g["filt_gains"])
+
+    for tag, eps_s, eps_t, ms in DBSCAN_CASES:
+        clusters = trk.st_dbscan(filt, eps_s, eps_t, ms)
+        rec = sorted((fid, c.cluster_id, c.num_points, c.centroid[0], c.centroid[1], c.mean_intensity)
+                     for fid, cl in clusters.items() for c in cl)
+        assert np.array_equal(np.array(rec, dtype=np.float64).reshape(-1, 6), g[f"clusters_{tag}"])
+    # error behaviour of the reference: unreadable file -> empty arrays and gain 0; empty frame -> None
+    bad = tmp_path / "gain_40" / "20250101_000000_000.csv"
+    bad.write_text("")
+    x, y, z, gain = trk.load_radar_csv(bad)
+    assert len(x) == 0 and gain == 0
+    assert trk.build_frame({40: bad}, 0) is None
+    assert trk.st_dbscan([], 8.0, 2.0, 15) == {}
+
+
+# ------------------------------------------------------------------------------- device pipeline
+def test_device_pipeline_vs_golden(gpu):
+    from radar_point_cloud_tracking_b200.pipeline import DetectionConfig, DetectionPipeline
+    g = golden("pipeline_small")
+    spec, echo = pipe_inputs()
+    pipe = DetectionPipeline(DetectionConfig())
+    out = pipe.run_host(echo, spec.angle_units(), spec.scale())
+    assert np.array_equal(out["points"], g["filt_points"]) and np.array_equal(out["gains"], g["filt_gains"])
+    assert np.array_equal(out["frame_off"], g["filt_offsets"])
+    # device generator + device path gives the same thing
+    d_echo = gpu.synth_echo(spec)
+    c, s, r = pipe.spoke_tables(spec.angle_units(), spec.scale(), spec.frames, spec.bins)
+    res = pipe.run_device(d_echo, *(torch.from_numpy(t).cuda() for t in (c, s, r)))
+    assert np.array_equal(res.land.cpu().numpy().astype(bool), g["land"])
+    assert np.array_equal(res.count.cpu().numpy(), g["count"]) and np.array_equal(res.isum.cpu().numpy(), g["isum"])
+    raw = res.raw
+    assert np.array_equal(torch.stack([raw.x[:raw.n], raw.y[:raw.n], raw.inten[:raw.n]], 1).cpu().numpy(), g["points"])
+    rec = sorted((fid, c.cluster_id, c.num_points, c.centroid[0], c.centroid[1], c.mean_intensity)
+                 for fid, cl in res.clusters_by_frame().items() for c in cl)
+    rec = np.array(rec, dtype=np.float64).reshape(-1, 6)
+    assert np.array_equal(rec, g["clusters_default"])
+    csv = g["clusters_csv"]
+    csv = csv[np.lexsort((csv[:, 1], csv[:, 0]))]
+    assert np.array_equal(csv.astype(np.float32), rec.astype(np.float32))     # the real CLI's clusters.csv
+
+
+# ------------------------------------------------------------------------------- a7: ST-DBSCAN
+def test_stdbscan_random_cases_vs_reference_golden(gpu):
+    from radar_point_cloud_tracking_b200.clustering import st_dbscan
+    g = golden("stdbscan_random")
+    for k in range(24):
+        eps_s, eps_t, ms = g[f"c{k}_params"]
+        got = st_dbscan(g[f"c{k}_coords"], g[f"c{k}_times"], float(eps_s), float(eps_t), int(ms))
+        assert got.dtype == np.int32 and np.array_equal(got, g[f"c{k}_labels"]), k
+
+
+def test_stdbscan_package_3d_case_vs_golden(gpu):
+    from radar_point_cloud_tracking_b200.clustering import st_dbscan
+    g = golden("package")
+    spec3 = syn.SweepSpec(**CLUSTER3D_SPEC)
+    pts, tms = [], []
+    for gi in range(3):
+        x, y, z = O.sweep_to_points(syn.synth_sweep(spec3, 0, gi), spec3.angle_units(), spec3.scale(), 10.0, 2)
+        pts.append(np.column_stack((x, y, z)))
+        tms.append(np.full(len(x), gi, dtype=np.float32))
+    assert np.array_equal(st_dbscan(np.concatenate(pts), np.concatenate(tms), 5.0, 1.0, 10), g["cluster3d_labels"])
+
+
+def test_stdbscan_known_answers(gpu):
+    """radar-pipeline-rs/src/processors/clustering.rs:502-597 + edge cases."""
+    from radar_point_cloud_tracking_b200.clustering import st_dbscan
+    sq = [[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0]]
+    coords = np.array(sq + [[100 + a, 100 + b, 0] for a, b, _ in sq], dtype=np.float32)
+    lab = st_dbscan(coords, np.zeros(8, np.float32), 5.0, 1.0, 2)
+    assert list(lab) == [0, 0, 0, 0, 1, 1, 1, 1]
+    lab = st_dbscan(np.array(sq, np.float32), np.array([0, 0, 5, 5], np.float32), 5.0, 1.0, 2)
+    assert list(lab) == [0, 0, 1, 1]
+    lab = st_dbscan(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [100, 100, 100]], np.float32), np.zeros(4, np.float32), 5.0, 1.0, 3)
+    assert list(lab) == [0, 0, 0, -1]
+    assert len(st_dbscan(np.zeros((0, 3), np.float32), np.zeros(0, np.float32), 5.0, 1.0, 3)) == 0
+    assert list(st_dbscan(np.zeros((1, 3), np.float32), np.zeros(1, np.float32), 5.0, 1.0, 2)) == [-1]
+    # duplicates, eps 0, min_samples 1, exact-distance inclusivity (3-4-5 triangle: d == eps)
+    dup = np.array([[1, 1], [1, 1], [1, 1], [2, 2]], np.float32)
+    assert list(st_dbscan(dup, np.zeros(4, np.float32), 0.0, 0.0, 3)) == [0, 0, 0, -1]
+    assert list(st_dbscan(dup, np.zeros(4, np.float32), 0.0, 0.0, 1)) == [0, 0, 0, 1]
+    tri = np.array([[0, 0], [3, 4]], np.float32)
+    assert list(st_dbscan(tri, np.zeros(2, np.float32), 5.0, 0.0, 2)) == [0, 0]
+    assert list(st_dbscan(tri, np.zeros(2, np.float32), 4.999999, 0.0, 2)) == [-1, -1]
+    with pytest.raises(Exception):
+        st_dbscan(np.array([[0.1, 0.2]], np.float64), np.zeros(1, np.float32), 1.0, 1.0, 1)
+
+
+@pytest.mark.parametrize("n,frames,eps_s,eps_t,ms,dim", [(60000, 40, 8.0, 2.0, 15, 2), (40000, 3, 5.0, 1.0, 10, 3),
+                                                          (30000, 200, 3.0, 0.5, 4, 2), (20000, 6, 6.0, 2.5, 8, 2)])
+def test_stdbscan_vs_c_oracle_medium(gpu, n, frames, eps_s, eps_t, ms, dim):
+    """Larger seeded problems against the C oracle: identical labels and core sets."""
+    rng = np.random.default_rng(n + frames)
+    span = 400.0
+    coords = (rng.random((n, dim)) * span).astype(np.float32)
+    k = n // 2
+    centres = (rng.random((40, dim)) * span).astype(np.float32)
+    coords[:k] = (centres[rng.integers(0, 40, k)] + rng.normal(0, 3.0, (k, dim))).astype(np.float32)
+    if eps_t != int(eps_t):
+        times = (rng.random(n) * frames).astype(np.float32)
+    else:
+        times = rng.integers(0, frames, n).astype(np.float32)
+    want, want_core = st_dbscan_c(coords, times, eps_s, eps_t, ms)
+    d = torch.device("cuda:0")
+    flat = torch.from_numpy(coords).to(d).view(-1)
+    lab, core, ncl = gpu.stdbscan(flat, flat[1:], flat[2:] if dim == 3 else None, torch.from_numpy(times).to(d),
+                                  eps_s, eps_t, ms, stride=dim, n=n, want_core=True)
+    assert np.array_equal(core.cpu().numpy().astype(bool), want_core)
+    assert np.array_equal(lab.cpu().numpy(), want)
+    assert ncl == want.max() + 1
+    st = gpu.stdbscan_stats()
+    assert st["n_points"] == n and st["pair_tests_count"] > 0
+
+
+def test_stdbscan_sparse_frame_ids_and_coarsening(gpu):
+    """Frame ids with huge gaps and a tiny eps over a wide extent force the grid to coarsen."""
+    from radar_point_cloud_tracking_b200.clustering import st_dbscan
+    rng = np.random.default_rng(1)
+    coords = (rng.random((5000, 2)) * 20000).astype(np.float32)
+    coords[:2500] = (coords[rng.integers(2500, 5000, 2500)] + rng.normal(0, 0.05, (2500, 2))).astype(np.float32)
+    times = rng.choice(np.array([0, 1, 2, 1000000, 1000001, 5000000], np.float32), 5000)
+    want, _ = st_dbscan_c(coords, times, 0.2, 1.0, 3)
+    assert np.array_equal(st_dbscan(coords, times, 0.2, 1.0, 3), want)
+
+
+# ------------------------------------------------------------------------------- a3 + package transforms
+def test_fuse_max_vs_reference_golden(gpu):
+    from radar_point_cloud_tracking_b200.fusion import fuse_points_absolute, fuse_points_max
+    g = golden("fuse_max")
+    spec, echo = pipe_inputs()
+    b = _run_sweeps(gpu, echo[0], spec, 5.0, 8, gains=[40, 50, 75], gpf=1)
+    off = b.frame_off.cpu().numpy()
+    x, y, z = (t[:b.n].cpu().numpy() for t in (b.x, b.y, b.inten))
+    per_gain = {gain: (x[off[i]:off[i + 1]], y[off[i]:off[i + 1]], z[off[i]:off[i + 1]]) for i, gain in enumerate(spec.gains)}
+    for tag, res in (("r1", 1.0), ("r2p5", 2.5)):
+        ox, oy, oi = fuse_points_max(per_gain, res)
+        assert ox.dtype == g[f"{tag}_x"].dtype
+        assert np.array_equal(ox, g[f"{tag}_x"]) and np.array_equal(oy, g[f"{tag}_y"]) and np.array_equal(oi, g[f"{tag}_i"])
+    ax, ay, ai, ag = fuse_points_absolute(per_gain)
+    assert digest(ax) + digest(ay) + digest(ai) + digest(ag) == str(g["abs_digest"])
+
+
+def test_package_transforms_vs_golden(gpu):
+    from types import SimpleNamespace
+    from radar_point_cloud_tracking_b200.transforms import polar_to_cartesian, sweep_to_point_cloud
+    g = golden("package")
+    spec = syn.SweepSpec(**SWEEP_SPEC)
+    angles = np.deg2rad(spec.angle_units().astype(np.float32) * (360.0 / 8196.0))
+    ranges = (spec.scale()[:, None] / spec.bins) * np.arange(spec.bins, dtype=np.float32)
+    x, y = polar_to_cartesian(angles, ranges)
+    assert digest(x) + digest(y) == str(g["p2c_digest"])
+    # known answers of radar-pipeline/tests/test_transforms.py:15-40 (atol 1e-6 in the reference)
+    a = np.array([0, np.pi / 2, np.pi], dtype=np.float32)
+    x, y = polar_to_cartesian(a, np.ones((3, 1), np.float32))
+    np.testing.assert_allclose(x[:, 0], [1, 0, -1], atol=1e-6)
+    np.testing.assert_allclose(y[:, 0], [0, 1, 0], atol=1e-6)
+    sweep = SimpleNamespace(angles_rad=angles, ranges=ranges, intensities=syn.synth_sweep(spec, 0, 1),
+                            scale=spec.scale(), gain=50)
+    for tag, thr, stride in (("default", 0.0, 16), ("t10_s4", 10.0, 4)):
+        pc = sweep_to_point_cloud(sweep, SimpleNamespace(intensity_threshold=thr, point_stride=stride))
+        assert pc.size == int(g[f"s2pc_{tag}_n"])
+        assert digest(pc.x) + digest(pc.y) + digest(pc.z) == str(g[f"s2pc_{tag}_digest"])
+    assert sweep_to_point_cloud(sweep).size == int(g["s2pc_default_n"])
+
+
+def test_abi_error_paths(gpu):
+    from radar_point_cloud_tracking_b200 import _lib
+    ctx = _lib.context(0)
+    rc = ctx.lib.rb_bounds(ctx.handle, None, None, 0, None, None)
+    assert rc == -2 and b"NULL" in ctx.lib.rb_last_error()
+    n = C.c_int64(7)
+    assert ctx.lib.rb_stdbscan(ctx.handle, None, None, None, 1, None, 0, 1.0, 1.0, 1, None, None, C.byref(n), None) == 0
+    assert n.value == 0 and ctx.launch_count() > 0
