@@ -171,6 +171,13 @@ int rb_synth_echo(rb_ctx* ctx, float* echo, int64_t n_sweeps, int n_spokes, int 
                   const uint32_t* sweep_keys, const uint32_t* clutter_thr,
                   const int32_t* rects, const int32_t* rect_off, void* stream);
 
+/* Diagnostic switches. "spoke_profile" = 1: rb_spoke_to_points records CUDA events (on the launch stream)
+ * around each of its three kernels; read them back with rb_get_info. */
+int rb_set_option(rb_ctx* ctx, const char* name, int64_t value);
+/* "launches"; "spoke_mask_ns" / "spoke_offsets_ns" / "spoke_emit_ns" = device time of the kernels of the
+ * last profiled rb_spoke_to_points (syncs on its last event); -1 for unknown names or nothing recorded. */
+int64_t rb_get_info(rb_ctx* ctx, const char* name);
+
 /* Number of kernels this library has launched on this ctx since creation (bench "gpu_launches"). */
 int64_t rb_launch_count(rb_ctx* ctx);
 

@@ -46,6 +46,8 @@ SIGNATURES = {
                             c_vp, c_vp, C.POINTER(c_i64), c_vp]),
     "rb_stdbscan_last_stats": (c_i32, [c_vp, C.POINTER(DbscanStats)]),
     "rb_synth_echo": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "rb_set_option": (c_i32, [c_vp, C.c_char_p, c_i64]),
+    "rb_get_info": (c_i64, [c_vp, C.c_char_p]),
     "rb_launch_count": (c_i64, [c_vp]),
 }
 
@@ -95,6 +97,12 @@ class Context:
         sm, maj, mnr, l2 = c_i32(), c_i32(), c_i32(), c_i64()
         check(lib.rb_device_info(h, C.byref(sm), C.byref(maj), C.byref(mnr), C.byref(l2)), "rb_device_info")
         self.sm_count, self.cc, self.l2_bytes = sm.value, (maj.value, mnr.value), l2.value
+
+    def set_option(self, name: str, value: int) -> None:
+        check(self.lib.rb_set_option(self.handle, name.encode(), int(value)), f"rb_set_option({name})")
+
+    def info(self, name: str) -> int:
+        return int(self.lib.rb_get_info(self.handle, name.encode()))
 
     def launch_count(self) -> int:
         return int(self.lib.rb_launch_count(self.handle))

@@ -16,8 +16,9 @@ struct rb_scratch {
 
 // Named scratch slots; each grows on demand and is reused across calls.
 enum rb_slot {
-    RB_S_TILE_STATUS = 0,   // spoke: decoupled look-back tile descriptors
-    RB_S_SWEEP_FLAGS,       // spoke: per-sweep ready flags + ticket
+    RB_S_TILE_STATUS = 0,   // spoke: tile survivor counts, in-sweep tile prefixes, sweep totals
+    RB_S_SWEEP_FLAGS,       // spoke: self-cleaning counters (done, ticket)
+    RB_S_SPOKE_MASK,        // spoke: survivor bitmask, 1 bit per cell
     RB_S_REDUCE,            // bounds partials
     RB_S_KEEP,              // land filter keep flags
     RB_S_BLOCKSUM,          // scan block sums
@@ -49,6 +50,8 @@ struct rb_ctx {
     void* pinned = nullptr;          // small pinned staging buffer (host)
     size_t pinned_cap = 0;
     rb_dbscan_stats last_stats;
+    int opt_spoke_profile = 0;       // 1: record events around the three spoke-to-point kernels
+    cudaEvent_t spoke_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 void rb_set_error(const char* fmt, ...);

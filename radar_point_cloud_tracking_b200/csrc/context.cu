@@ -57,6 +57,8 @@ extern "C" void rb_destroy(rb_ctx* ctx) {
     for (int i = 0; i < RB_S_COUNT; ++i)
         if (ctx->slots[i].ptr) cudaFree(ctx->slots[i].ptr);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (int i = 0; i < 4; ++i)
+        if (ctx->spoke_ev[i]) cudaEventDestroy(ctx->spoke_ev[i]);
     delete ctx;
 }
 
@@ -67,6 +69,29 @@ extern "C" int rb_device_info(rb_ctx* ctx, int* sm_count, int* cc_major, int* cc
     if (cc_minor) *cc_minor = ctx->cc_minor;
     if (l2_bytes) *l2_bytes = ctx->l2_bytes;
     return RB_OK;
+}
+
+extern "C" int rb_set_option(rb_ctx* ctx, const char* name, int64_t value) {
+    RB_REQUIRE(ctx && name, "NULL argument");
+    if (!strcmp(name, "spoke_profile")) { ctx->opt_spoke_profile = value != 0; return RB_OK; }
+    rb_set_error("rb_set_option: unknown option '%s'", name);
+    return RB_ERR_ARG;
+}
+
+extern "C" int64_t rb_get_info(rb_ctx* ctx, const char* name) {
+    if (!ctx || !name) return -1;
+    if (!strcmp(name, "launches")) return ctx->launches;
+    if (!strcmp(name, "spoke_profile")) return ctx->opt_spoke_profile;
+    // device time of the last profiled rb_spoke_to_points, per kernel, in nanoseconds (syncs on its last event)
+    int k = !strcmp(name, "spoke_mask_ns") ? 0 : !strcmp(name, "spoke_offsets_ns") ? 1 : !strcmp(name, "spoke_emit_ns") ? 2 : -1;
+    if (k >= 0) {
+        if (!ctx->spoke_ev[3]) return -1;
+        if (cudaEventSynchronize(ctx->spoke_ev[3]) != cudaSuccess) return -1;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->spoke_ev[k], ctx->spoke_ev[k + 1]) != cudaSuccess) return -1;
+        return (int64_t)((double)ms * 1e6);
+    }
+    return -1;
 }
 
 extern "C" int64_t rb_launch_count(rb_ctx* ctx) { return ctx ? ctx->launches : -1; }

@@ -1,207 +1,332 @@
-// Spoke-to-point: threshold + ordered stream compaction + stride + polar->Cartesian + gain concat,
-// one pass over the echo tensor (HBM-bound: every echo byte is read exactly once).
+// Spoke-to-point: threshold + ordered stream compaction + stride + polar->Cartesian + gain concat.
 //
 // Replaces load_radar_csv's numeric part (reference 4_temporal_object_tracker.py:200-232) and the
 // per-gain concatenation of build_frame (:322-344) for a batch of W = frames x gains sweeps.
 //
-// Layout: echo[W][S][E] float32. A tile is SP_TILE consecutive cells of ONE sweep; a warp owns
-// SP_VEC consecutive 128-cell chunks, a lane 4 consecutive cells of each chunk (one 128-bit
-// load), so the row-major order of survivors falls out of warp ballots without any shuffle scan.
-// Tile prefixes come from a decoupled look-back over per-tile descriptors (tiles are handed out
-// by an atomic ticket, so a tile only ever waits on tiles that are already running); the output
-// base of a sweep (sum of ceil(M_w/stride) of all earlier sweeps) is chained through a second,
-// per-sweep descriptor published by each sweep's last tile.
+// Three launches, no inter-CTA waiting anywhere (a single-pass decoupled look-back was built and
+// measured first: its prefix latency of ~9 us per 64 KiB tile capped it at 1.4 TB/s, see
+// profiles/r01_spoke_v2_tma_lookback_trace.txt):
+//
+//   1. spoke_mask_kernel    streams echo[W][S][E] ONCE at HBM speed (128-bit loads, 8 in flight per
+//                           lane, tiles handed out by a warp-level ticket). Output: 1 bit per cell
+//                           (survivor mask, cell order) and one survivor count per 4096-cell tile.
+//                           This is the HBM-bound kernel: 4 B read + 1/8 B written per cell.
+//   2. spoke_offsets_kernel in-sweep exclusive prefix of the tile counts (one block per sweep) and,
+//                           by the last block to finish, the output base of every sweep:
+//                           base[w] = sum_{w'<w} ceil(M_w' / stride)   (x[mask][::stride], T4:222-230)
+//   3. spoke_emit_kernel    one warp per group of 4 tiles: popcount-scan of the mask words gives the
+//                           in-sweep rank at the start of every 128-cell entry; the KEPT ranks
+//                           (multiples of the stride) of the group are dealt to the lanes round-robin,
+//                           each lane finds its survivor by a binary search over the entry ranks and
+//                           a select-in-word, gathers the echo value, and writes x, y, intensity and
+//                           gain. Consecutive lanes write consecutive output slots (coalesced), and
+//                           the work is proportional to the points kept, not to the cells.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
 
-constexpr int SP_THREADS = 256;
-constexpr int SP_WARPS = SP_THREADS / 32;
-constexpr int SP_VEC = 4;                          // 128-bit loads per lane
-constexpr int SP_CHUNK = 128;                      // cells per warp load
-constexpr int SP_WARP_CELLS = SP_CHUNK * SP_VEC;   // 512
-constexpr int SP_TILE = SP_WARP_CELLS * SP_WARPS;  // 4096 cells = 16 KiB
+constexpr int SK_THREADS = 256;
+constexpr int SK_WARPS = SK_THREADS / 32;
+constexpr int SK_TILE = 4096;                       // cells per tile (16 KiB of echo), one warp per tile
+constexpr int SK_WORDS = SK_TILE / 32;              // 128 mask words per tile
+constexpr int SK_BATCH = 8;                         // 128-bit loads in flight per lane
+constexpr int SK_BATCH_CELLS = SK_BATCH * 128;      // 1024 cells per batch and warp
+constexpr int SK_BATCHES = SK_TILE / SK_BATCH_CELLS;
+constexpr int SK_GROUP = 4;                         // tiles per warp in the emit kernel
+constexpr int SK_ENTRIES = SK_GROUP * 32;           // 128-cell entries per group
+constexpr int SK_CTAS_PER_SM = 4;
 
-constexpr unsigned long long ST_INVALID = 0ull;
-constexpr unsigned long long ST_AGGREGATE = 1ull << 32;
-constexpr unsigned long long ST_INCLUSIVE = 2ull << 32;
+// unsigned division by a launch-invariant divisor (magic multiply), exact for all 32-bit n
+struct FastDiv { uint32_t mul, shift, d; };
+inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f; f.d = d; f.mul = 0; f.shift = 0;
+    if (d <= 1) return f;
+    uint32_t l = 0;
+    while ((1ull << l) < d) ++l;                                   // ceil(log2 d)
+    f.mul = (uint32_t)((((1ull << l) - d) << 32) / d + 1);
+    f.shift = l;
+    return f;
+}
+__device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv& f) {
+    if (f.d <= 1) return n;
+    uint32_t t = __umulhi(f.mul, n);
+    return (t + ((n - t) >> 1)) >> (f.shift - 1);
+}
 
-struct SpokeArgs {
+struct SpokeGeom {
+    int64_t total_tiles;
+    int sweep_cells;                     // S*E
+    int tiles_per_sweep;
+    int n_bins;
+    int n_spokes;
+};
+
+// ---- 1. mask + count ------------------------------------------------------------------------------
+// Lane l of a warp owns cells 4l..4l+3 of each 128-cell chunk (one LDG.128). The 4-bit survivor
+// nibbles of 8 chunks are OR-reduced across each group of 8 lanes with a transposing butterfly
+// (7 shuffles for 8 chunks): afterwards lane l holds the finished 32-bit word of chunk (l & 7),
+// lane group (l >> 3), i.e. word (l & 7) * 4 + (l >> 3) of the batch - one 128-byte store per batch.
+template <bool VEC>
+__global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM)
+spoke_mask_kernel(const float* __restrict__ echo, const SpokeGeom g, const float threshold,
+                  uint32_t* __restrict__ mask, uint32_t* __restrict__ tile_count, unsigned* __restrict__ ticket) {
+    const unsigned lane = rb_lane();
+    const unsigned sh = 4u * (lane & 7u);
+    const unsigned word_slot = (lane & 7u) * 4u + (lane >> 3);
+    long long tile = (long long)blockIdx.x * SK_WARPS + (threadIdx.x >> 5);
+    const long long first_dynamic = (long long)gridDim.x * SK_WARPS;
+    while (tile < g.total_tiles) {
+        // ticket for the NEXT tile now: the atomic's latency hides behind this tile's loads
+        unsigned nxt = 0;
+        if (lane == 0) nxt = atomicAdd(ticket, 1u);
+        const int w = (int)(tile / g.tiles_per_sweep);
+        const int t = (int)(tile - (long long)w * g.tiles_per_sweep);
+        const int cell0 = t * SK_TILE;
+        const int valid = min(SK_TILE, g.sweep_cells - cell0);     // cells of this tile inside the sweep
+        const float* __restrict__ src = echo + (int64_t)w * g.sweep_cells + cell0;
+        uint32_t* __restrict__ mw = mask + tile * SK_WORDS;
+        unsigned cnt = 0;
+#pragma unroll 1
+        for (int b = 0; b < SK_BATCHES; ++b) {
+            const int c0 = b * SK_BATCH_CELLS + (int)lane * 4;
+            unsigned nib[SK_BATCH];
+            if (VEC) {
+                float4 v[SK_BATCH];
+#pragma unroll
+                for (int k = 0; k < SK_BATCH; ++k) {
+                    const int c = c0 + k * 128;
+                    v[k] = c < valid ? rb_ld_stream4(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int k = 0; k < SK_BATCH; ++k) {
+                    const int c = c0 + k * 128;
+                    unsigned m = (unsigned)(v[k].x > threshold) | ((unsigned)(v[k].y > threshold) << 1) |
+                                 ((unsigned)(v[k].z > threshold) << 2) | ((unsigned)(v[k].w > threshold) << 3);
+                    nib[k] = c < valid ? m << sh : 0u;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < SK_BATCH; ++k) {
+                    const int c = c0 + k * 128;
+                    unsigned m = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (c + i < valid) m |= (unsigned)(__ldg(src + c + i) > threshold) << i;
+                    nib[k] = m << sh;
+                }
+            }
+            // transposing OR-butterfly over the 8 lanes of a group: 8 -> 4 -> 2 -> 1 registers
+            unsigned a4[4], a2[2], a1;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool hi = lane & 1u;
+                unsigned keep = hi ? nib[2 * i + 1] : nib[2 * i];
+                unsigned give = hi ? nib[2 * i] : nib[2 * i + 1];
+                a4[i] = keep | __shfl_xor_sync(0xffffffffu, give, 1);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const bool hi = lane & 2u;
+                unsigned keep = hi ? a4[2 * i + 1] : a4[2 * i];
+                unsigned give = hi ? a4[2 * i] : a4[2 * i + 1];
+                a2[i] = keep | __shfl_xor_sync(0xffffffffu, give, 2);
+            }
+            {
+                const bool hi = lane & 4u;
+                unsigned keep = hi ? a2[1] : a2[0];
+                unsigned give = hi ? a2[0] : a2[1];
+                a1 = keep | __shfl_xor_sync(0xffffffffu, give, 4);
+            }
+            cnt += __popc(a1);
+            mw[b * 32 + word_slot] = a1;
+        }
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (lane == 0) tile_count[tile] = cnt;
+        tile = first_dynamic + (long long)__shfl_sync(0xffffffffu, nxt, 0);
+    }
+}
+
+// ---- 2. offsets -------------------------------------------------------------------------------------
+constexpr int SO_THREADS = 512;
+
+template <typename T>
+__device__ __forceinline__ T block_exclusive_scan(T v, T* s_warp, T* total) {
+    const unsigned lane = rb_lane(), warp = threadIdx.x >> 5;
+    T incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        T o = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((int)lane >= d) incl += o;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    T before = 0, all = 0;
+#pragma unroll
+    for (int i = 0; i < SO_THREADS / 32; ++i) {
+        T c = s_warp[i];
+        if (i < (int)warp) before += c;
+        all += c;
+    }
+    __syncthreads();
+    *total = all;
+    return before + incl - v;
+}
+
+__global__ void __launch_bounds__(SO_THREADS)
+spoke_offsets_kernel(const uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_prefix, int tiles_per_sweep,
+                     int64_t n_sweeps, int stride, uint32_t* __restrict__ sweep_total, int64_t* __restrict__ sweep_base,
+                     unsigned* __restrict__ done, unsigned* __restrict__ ticket) {
+    __shared__ uint32_t s_warp[SO_THREADS / 32];
+    __shared__ unsigned long long s_warp64[SO_THREADS / 32];
+    __shared__ bool s_last;
+    const int64_t w = blockIdx.x;
+    const uint32_t* __restrict__ cnt = tile_count + w * tiles_per_sweep;
+    uint32_t* __restrict__ pfx = tile_prefix + w * tiles_per_sweep;
+    uint32_t carry = 0;
+    for (int t0 = 0; t0 < tiles_per_sweep; t0 += SO_THREADS) {
+        const int t = t0 + (int)threadIdx.x;
+        uint32_t v = t < tiles_per_sweep ? cnt[t] : 0u, total;
+        uint32_t e = block_exclusive_scan<uint32_t>(v, s_warp, &total);
+        if (t < tiles_per_sweep) pfx[t] = carry + e;
+        carry += total;
+    }
+    if (threadIdx.x == 0) {
+        sweep_total[w] = carry;
+        __threadfence();
+        s_last = atomicAdd(done, 1u) == (unsigned)gridDim.x - 1u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // last block: output base of every sweep (int64), each sweep contributes ceil(M / stride) points
+    unsigned long long base = 0;
+    for (int64_t w0 = 0; w0 < n_sweeps; w0 += SO_THREADS) {
+        const int64_t ww = w0 + threadIdx.x;
+        const unsigned long long m = ww < n_sweeps ? *(volatile uint32_t*)(sweep_total + ww) : 0u;
+        unsigned long long kept = (m + (unsigned)stride - 1u) / (unsigned)stride, total;
+        unsigned long long e = block_exclusive_scan<unsigned long long>(kept, s_warp64, &total);
+        if (ww < n_sweeps) sweep_base[ww] = (int64_t)(base + e);
+        base += total;
+    }
+    if (threadIdx.x == 0) {
+        sweep_base[n_sweeps] = (int64_t)base;
+        *done = 0;                        // self-cleaning: ready for the next launch
+        *ticket = 0;
+    }
+}
+
+// ---- 3. emit ------------------------------------------------------------------------------------------
+struct EmitArgs {
     const float* echo;
     const float* cos_tab;
     const float* sin_tab;
     const float* range_res;
     const float* ranges;                 // optional [W][S][E] explicit range per cell (NULL: range_res*j)
     const int32_t* sweep_gain;
+    const uint32_t* mask;
+    const uint32_t* tile_count;
+    const uint32_t* tile_prefix;
+    const int64_t* sweep_base;
     float* x;
     float* y;
     float* inten;
     int32_t* gain;
-    int64_t* sweep_base;                 // [W+1]
-    unsigned long long* tile_status;     // [W * tiles_per_sweep]
-    int* sweep_ready;                    // [W+1]
-    int* ticket;
     int64_t cap;
-    int64_t total_tiles;
-    int sweep_cells;                     // S*E
-    int tiles_per_sweep;
-    int n_bins;
+    int64_t total_groups;
+    int groups_per_sweep;
+    SpokeGeom g;
     int stride;
-    float threshold;
-    int vec_ok;                          // sweep_cells % 4 == 0, bins % 4 == 0 and base 16B aligned
+    FastDiv div_stride, div_bins;
 };
 
-// Exclusive prefix (survivors of this sweep before tile t) by warp 0. Descriptors of tiles of the
-// same sweep only: idx < 0 means "before the sweep" and counts as an inclusive 0.
-__device__ __forceinline__ unsigned lookback(const unsigned long long* status, int t) {
-    unsigned excl = 0;
-    int look = t - 1;
-    const unsigned lane = rb_lane();
-    while (true) {
-        int idx = look - (int)lane;
-        unsigned long long st = ST_INCLUSIVE;
-        if (idx >= 0) {
-            st = rb_ld_acquire_u64(status + idx);
-            while ((st >> 32) == 0) st = rb_ld_acquire_u64(status + idx);
-        }
-        unsigned incl_mask = __ballot_sync(0xffffffffu, (st >> 32) == 2ull);
-        unsigned val = (unsigned)(st & 0xffffffffull);
-        if (incl_mask) {
-            int first = __ffs(incl_mask) - 1;          // nearest predecessor with a full prefix
-            if ((int)lane > first) val = 0;
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
-        excl += val;
-        if (incl_mask) break;
-        look -= 32;
-    }
-    return excl;
+__device__ __forceinline__ int select_bit(uint32_t word, uint32_t o) {   // position of the o-th (0-based) set bit
+    int pos = 0;
+    uint32_t c;
+    c = __popc(word & 0xffffu); if (o >= c) { o -= c; pos += 16; word >>= 16; }
+    c = __popc(word & 0xffu);   if (o >= c) { o -= c; pos += 8;  word >>= 8; }
+    c = __popc(word & 0xfu);    if (o >= c) { o -= c; pos += 4;  word >>= 4; }
+    c = __popc(word & 0x3u);    if (o >= c) { o -= c; pos += 2;  word >>= 2; }
+    c = word & 1u;              if (o >= c) { pos += 1; }
+    return pos;
 }
 
-__global__ void __launch_bounds__(SP_THREADS) spoke_to_points_kernel(const SpokeArgs a) {
-    __shared__ int s_tile;
-    __shared__ unsigned s_warp_total[SP_WARPS];
-    __shared__ unsigned s_excl;
-    __shared__ long long s_sweep_base;
-
-    if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1);
-    __syncthreads();
-    const int tile = s_tile;
-    if (tile >= a.total_tiles) return;
-    const int w = tile / a.tiles_per_sweep;
-    const int t = tile - w * a.tiles_per_sweep;
+__global__ void __launch_bounds__(SK_THREADS) spoke_emit_kernel(const EmitArgs a) {
+    __shared__ uint4 s_mask[SK_WARPS][SK_ENTRIES];
+    __shared__ uint32_t s_rank[SK_WARPS][SK_ENTRIES];
     const unsigned lane = rb_lane();
     const int warp = threadIdx.x >> 5;
-    const float* __restrict__ src = a.echo + (int64_t)w * a.sweep_cells;
-    const int cell0 = t * SP_TILE + warp * SP_WARP_CELLS + (int)lane * 4;
+    const int64_t gidx = (int64_t)blockIdx.x * SK_WARPS + warp;
+    if (gidx >= a.total_groups) return;
+    const int w = (int)(gidx / a.groups_per_sweep);
+    const int tile0 = (int)(gidx - (int64_t)w * a.groups_per_sweep) * SK_GROUP;
+    const int ntile = min(SK_GROUP, a.g.tiles_per_sweep - tile0);
+    const int64_t tile_base = (int64_t)w * a.g.tiles_per_sweep + tile0;
 
-    // ---- load: SP_VEC independent 128-bit streaming loads per lane -------------------------
-    float4 v[SP_VEC];
-    const float qnan = __int_as_float(0x7fc00000);
+    uint32_t my_cnt = 0, my_pfx = 0;
+    if ((int)lane < ntile) { my_cnt = a.tile_count[tile_base + lane]; my_pfx = a.tile_prefix[tile_base + lane]; }
+    const uint32_t r_begin = __shfl_sync(0xffffffffu, my_pfx, 0);
+    const uint32_t r_end = __shfl_sync(0xffffffffu, my_pfx + my_cnt, ntile - 1);
+    // kept ranks of the sweep are q * stride; this group owns q in [q0, q1)
+    const uint32_t s = (uint32_t)a.stride;
+    const uint32_t q0 = fastdiv(r_begin + s - 1u, a.div_stride), q1 = fastdiv(r_end + s - 1u, a.div_stride);
+    if (q0 >= q1) return;
+
+    const uint4* __restrict__ mask4 = reinterpret_cast<const uint4*>(a.mask) + tile_base * 32;
+    uint4 m[SK_GROUP];
 #pragma unroll
-    for (int k = 0; k < SP_VEC; ++k) {
-        int c = cell0 + k * SP_CHUNK;
-        if (a.vec_ok && c + 3 < a.sweep_cells) {
-            v[k] = rb_ld_stream4(src + c);
-        } else {
-            v[k].x = c + 0 < a.sweep_cells ? __ldg(src + c + 0) : qnan;
-            v[k].y = c + 1 < a.sweep_cells ? __ldg(src + c + 1) : qnan;
-            v[k].z = c + 2 < a.sweep_cells ? __ldg(src + c + 2) : qnan;
-            v[k].w = c + 3 < a.sweep_cells ? __ldg(src + c + 3) : qnan;
-        }
+    for (int t = 0; t < SK_GROUP; ++t) {
+        const uint32_t c = __shfl_sync(0xffffffffu, my_cnt, t);
+        m[t] = (t < ntile && c) ? mask4[t * 32 + lane] : make_uint4(0u, 0u, 0u, 0u);
     }
-
-    // ---- threshold + in-warp ranks from ballots ---------------------------------------------
-    const unsigned lt = rb_lanemask_lt();
-    unsigned pass_bits = 0;            // bit (4k + c): cell c of chunk k survives
-    unsigned rank_base[SP_VEC];        // survivors of this warp before my first cell of chunk k
-    unsigned running = 0;
 #pragma unroll
-    for (int k = 0; k < SP_VEC; ++k) {
-        bool p0 = v[k].x > a.threshold, p1 = v[k].y > a.threshold;
-        bool p2 = v[k].z > a.threshold, p3 = v[k].w > a.threshold;
-        unsigned b0 = __ballot_sync(0xffffffffu, p0), b1 = __ballot_sync(0xffffffffu, p1);
-        unsigned b2 = __ballot_sync(0xffffffffu, p2), b3 = __ballot_sync(0xffffffffu, p3);
-        rank_base[k] = running + __popc(b0 & lt) + __popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt);
-        running += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
-        pass_bits |= ((unsigned)p0 | ((unsigned)p1 << 1) | ((unsigned)p2 << 2) | ((unsigned)p3 << 3)) << (4 * k);
-    }
-    if (lane == 0) s_warp_total[warp] = running;
-    __syncthreads();
-    unsigned warp_prefix = 0, tile_total = 0;
+    for (int t = 0; t < SK_GROUP; ++t) {
+        const uint32_t c = __popc(m[t].x) + __popc(m[t].y) + __popc(m[t].z) + __popc(m[t].w);
+        uint32_t incl = c;
 #pragma unroll
-    for (int i = 0; i < SP_WARPS; ++i) {
-        unsigned c = s_warp_total[i];
-        if (i < warp) warp_prefix += c;
-        tile_total += c;
-    }
-
-    // ---- tile prefix (decoupled look-back) and sweep output base -----------------------------
-    if (warp == 0) {
-        unsigned long long* status = a.tile_status + (int64_t)w * a.tiles_per_sweep;
-        unsigned excl = 0;
-        if (t == 0) {
-            if (lane == 0) rb_st_release_u64(status, ST_INCLUSIVE | tile_total);
-        } else {
-            if (lane == 0) rb_st_release_u64(status + t, ST_AGGREGATE | tile_total);
-            excl = lookback(status, t);
-            if (lane == 0) rb_st_release_u64(status + t, ST_INCLUSIVE | (unsigned long long)(excl + tile_total));
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((int)lane >= d) incl += o;
         }
-        if (lane == 0) {
-            long long base = 0;
-            if (w > 0) {
-                while (rb_ld_acquire_s32(a.sweep_ready + w) == 0) { }
-                base = a.sweep_base[w];
-            } else if (t == 0) {
-                a.sweep_base[0] = 0;
-            }
-            if (t == a.tiles_per_sweep - 1) {          // last tile of the sweep: publish the next base
-                long long m = (long long)excl + tile_total;
-                a.sweep_base[w + 1] = base + (m + a.stride - 1) / a.stride;
-                __threadfence();
-                rb_st_release_s32(a.sweep_ready + w + 1, 1);
-            }
-            s_excl = excl;
-            s_sweep_base = base;
-        }
+        const uint32_t pfx = __shfl_sync(0xffffffffu, my_pfx, t);
+        s_mask[warp][t * 32 + lane] = m[t];
+        s_rank[warp][t * 32 + lane] = t < ntile ? pfx + incl - c : 0xffffffffu;   // rank at the entry's first cell
     }
-    __syncthreads();
-    if (pass_bits == 0) return;
+    __syncwarp();
 
-    // ---- write survivors whose rank in the sweep is a multiple of the stride ------------------
-    const unsigned rank0 = s_excl + warp_prefix;
-    const long long out_base = s_sweep_base;
+    const long long out_base = a.sweep_base[w];
     const int gain_label = a.sweep_gain[w];
-    const float* __restrict__ cos_w = a.cos_tab + (int64_t)w * (a.sweep_cells / a.n_bins);
-    const float* __restrict__ sin_w = a.sin_tab + (int64_t)w * (a.sweep_cells / a.n_bins);
-    const float* __restrict__ res_w = a.range_res ? a.range_res + (int64_t)w * (a.sweep_cells / a.n_bins) : nullptr;
+    const int64_t tab_off = (int64_t)w * a.g.n_spokes;
+    const int64_t cell_off = (int64_t)w * a.g.sweep_cells;
+    const uint32_t* __restrict__ rk = s_rank[warp];
+    for (uint32_t q = q0 + lane; q < q1; q += 32) {
+        const uint32_t r = q * s;
+        int e = 0;                                    // largest entry with rank[e] <= r (rank[0] <= r always)
 #pragma unroll
-    for (int k = 0; k < SP_VEC; ++k) {
-        unsigned bits = (pass_bits >> (4 * k)) & 0xfu;
-        if (!bits) continue;
-        const int c = cell0 + k * SP_CHUNK;
-        unsigned r = rank0 + rank_base[k];
-        const float vals[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (!(bits & (1u << i))) continue;
-            unsigned q = r / (unsigned)a.stride;
-            if (q * (unsigned)a.stride == r) {
-                long long pos = out_base + q;
-                if (pos < a.cap) {
-                    int cell = c + i;
-                    int s = cell / a.n_bins;
-                    int j = cell - s * a.n_bins;
-                    float rng = a.ranges ? a.ranges[(int64_t)w * a.sweep_cells + cell]
-                                         : __fmul_rn(res_w[s], (float)j);   // T4:214
-                    a.x[pos] = __fmul_rn(rng, cos_w[s]);                // T4:217
-                    a.y[pos] = __fmul_rn(rng, sin_w[s]);                // T4:218
-                    a.inten[pos] = vals[i];
-                    a.gain[pos] = gain_label;
-                }
-            }
-            ++r;
+        for (int step = SK_ENTRIES / 2; step >= 1; step >>= 1)
+            if (rk[e + step] <= r) e += step;
+        uint32_t o = r - rk[e];
+        const uint4 mm = s_mask[warp][e];
+        uint32_t word = mm.x;
+        int wi = 0;
+        uint32_t c = __popc(mm.x);
+        if (o >= c) { o -= c; word = mm.y; wi = 1; c = __popc(mm.y);
+            if (o >= c) { o -= c; word = mm.z; wi = 2; c = __popc(mm.z);
+                if (o >= c) { o -= c; word = mm.w; wi = 3; } } }
+        const int cell = (tile0 + (e >> 5)) * SK_TILE + (e & 31) * 128 + wi * 32 + select_bit(word, o);
+        const long long pos = out_base + q;
+        if (pos < a.cap) {
+            const int sp = (int)fastdiv((uint32_t)cell, a.div_bins);
+            const int j = cell - sp * a.g.n_bins;
+            const float val = __ldg(a.echo + cell_off + cell);
+            const float cs = __ldg(a.cos_tab + tab_off + sp), sn = __ldg(a.sin_tab + tab_off + sp);
+            const float rng = a.ranges ? __ldg(a.ranges + cell_off + cell)
+                                       : __fmul_rn(__ldg(a.range_res + tab_off + sp), (float)j);   // T4:214
+            a.x[pos] = __fmul_rn(rng, cs);                  // T4:217
+            a.y[pos] = __fmul_rn(rng, sn);                  // T4:218
+            a.inten[pos] = val;
+            a.gain[pos] = gain_label;
         }
     }
 }
@@ -270,37 +395,71 @@ extern "C" int rb_spoke_to_points(rb_ctx* ctx, const float* echo, const float* c
     }
     RB_REQUIRE(echo && cos_tab && sin_tab && (range_res || ranges) && sweep_gain, "NULL input");
     RB_REQUIRE(cap == 0 || (x && y && inten && gain), "NULL output");
-    int64_t tiles_per_sweep = rb_div_up(cells, SP_TILE);
-    int64_t total_tiles = tiles_per_sweep * n_sweeps;
-    RB_REQUIRE(total_tiles < (int64_t)1 << 31, "too many tiles in one batch; split the batch");
+    RB_REQUIRE(n_sweeps < (int64_t)1 << 31, "too many sweeps in one batch; split the batch");
 
-    void* status;
-    void* flags;
-    RB_TRY(rb_scratch_get(ctx, RB_S_TILE_STATUS, sizeof(unsigned long long) * (size_t)total_tiles, &status));
-    size_t flag_bytes = sizeof(int) * (size_t)(n_sweeps + 2);
-    RB_TRY(rb_scratch_get(ctx, RB_S_SWEEP_FLAGS, flag_bytes, &flags));
-    RB_CUDA(cudaMemsetAsync(status, 0, sizeof(unsigned long long) * (size_t)total_tiles, stream));
-    RB_CUDA(cudaMemsetAsync(flags, 0, flag_bytes, stream));
+    SpokeGeom g;
+    g.sweep_cells = (int)cells;
+    g.tiles_per_sweep = (int)rb_div_up(cells, SK_TILE);
+    g.total_tiles = (int64_t)g.tiles_per_sweep * n_sweeps;
+    g.n_bins = n_bins;
+    g.n_spokes = n_spokes;
 
-    SpokeArgs a;
-    a.echo = echo; a.cos_tab = cos_tab; a.sin_tab = sin_tab; a.range_res = range_res;
-    a.ranges = ranges;
-    a.sweep_gain = sweep_gain;
-    a.x = x; a.y = y; a.inten = inten; a.gain = gain;
-    a.sweep_base = sweep_base;
-    a.tile_status = (unsigned long long*)status;
-    a.sweep_ready = (int*)flags;
-    a.ticket = (int*)flags + (n_sweeps + 1);
-    a.cap = cap;
-    a.total_tiles = total_tiles;
-    a.sweep_cells = (int)cells;
-    a.tiles_per_sweep = (int)tiles_per_sweep;
-    a.n_bins = n_bins;
-    a.stride = stride;
-    a.threshold = threshold;
-    a.vec_ok = (cells % 4 == 0) && (n_bins % 4 == 0) && (((uintptr_t)echo & 15u) == 0);
-    spoke_to_points_kernel<<<(unsigned)total_tiles, SP_THREADS, 0, stream>>>(a);
+    // scratch: mask words (1 bit per cell), tile counts, tile prefixes, sweep totals, {done, ticket}
+    const size_t mask_bytes = sizeof(uint32_t) * (size_t)g.total_tiles * SK_WORDS;
+    const size_t tile_bytes = (sizeof(uint32_t) * (size_t)g.total_tiles + 255) & ~size_t(255);
+    const size_t sweep_bytes = (sizeof(uint32_t) * (size_t)n_sweeps + 255) & ~size_t(255);
+    void *mask_v, *tiles_v, *flags_v;
+    RB_TRY(rb_scratch_get(ctx, RB_S_SPOKE_MASK, mask_bytes, &mask_v));
+    RB_TRY(rb_scratch_get(ctx, RB_S_TILE_STATUS, 2 * tile_bytes + sweep_bytes, &tiles_v));
+    rb_scratch& fslot = ctx->slots[RB_S_SWEEP_FLAGS];
+    const void* flags_before = fslot.ptr;
+    RB_TRY(rb_scratch_get(ctx, RB_S_SWEEP_FLAGS, 256, &flags_v));
+    if (fslot.ptr != flags_before) RB_CUDA(cudaMemsetAsync(flags_v, 0, 256, stream));   // counters clean themselves afterwards
+    uint32_t* mask = (uint32_t*)mask_v;
+    uint32_t* tile_count = (uint32_t*)tiles_v;
+    uint32_t* tile_prefix = (uint32_t*)((unsigned char*)tiles_v + tile_bytes);
+    uint32_t* sweep_total = (uint32_t*)((unsigned char*)tiles_v + 2 * tile_bytes);
+    unsigned* done = (unsigned*)flags_v;
+    unsigned* ticket = done + 32;                    // its own 128-byte line
+
+    const bool prof = ctx->opt_spoke_profile != 0;
+    if (prof && !ctx->spoke_ev[0])
+        for (int i = 0; i < 4; ++i) RB_CUDA(cudaEventCreate(&ctx->spoke_ev[i]));
+    if (prof) RB_CUDA(cudaEventRecord(ctx->spoke_ev[0], stream));
+
+    const bool vec = (cells % 4 == 0) && (((uintptr_t)echo & 15u) == 0);
+    const int64_t want_blocks = rb_div_up(g.total_tiles, SK_WARPS);
+    const int64_t max_blocks = (int64_t)ctx->sm_count * SK_CTAS_PER_SM;
+    const unsigned blocks = (unsigned)(want_blocks < max_blocks ? want_blocks : max_blocks);
+    if (vec) spoke_mask_kernel<true><<<blocks, SK_THREADS, 0, stream>>>(echo, g, threshold, mask, tile_count, ticket);
+    else spoke_mask_kernel<false><<<blocks, SK_THREADS, 0, stream>>>(echo, g, threshold, mask, tile_count, ticket);
     RB_LAUNCH_CHECK(ctx);
+    if (prof) RB_CUDA(cudaEventRecord(ctx->spoke_ev[1], stream));
+
+    spoke_offsets_kernel<<<(unsigned)n_sweeps, SO_THREADS, 0, stream>>>(tile_count, tile_prefix, g.tiles_per_sweep, n_sweeps,
+                                                                       stride, sweep_total, sweep_base, done, ticket);
+    RB_LAUNCH_CHECK(ctx);
+    if (prof) RB_CUDA(cudaEventRecord(ctx->spoke_ev[2], stream));
+
+    if (cap > 0) {
+        EmitArgs a;
+        a.echo = echo; a.cos_tab = cos_tab; a.sin_tab = sin_tab; a.range_res = range_res; a.ranges = ranges;
+        a.sweep_gain = sweep_gain;
+        a.mask = mask; a.tile_count = tile_count; a.tile_prefix = tile_prefix; a.sweep_base = sweep_base;
+        a.x = x; a.y = y; a.inten = inten; a.gain = gain;
+        a.cap = cap;
+        a.groups_per_sweep = (int)rb_div_up(g.tiles_per_sweep, SK_GROUP);
+        a.total_groups = (int64_t)a.groups_per_sweep * n_sweeps;
+        a.g = g;
+        a.stride = stride;
+        a.div_stride = make_fastdiv((uint32_t)stride);
+        a.div_bins = make_fastdiv((uint32_t)n_bins);
+        const int64_t eblocks = rb_div_up(a.total_groups, SK_WARPS);
+        RB_REQUIRE(eblocks < (int64_t)1 << 31, "too many tiles in one batch; split the batch");
+        spoke_emit_kernel<<<(unsigned)eblocks, SK_THREADS, 0, stream>>>(a);
+        RB_LAUNCH_CHECK(ctx);
+    }
+    if (prof) RB_CUDA(cudaEventRecord(ctx->spoke_ev[3], stream));
     return RB_OK;
 }
 

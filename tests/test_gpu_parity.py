@@ -62,7 +62,8 @@ def test_spoke_to_points_vs_reference_golden(gpu, tag, thr, stride):
 
 
 @pytest.mark.parametrize("S,E,stride,thr", [(7, 100, 3, 4.0), (33, 130, 1, 8.0), (5, 1023, 5, 2.0), (1, 1, 1, -1.0),
-                                            (64, 1024, 7, 9.0), (3, 4096, 2, 0.0)])
+                                            (64, 1024, 7, 9.0), (3, 4096, 2, 0.0), (17, 1000, 3, 1.0),
+                                            (2200, 1024, 4, 9.0), (4100, 1024, 3, 2.0)])
 def test_spoke_to_points_ragged_shapes(gpu, S, E, stride, thr):
     """Sweeps that do not fill tiles / are not multiples of the vector width; several sweeps per
     launch so stride phases restart at each sweep and output offsets chain across sweeps."""
@@ -132,6 +133,41 @@ def test_batch_properties_at_scale(gpu):
     for a, b in zip(out1[:4], out2[:4]):
         assert torch.equal(a[:n], b[:n])
     assert bool((out1[2][:n] > 10.0).all())
+
+
+def test_spoke_dense_batch_properties(gpu):
+    """Dense clutter (thr 2 -> ~70 % of the cells survive), 12 sweeps, stride 2: per-sweep counts against
+    torch, order and values against a torch boolean-mask compaction of two sweeps."""
+    spec = syn.SweepSpec(seed=8, frames=4)
+    echo = gpu.synth_echo(spec).view(12, spec.spokes, spec.bins)
+    d = echo.device
+    c, s, r = _tables(gpu, spec, 12, d)
+    gains = torch.tensor([40, 50, 75] * 4, dtype=torch.int32, device=d)
+    b = gpu.spoke_to_points(echo, c, s, r, gains, 2.0, 2, gains_per_frame=3)
+    assert b.n > 8_000_000
+    m = (echo > 2.0).view(12, -1).sum(dim=1)
+    kept = (m + 1) // 2
+    assert b.n == int(kept.sum())
+    off = b.frame_off.cpu().numpy()
+    assert list(off) == [0] + list(np.cumsum(kept.view(4, 3).sum(dim=1).cpu().numpy()))
+    base = np.concatenate([[0], np.cumsum(kept.cpu().numpy())])
+    for w in (0, 7):
+        want = echo[w].reshape(-1)[(echo[w] > 2.0).reshape(-1)][::2]
+        assert torch.equal(b.inten[base[w]:base[w + 1]], want)
+        assert bool((b.gain[base[w]:base[w + 1]] == gains[w]).all())
+
+
+def test_spoke_profile_option(gpu):
+    from radar_point_cloud_tracking_b200 import _lib
+    ctx = _lib.context(0)
+    spec = syn.SweepSpec(**SWEEP_SPEC)
+    echo = syn.synth_sweep(spec, 0, 2)[None]
+    ctx.set_option("spoke_profile", 1)
+    try:
+        _run_sweeps(gpu, echo, spec, 10.0, 4)
+        assert all(ctx.info(k) >= 0 for k in ("spoke_mask_ns", "spoke_offsets_ns", "spoke_emit_ns"))
+    finally:
+        ctx.set_option("spoke_profile", 0)
 
 
 # ------------------------------------------------------------------------------- T4 mirror on CSV files
