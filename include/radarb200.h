@@ -172,9 +172,11 @@ int rb_synth_echo(rb_ctx* ctx, float* echo, int64_t n_sweeps, int n_spokes, int 
                   const int32_t* rects, const int32_t* rect_off, void* stream);
 
 /* Diagnostic switches. "spoke_profile" = 1: rb_spoke_to_points records CUDA events (on the launch stream)
- * around each of its three kernels; read them back with rb_get_info. */
+ * around each of its three kernels; read them back with rb_get_info. "spoke_mask_variant": 0 = auto (the
+ * TMA-staged mask kernel when S*E % 4 == 0 and echo is 16-byte aligned, else the register-staged one),
+ * 1 = always register-staged, 2 = require TMA-staged (error when the shape is not eligible). */
 int rb_set_option(rb_ctx* ctx, const char* name, int64_t value);
-/* "launches"; "spoke_mask_ns" / "spoke_offsets_ns" / "spoke_emit_ns" = device time of the kernels of the
+/* "launches"; "spoke_last_variant" (1 = register-staged, 2 = TMA-staged); "spoke_mask_ns" / "spoke_offsets_ns" / "spoke_emit_ns" = device time of the kernels of the
  * last profiled rb_spoke_to_points (syncs on its last event); -1 for unknown names or nothing recorded. */
 int64_t rb_get_info(rb_ctx* ctx, const char* name);
 

@@ -50,6 +50,8 @@ struct rb_ctx {
     void* pinned = nullptr;          // small pinned staging buffer (host)
     size_t pinned_cap = 0;
     rb_dbscan_stats last_stats;
+    int opt_spoke_mask_variant = 0;  // 0 = auto, 1 = register-staged mask kernel, 2 = require the TMA-staged one
+    int spoke_last_variant = 0;      // mask kernel the last rb_spoke_to_points launched (1 / 2)
     int opt_spoke_profile = 0;       // 1: record events around the three spoke-to-point kernels
     cudaEvent_t spoke_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };

@@ -64,28 +64,241 @@ struct SpokeGeom {
 };
 
 // ---- 1. mask + count ------------------------------------------------------------------------------
-// Lane l of a warp owns cells 4l..4l+3 of each 128-cell chunk (one LDG.128). The 4-bit survivor
+// Lane l of a warp owns cells 4l..4l+3 of each 128-cell chunk (one 128-bit load). The 4-bit survivor
 // nibbles of 8 chunks are OR-reduced across each group of 8 lanes with a transposing butterfly
 // (7 shuffles for 8 chunks): afterwards lane l holds the finished 32-bit word of chunk (l & 7),
 // lane group (l >> 3), i.e. word (l & 7) * 4 + (l >> 3) of the batch - one 128-byte store per batch.
+__device__ __forceinline__ unsigned set_gt(float a, float b) {            // 0xffffffff if a > b (false for NaN)
+    unsigned r;
+    asm("set.gt.u32.f32 %0, %1, %2;" : "=r"(r) : "f"(a), "f"(b));
+    return r;
+}
+
+struct LaneBits { unsigned b0, b1, b2, b3; };                             // (1 << i) << 4 * (lane & 7)
+__device__ __forceinline__ LaneBits lane_bits(unsigned lane) {
+    const unsigned sh = 4u * (lane & 7u);
+    return LaneBits{1u << sh, 2u << sh, 4u << sh, 8u << sh};
+}
+__device__ __forceinline__ unsigned nibble(const float4& v, float thr, const LaneBits& lb) {
+    return (set_gt(v.x, thr) & lb.b0) | (set_gt(v.y, thr) & lb.b1) | (set_gt(v.z, thr) & lb.b2) | (set_gt(v.w, thr) & lb.b3);
+}
+
+// transposing OR-butterfly over the 8 lanes of a group: 8 -> 4 -> 2 -> 1 registers
+__device__ __forceinline__ unsigned butterfly8(const unsigned (&nib)[8], unsigned lane) {
+    unsigned a4[4], a2[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const bool hi = lane & 1u;
+        unsigned keep = hi ? nib[2 * i + 1] : nib[2 * i];
+        unsigned give = hi ? nib[2 * i] : nib[2 * i + 1];
+        a4[i] = keep | __shfl_xor_sync(0xffffffffu, give, 1);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const bool hi = lane & 2u;
+        unsigned keep = hi ? a4[2 * i + 1] : a4[2 * i];
+        unsigned give = hi ? a4[2 * i] : a4[2 * i + 1];
+        a2[i] = keep | __shfl_xor_sync(0xffffffffu, give, 2);
+    }
+    const bool hi = lane & 4u;
+    unsigned keep = hi ? a2[1] : a2[0];
+    unsigned give = hi ? a2[0] : a2[1];
+    return keep | __shfl_xor_sync(0xffffffffu, give, 4);
+}
+
+struct TileRef { const float* src; int valid; };                          // first cell + cells inside the sweep
+__device__ __forceinline__ TileRef tile_ref(const float* echo, const SpokeGeom& g, long long tile) {
+    const int w = (int)(tile / g.tiles_per_sweep);
+    const int cell0 = (int)(tile - (long long)w * g.tiles_per_sweep) * SK_TILE;
+    return TileRef{echo + (int64_t)w * g.sweep_cells + cell0, min(SK_TILE, g.sweep_cells - cell0)};
+}
+
+// ---- 1a. TMA-staged variant (the default) --------------------------------------------------------------
+// One persistent CTA per SM: a producer thread streams stages of MT_TILES tiles (64 KiB) into a ring of
+// MT_STAGES shared-memory buffers with 1-D bulk async copies (cp.async.bulk ... mbarrier::complete_tx, one
+// per tile), so the bytes in flight per SM (up to 192 KiB) are held by the TMA engine and shared memory,
+// not by registers. MT_WARPS consumer warps turn each stage into mask words, one 1024-cell batch (= one
+// 128-byte line of mask) per warp at a time, and add their survivor counts to per-tile shared counters
+// that the producer flushes to global memory when it recycles the slot. Stages are handed out by one
+// atomic ticket per CTA and stage (a ticket per WARP and tile serialises on the atomic unit: measured
+// 4.8 instead of 7.0 TB/s, tools/mask_bench.cu).
+constexpr int MT_WARPS = 8;                                                // consumer warps
+constexpr int MT_STAGES = 3;
+constexpr int MT_TILES = 4;                                                // tiles per stage
+constexpr int MT_STAGE_CELLS = MT_TILES * SK_TILE;                         // 16384 cells = 64 KiB
+constexpr int MT_STAGE_BATCHES = MT_STAGE_CELLS / SK_BATCH_CELLS;          // 16
+constexpr int MT_THREADS = MT_WARPS * 32 + 32;
+
+struct MtMeta {
+    long long first_tile;                 // global id of the stage's first tile; < 0: no more work
+    int n_tiles;
+    int valid[MT_TILES];                  // cells of each tile inside its sweep
+    unsigned cnt[MT_TILES];               // survivors, accumulated by the consumers
+};
+struct __align__(128) MtSmem {
+    float ring[MT_STAGES][MT_STAGE_CELLS];
+    unsigned long long full[MT_STAGES];
+    unsigned long long empty[MT_STAGES];
+    MtMeta meta[MT_STAGES];
+};
+constexpr int MT_SMEM = (int)sizeof(MtSmem) + 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MT_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni MT_DONE;\n"
+        "bra.uni MT_WAIT;\n"
+        "MT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk async copy (TMA engine, 1-D), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(MT_THREADS, 1)
+spoke_mask_tma_kernel(const float* __restrict__ echo, const SpokeGeom g, const float threshold,
+                      uint32_t* __restrict__ mask, uint32_t* __restrict__ tile_count, unsigned* __restrict__ ticket) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    MtSmem& sm = *reinterpret_cast<MtSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    const unsigned lane = rb_lane();
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < MT_STAGES; ++i) {
+            mbar_init(&sm.full[i], 1);
+            mbar_init(&sm.empty[i], MT_WARPS);
+#pragma unroll
+            for (int t = 0; t < MT_TILES; ++t) sm.meta[i].cnt[t] = 0;
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    const long long n_stages = (g.total_tiles + MT_TILES - 1) / MT_TILES;
+
+    if (warp == MT_WARPS) {
+        // ================= producer (one thread) =================
+        if (lane != 0) return;
+        auto flush = [&](int s) {                                          // counts of the stage that just left slot s
+            MtMeta& m = sm.meta[s];
+            for (int t = 0; t < m.n_tiles; ++t) {
+                tile_count[m.first_tile + t] = m.cnt[t];
+                m.cnt[t] = 0;
+            }
+        };
+        long long st = blockIdx.x;
+        int it = 0;
+        while (true) {
+            const int s = it % MT_STAGES;
+            if (it >= MT_STAGES) {
+                mbar_wait(&sm.empty[s], (uint32_t)(it / MT_STAGES - 1) & 1u);
+                flush(s);
+            }
+            MtMeta& m = sm.meta[s];
+            if (st >= n_stages) {                                          // end marker for the consumers
+                m.first_tile = -1;
+                m.n_tiles = 0;
+                mbar_arrive(&sm.full[s]);
+                break;
+            }
+            const long long t0 = st * MT_TILES;
+            const int nt = (int)min((long long)MT_TILES, g.total_tiles - t0);
+            m.first_tile = t0;
+            m.n_tiles = nt;
+            TileRef tr[MT_TILES];
+            uint32_t bytes = 0;
+#pragma unroll
+            for (int t = 0; t < MT_TILES; ++t) {
+                tr[t] = t < nt ? tile_ref(echo, g, t0 + t) : TileRef{nullptr, 0};
+                m.valid[t] = tr[t].valid;
+                bytes += (uint32_t)tr[t].valid * 4u;
+            }
+            mbar_expect_tx(&sm.full[s], bytes);
+#pragma unroll
+            for (int t = 0; t < MT_TILES; ++t)
+                if (tr[t].valid > 0) bulk_g2s(&sm.ring[s][t * SK_TILE], tr[t].src, (uint32_t)tr[t].valid * 4u, &sm.full[s]);
+            st = (long long)gridDim.x + atomicAdd(ticket, 1u);
+            ++it;
+        }
+        // stages still in flight: fills it-1 .. it-(MT_STAGES-1)
+        for (int j = max(0, it - (MT_STAGES - 1)); j < it; ++j) {
+            const int s = j % MT_STAGES;
+            mbar_wait(&sm.empty[s], (uint32_t)(j / MT_STAGES) & 1u);
+            flush(s);
+        }
+        return;
+    }
+
+    // ================= consumers =================
+    const LaneBits lb = lane_bits(lane);
+    const unsigned word_slot = (lane & 7u) * 4u + (lane >> 3);
+    for (int it = 0;; ++it) {
+        const int s = it % MT_STAGES;
+        mbar_wait(&sm.full[s], (uint32_t)(it / MT_STAGES) & 1u);
+        MtMeta& m = sm.meta[s];
+        const long long t0 = m.first_tile;
+        if (t0 < 0) break;
+        const int nt = m.n_tiles;
+        const float4* __restrict__ b4 = reinterpret_cast<const float4*>(sm.ring[s]);
+#pragma unroll
+        for (int b = warp; b < MT_STAGE_BATCHES; b += MT_WARPS) {
+            const int t = b / SK_BATCHES;                                  // tile of the batch inside the stage
+            if (t >= nt) break;
+            const int valid = m.valid[t] - (b % SK_BATCHES) * SK_BATCH_CELLS;   // cells of this batch inside the sweep
+            unsigned nib[SK_BATCH];
+            if (valid >= SK_BATCH_CELLS) {
+                float4 v[SK_BATCH];
+#pragma unroll
+                for (int k = 0; k < SK_BATCH; ++k) v[k] = b4[b * (SK_BATCH_CELLS / 4) + k * 32 + lane];
+#pragma unroll
+                for (int k = 0; k < SK_BATCH; ++k) nib[k] = nibble(v[k], threshold, lb);
+            } else {
+#pragma unroll
+                for (int k = 0; k < SK_BATCH; ++k) {
+                    const int c = k * 128 + (int)lane * 4;                  // valid is a multiple of 4 here
+                    nib[k] = c < valid ? nibble(b4[b * (SK_BATCH_CELLS / 4) + k * 32 + lane], threshold, lb) : 0u;
+                }
+            }
+            const unsigned word = butterfly8(nib, lane);
+            mask[(t0 + t) * SK_WORDS + (b % SK_BATCHES) * 32 + word_slot] = word;
+            const unsigned c = __reduce_add_sync(0xffffffffu, __popc(word));
+            if (lane == 0 && c) atomicAdd(&m.cnt[t], c);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[s]);
+    }
+}
+
+// ---- 1b. register-staged variant (any shape; 128-bit loads when VEC) -------------------------------------
 template <bool VEC>
 __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM)
 spoke_mask_kernel(const float* __restrict__ echo, const SpokeGeom g, const float threshold,
-                  uint32_t* __restrict__ mask, uint32_t* __restrict__ tile_count, unsigned* __restrict__ ticket) {
+                  uint32_t* __restrict__ mask, uint32_t* __restrict__ tile_count) {
     const unsigned lane = rb_lane();
+    const LaneBits lb = lane_bits(lane);
     const unsigned sh = 4u * (lane & 7u);
     const unsigned word_slot = (lane & 7u) * 4u + (lane >> 3);
-    long long tile = (long long)blockIdx.x * SK_WARPS + (threadIdx.x >> 5);
-    const long long first_dynamic = (long long)gridDim.x * SK_WARPS;
-    while (tile < g.total_tiles) {
-        // ticket for the NEXT tile now: the atomic's latency hides behind this tile's loads
-        unsigned nxt = 0;
-        if (lane == 0) nxt = atomicAdd(ticket, 1u);
-        const int w = (int)(tile / g.tiles_per_sweep);
-        const int t = (int)(tile - (long long)w * g.tiles_per_sweep);
-        const int cell0 = t * SK_TILE;
-        const int valid = min(SK_TILE, g.sweep_cells - cell0);     // cells of this tile inside the sweep
-        const float* __restrict__ src = echo + (int64_t)w * g.sweep_cells + cell0;
+    // static round-robin over the tiles: a per-warp ticket would serialise on the atomic unit (see above)
+    const long long n_warps = (long long)gridDim.x * SK_WARPS;
+    for (long long tile = (long long)blockIdx.x * SK_WARPS + (threadIdx.x >> 5); tile < g.total_tiles; tile += n_warps) {
+        const TileRef tr = tile_ref(echo, g, tile);
+        const int valid = tr.valid;
+        const float* __restrict__ src = tr.src;
         uint32_t* __restrict__ mw = mask + tile * SK_WORDS;
         unsigned cnt = 0;
 #pragma unroll 1
@@ -93,18 +306,18 @@ spoke_mask_kernel(const float* __restrict__ echo, const SpokeGeom g, const float
             const int c0 = b * SK_BATCH_CELLS + (int)lane * 4;
             unsigned nib[SK_BATCH];
             if (VEC) {
-                float4 v[SK_BATCH];
+                if (valid == SK_TILE) {
+                    float4 v[SK_BATCH];
 #pragma unroll
-                for (int k = 0; k < SK_BATCH; ++k) {
-                    const int c = c0 + k * 128;
-                    v[k] = c < valid ? rb_ld_stream4(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                    for (int k = 0; k < SK_BATCH; ++k) v[k] = rb_ld_stream4(src + c0 + k * 128);
 #pragma unroll
-                for (int k = 0; k < SK_BATCH; ++k) {
-                    const int c = c0 + k * 128;
-                    unsigned m = (unsigned)(v[k].x > threshold) | ((unsigned)(v[k].y > threshold) << 1) |
-                                 ((unsigned)(v[k].z > threshold) << 2) | ((unsigned)(v[k].w > threshold) << 3);
-                    nib[k] = c < valid ? m << sh : 0u;
+                    for (int k = 0; k < SK_BATCH; ++k) nib[k] = nibble(v[k], threshold, lb);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < SK_BATCH; ++k) {
+                        const int c = c0 + k * 128;
+                        nib[k] = c < valid ? nibble(rb_ld_stream4(src + c), threshold, lb) : 0u;
+                    }
                 }
             } else {
 #pragma unroll
@@ -117,34 +330,12 @@ spoke_mask_kernel(const float* __restrict__ echo, const SpokeGeom g, const float
                     nib[k] = m << sh;
                 }
             }
-            // transposing OR-butterfly over the 8 lanes of a group: 8 -> 4 -> 2 -> 1 registers
-            unsigned a4[4], a2[2], a1;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const bool hi = lane & 1u;
-                unsigned keep = hi ? nib[2 * i + 1] : nib[2 * i];
-                unsigned give = hi ? nib[2 * i] : nib[2 * i + 1];
-                a4[i] = keep | __shfl_xor_sync(0xffffffffu, give, 1);
-            }
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const bool hi = lane & 2u;
-                unsigned keep = hi ? a4[2 * i + 1] : a4[2 * i];
-                unsigned give = hi ? a4[2 * i] : a4[2 * i + 1];
-                a2[i] = keep | __shfl_xor_sync(0xffffffffu, give, 2);
-            }
-            {
-                const bool hi = lane & 4u;
-                unsigned keep = hi ? a2[1] : a2[0];
-                unsigned give = hi ? a2[0] : a2[1];
-                a1 = keep | __shfl_xor_sync(0xffffffffu, give, 4);
-            }
-            cnt += __popc(a1);
-            mw[b * 32 + word_slot] = a1;
+            const unsigned word = butterfly8(nib, lane);
+            cnt += __popc(word);
+            mw[b * 32 + word_slot] = word;
         }
         cnt = __reduce_add_sync(0xffffffffu, cnt);
         if (lane == 0) tile_count[tile] = cnt;
-        tile = first_dynamic + (long long)__shfl_sync(0xffffffffu, nxt, 0);
     }
 }
 
@@ -428,11 +619,27 @@ extern "C" int rb_spoke_to_points(rb_ctx* ctx, const float* echo, const float* c
     if (prof) RB_CUDA(cudaEventRecord(ctx->spoke_ev[0], stream));
 
     const bool vec = (cells % 4 == 0) && (((uintptr_t)echo & 15u) == 0);
-    const int64_t want_blocks = rb_div_up(g.total_tiles, SK_WARPS);
-    const int64_t max_blocks = (int64_t)ctx->sm_count * SK_CTAS_PER_SM;
-    const unsigned blocks = (unsigned)(want_blocks < max_blocks ? want_blocks : max_blocks);
-    if (vec) spoke_mask_kernel<true><<<blocks, SK_THREADS, 0, stream>>>(echo, g, threshold, mask, tile_count, ticket);
-    else spoke_mask_kernel<false><<<blocks, SK_THREADS, 0, stream>>>(echo, g, threshold, mask, tile_count, ticket);
+    // 0 = auto (TMA-staged when the shape allows 16-byte bulk copies), 1 = register-staged, 2 = require TMA
+    const int variant = ctx->opt_spoke_mask_variant;
+    RB_REQUIRE(variant != 2 || vec, "TMA-staged mask kernel needs S*E % 4 == 0 and a 16-byte aligned echo pointer");
+    if (vec && variant != 1) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            RB_CUDA(cudaFuncSetAttribute(spoke_mask_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM));
+            attr_set = true;
+        }
+        const int64_t want_blocks = rb_div_up(g.total_tiles, MT_TILES);
+        const unsigned blocks = (unsigned)(want_blocks < ctx->sm_count ? want_blocks : ctx->sm_count);
+        spoke_mask_tma_kernel<<<blocks, MT_THREADS, MT_SMEM, stream>>>(echo, g, threshold, mask, tile_count, ticket);
+        ctx->spoke_last_variant = 2;
+    } else {
+        const int64_t want_blocks = rb_div_up(g.total_tiles, SK_WARPS);
+        const int64_t max_blocks = (int64_t)ctx->sm_count * SK_CTAS_PER_SM;
+        const unsigned blocks = (unsigned)(want_blocks < max_blocks ? want_blocks : max_blocks);
+        if (vec) spoke_mask_kernel<true><<<blocks, SK_THREADS, 0, stream>>>(echo, g, threshold, mask, tile_count);
+        else spoke_mask_kernel<false><<<blocks, SK_THREADS, 0, stream>>>(echo, g, threshold, mask, tile_count);
+        ctx->spoke_last_variant = 1;
+    }
     RB_LAUNCH_CHECK(ctx);
     if (prof) RB_CUDA(cudaEventRecord(ctx->spoke_ev[1], stream));
 

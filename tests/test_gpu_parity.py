@@ -26,6 +26,23 @@ def gpu():
     return dev
 
 
+@pytest.fixture(params=["auto", "registers"])
+def mask_variant(request, gpu):
+    """Run the spoke-to-point tests on both mask kernels: the default (TMA-staged whenever S*E % 4 == 0)
+    and the register-staged one."""
+    from radar_point_cloud_tracking_b200 import _lib
+    ctx = _lib.context(0)
+    ctx.set_option("spoke_mask_variant", 0 if request.param == "auto" else 1)
+    yield request.param
+    ctx.set_option("spoke_mask_variant", 0)
+
+
+def _expect_variant(mode, cells):
+    from radar_point_cloud_tracking_b200 import _lib
+    want = 2 if (mode == "auto" and cells % 4 == 0) else 1
+    assert _lib.context(0).info("spoke_last_variant") == want
+
+
 def _tables(dev, spec, n_sweeps, d):
     from radar_point_cloud_tracking_b200.tracker import sweep_tables
     c, s, r = sweep_tables(spec.angle_units(), spec.scale(), spec.bins)
@@ -51,11 +68,12 @@ def test_device_generator_matches_numpy(gpu):
 
 # ------------------------------------------------------------------------------- a1: spoke-to-point
 @pytest.mark.parametrize("tag,thr,stride", SWEEP_CASES)
-def test_spoke_to_points_vs_reference_golden(gpu, tag, thr, stride):
+def test_spoke_to_points_vs_reference_golden(gpu, mask_variant, tag, thr, stride):
     g = golden("sweeps")
     spec = syn.SweepSpec(**SWEEP_SPEC)
     echo = syn.synth_sweep(spec, 0, 2)[None]
     b = _run_sweeps(gpu, echo, spec, thr, stride)
+    _expect_variant(mask_variant, echo[0].size)
     assert b.n == int(g[f"{tag}_n"])
     x, y, z = (t[:b.n].cpu().numpy() for t in (b.x, b.y, b.inten))
     assert digest(x) + digest(y) + digest(z) == str(g[f"{tag}_digest"])
@@ -64,12 +82,13 @@ def test_spoke_to_points_vs_reference_golden(gpu, tag, thr, stride):
 @pytest.mark.parametrize("S,E,stride,thr", [(7, 100, 3, 4.0), (33, 130, 1, 8.0), (5, 1023, 5, 2.0), (1, 1, 1, -1.0),
                                             (64, 1024, 7, 9.0), (3, 4096, 2, 0.0), (17, 1000, 3, 1.0),
                                             (2200, 1024, 4, 9.0), (4100, 1024, 3, 2.0)])
-def test_spoke_to_points_ragged_shapes(gpu, S, E, stride, thr):
+def test_spoke_to_points_ragged_shapes(gpu, mask_variant, S, E, stride, thr):
     """Sweeps that do not fill tiles / are not multiples of the vector width; several sweeps per
     launch so stride phases restart at each sweep and output offsets chain across sweeps."""
     spec = syn.SweepSpec(seed=3, frames=2, spokes=S, bins=E, clutter_p=0.05, land_blobs=1, buoys=1, boats=1)
     echo = syn.synth_echo(spec).reshape(-1, S, E)
     b = _run_sweeps(gpu, echo, spec, thr, stride, gains=[40, 50, 75] * 2, gpf=3)
+    _expect_variant(mask_variant, S * E)
     off = b.frame_off.cpu().numpy()
     want = [O.sweep_to_points(echo[w], spec.angle_units(), spec.scale(), thr, stride) for w in range(6)]
     wx = np.concatenate([w[0] for w in want])
@@ -82,7 +101,7 @@ def test_spoke_to_points_ragged_shapes(gpu, S, E, stride, thr):
     assert list(off) == [0, sum(len(w[0]) for w in want[:3]), len(wx)]
 
 
-def test_spoke_to_points_empty_and_capacity(gpu):
+def test_spoke_to_points_empty_and_capacity(gpu, mask_variant):
     spec = syn.SweepSpec(**SWEEP_SPEC)
     echo = syn.synth_sweep(spec, 0, 0)[None]
     b = _run_sweeps(gpu, echo, spec, 300.0, 4)            # nothing above the threshold
@@ -96,7 +115,7 @@ def test_spoke_to_points_empty_and_capacity(gpu):
     assert b.n == 0
 
 
-def test_full_size_frame_bit_exact(gpu):
+def test_full_size_frame_bit_exact(gpu, mask_variant):
     """One full 2048 x 1024 x 3-gain frame (BASELINE shape) against the numpy oracle."""
     spec = syn.SweepSpec(seed=123, frames=1)
     echo = gpu.synth_echo(spec)
@@ -114,7 +133,7 @@ def test_full_size_frame_bit_exact(gpu):
         assert np.array_equal(got, pts) and np.array_equal(b.gain[:b.n].cpu().numpy(), gains)
 
 
-def test_batch_properties_at_scale(gpu):
+def test_batch_properties_at_scale(gpu, mask_variant):
     """Size-independent properties on a 24-sweep batch: per-sweep counts = ceil(M/stride), offsets
     monotone, intensities above threshold, idempotent re-run."""
     spec = syn.SweepSpec(seed=5, frames=8)
@@ -135,7 +154,7 @@ def test_batch_properties_at_scale(gpu):
     assert bool((out1[2][:n] > 10.0).all())
 
 
-def test_spoke_dense_batch_properties(gpu):
+def test_spoke_dense_batch_properties(gpu, mask_variant):
     """Dense clutter (thr 2 -> ~70 % of the cells survive), 12 sweeps, stride 2: per-sweep counts against
     torch, order and values against a torch boolean-mask compaction of two sweeps."""
     spec = syn.SweepSpec(seed=8, frames=4)
