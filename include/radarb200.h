@@ -159,8 +159,41 @@ typedef struct rb_dbscan_stats {
     double cell_size, time_bin;
     int32_t dims[4];            /* nx, ny, nz, nt */
     int32_t time_radius;
+    int32_t tight;              /* 1 = tight-cell bucket algorithm, 0 = general algorithm */
 } rb_dbscan_stats;
 int rb_stdbscan_last_stats(rb_ctx* ctx, rb_dbscan_stats* out);
+
+/* ---- a7 in phases (what rb_stdbscan runs back to back) -------------------------------------------
+ * For callers that must exchange data between the phases - the time-sharded multi-GPU driver
+ * (SURVEY.md section 8 e): every rank clusters its own frames plus a floor(eps_time)-frame halo,
+ * replaces the core flags of the halo points by their owner's, and numbers components globally.
+ * The plan (grid, sorted copies, bucket table) lives in the ctx until the next rb_stdbscan_plan /
+ * rb_stdbscan; the coordinate and time buffers are only read by rb_stdbscan_plan.
+ *
+ *   rb_stdbscan_plan        same inputs as rb_stdbscan. Syncs (the grid is chosen on the host).
+ *   rb_stdbscan_cores       core flags (neighbour count >= min_samples); core_out uint8[n]
+ *                           (original order) optional.
+ *   rb_stdbscan_set_cores   overwrite the core flags (uint8[n], original order).
+ *   rb_stdbscan_components  connected components of the core points. global_index int64[n]
+ *                           (optional; NULL = 0..n-1) gives every point its key; comp_key int64[n]
+ *                           (optional output) = smallest key among the core points of the point's
+ *                           component, -1 for non-core points.
+ *   rb_stdbscan_assign      core_label int32[n]: final cluster id of every core point (ignored for
+ *                           the others); labels int32[n] out: core points keep their id, border
+ *                           points take the smallest id among their core neighbours, noise = -1.
+ *                           labels may alias core_label.
+ *   rb_relabel              out[i] = ids[j] with table_keys[j] == keys[i] (table_keys sorted
+ *                           ascending, int64[m]); -1 when keys[i] < 0 or absent.
+ * None of these sync except rb_stdbscan_plan. */
+int rb_stdbscan_plan(rb_ctx* ctx, const float* x, const float* y, const float* z, int64_t stride,
+                     const float* times, int64_t n, double eps_space, float eps_time, int min_samples,
+                     void* stream);
+int rb_stdbscan_cores(rb_ctx* ctx, uint8_t* core_out, void* stream);
+int rb_stdbscan_set_cores(rb_ctx* ctx, const uint8_t* core_in, void* stream);
+int rb_stdbscan_components(rb_ctx* ctx, const int64_t* global_index, int64_t* comp_key, void* stream);
+int rb_stdbscan_assign(rb_ctx* ctx, const int32_t* core_label, int32_t* labels, void* stream);
+int rb_relabel(rb_ctx* ctx, const int64_t* keys, int64_t n, const int64_t* table_keys,
+               const int32_t* table_ids, int64_t m, int32_t* out, void* stream);
 
 /* ---- test/bench infrastructure (not part of the reference surface) ---------------------------
  * Device twin of radar_point_cloud_tracking_b200.synthetic.synth_echo: fills echo[W][S][E] for
@@ -174,7 +207,9 @@ int rb_synth_echo(rb_ctx* ctx, float* echo, int64_t n_sweeps, int n_spokes, int 
 /* Diagnostic switches. "spoke_profile" = 1: rb_spoke_to_points records CUDA events (on the launch stream)
  * around each of its three kernels; read them back with rb_get_info. "spoke_mask_variant": 0 = auto (the
  * TMA-staged mask kernel when S*E % 4 == 0 and echo is 16-byte aligned, else the register-staged one),
- * 1 = always register-staged, 2 = require TMA-staged (error when the shape is not eligible). */
+ * 1 = always register-staged, 2 = require TMA-staged (error when the shape is not eligible).
+ * "dbscan_mode": 0 = auto (tight-cell bucket algorithm when the times are integers and the bucket table
+ * fits the budget), 1 = always the general algorithm, 2 = require the tight one. */
 int rb_set_option(rb_ctx* ctx, const char* name, int64_t value);
 /* "launches"; "spoke_last_variant" (1 = register-staged, 2 = TMA-staged); "spoke_mask_ns" / "spoke_offsets_ns" / "spoke_emit_ns" = device time of the kernels of the
  * last profiled rb_spoke_to_points (syncs on its last event); -1 for unknown names or nothing recorded. */

@@ -20,7 +20,7 @@ c_i32, c_i64, c_f32, c_f64, c_vp = C.c_int, C.c_int64, C.c_float, C.c_double, C.
 class DbscanStats(C.Structure):
     _fields_ = [("n_points", c_i64), ("n_cells", c_i64), ("n_core", c_i64), ("n_clusters", c_i64),
                 ("pair_tests_count", c_i64), ("pair_tests_union", c_i64), ("pair_tests_border", c_i64),
-                ("cell_size", c_f64), ("time_bin", c_f64), ("dims", c_i32 * 4), ("time_radius", c_i32)]
+                ("cell_size", c_f64), ("time_bin", c_f64), ("dims", c_i32 * 4), ("time_radius", c_i32), ("tight", c_i32)]
 
 
 #: name -> (restype, argtypes); must list every symbol of include/radarb200.h
@@ -45,6 +45,12 @@ SIGNATURES = {
     "rb_stdbscan": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_f64, c_f32, c_i32,
                             c_vp, c_vp, C.POINTER(c_i64), c_vp]),
     "rb_stdbscan_last_stats": (c_i32, [c_vp, C.POINTER(DbscanStats)]),
+    "rb_stdbscan_plan": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_f64, c_f32, c_i32, c_vp]),
+    "rb_stdbscan_cores": (c_i32, [c_vp, c_vp, c_vp]),
+    "rb_stdbscan_set_cores": (c_i32, [c_vp, c_vp, c_vp]),
+    "rb_stdbscan_components": (c_i32, [c_vp, c_vp, c_vp, c_vp]),
+    "rb_stdbscan_assign": (c_i32, [c_vp, c_vp, c_vp, c_vp]),
+    "rb_relabel": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "rb_synth_echo": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "rb_set_option": (c_i32, [c_vp, C.c_char_p, c_i64]),
     "rb_get_info": (c_i64, [c_vp, C.c_char_p]),

@@ -37,8 +37,12 @@ enum rb_slot {
     RB_S_STATS,
     RB_S_MISC,
     RB_S_FUSE_GRID,
+    RB_S_COMP_KEY,          // dbscan: component key per point (original order)
+    RB_S_B_NCORE, RB_S_B_PARENT, RB_S_B_LABEL, RB_S_B_MINKEY, RB_S_CORE_START, RB_S_CB_LIST,   // dbscan, tight: per-bucket arrays
     RB_S_COUNT
 };
+
+struct rb_db_plan;
 
 struct rb_ctx {
     int device = 0;
@@ -50,6 +54,8 @@ struct rb_ctx {
     void* pinned = nullptr;          // small pinned staging buffer (host)
     size_t pinned_cap = 0;
     rb_dbscan_stats last_stats;
+    rb_db_plan* db_plan = nullptr;   // state shared by the rb_stdbscan_* phases (dbscan.cu)
+    int opt_dbscan_mode = 0;         // 0 = auto, 1 = always the general algorithm, 2 = require the tight one
     int opt_spoke_mask_variant = 0;  // 0 = auto, 1 = register-staged mask kernel, 2 = require the TMA-staged one
     int spoke_last_variant = 0;      // mask kernel the last rb_spoke_to_points launched (1 / 2)
     int opt_spoke_profile = 0;       // 1: record events around the three spoke-to-point kernels
@@ -57,6 +63,7 @@ struct rb_ctx {
 };
 
 void rb_set_error(const char* fmt, ...);
+void rb_db_plan_free(rb_ctx* ctx);
 int rb_scratch_get(rb_ctx* ctx, rb_slot slot, size_t bytes, void** out);
 
 #define RB_CUDA(call)                                                                      \

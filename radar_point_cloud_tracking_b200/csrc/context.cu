@@ -59,6 +59,7 @@ extern "C" void rb_destroy(rb_ctx* ctx) {
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (int i = 0; i < 4; ++i)
         if (ctx->spoke_ev[i]) cudaEventDestroy(ctx->spoke_ev[i]);
+    rb_db_plan_free(ctx);
     delete ctx;
 }
 
@@ -74,6 +75,11 @@ extern "C" int rb_device_info(rb_ctx* ctx, int* sm_count, int* cc_major, int* cc
 extern "C" int rb_set_option(rb_ctx* ctx, const char* name, int64_t value) {
     RB_REQUIRE(ctx && name, "NULL argument");
     if (!strcmp(name, "spoke_profile")) { ctx->opt_spoke_profile = value != 0; return RB_OK; }
+    if (!strcmp(name, "dbscan_mode")) {
+        RB_REQUIRE(value >= 0 && value <= 2, "dbscan_mode: 0 = auto, 1 = general algorithm, 2 = require the tight-cell algorithm");
+        ctx->opt_dbscan_mode = (int)value;
+        return RB_OK;
+    }
     if (!strcmp(name, "spoke_mask_variant")) {
         RB_REQUIRE(value >= 0 && value <= 2, "spoke_mask_variant: 0 = auto, 1 = register-staged, 2 = TMA-staged");
         ctx->opt_spoke_mask_variant = (int)value;
@@ -88,6 +94,7 @@ extern "C" int64_t rb_get_info(rb_ctx* ctx, const char* name) {
     if (!strcmp(name, "launches")) return ctx->launches;
     if (!strcmp(name, "spoke_profile")) return ctx->opt_spoke_profile;
     if (!strcmp(name, "spoke_mask_variant")) return ctx->opt_spoke_mask_variant;
+    if (!strcmp(name, "dbscan_mode")) return ctx->opt_dbscan_mode;
     if (!strcmp(name, "spoke_last_variant")) return ctx->spoke_last_variant;
     // device time of the last profiled rb_spoke_to_points, per kernel, in nanoseconds (syncs on its last event)
     int k = !strcmp(name, "spoke_mask_ns") ? 0 : !strcmp(name, "spoke_offsets_ns") ? 1 : !strcmp(name, "spoke_emit_ns") ? 2 : -1;

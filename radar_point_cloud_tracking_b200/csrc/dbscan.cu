@@ -2,19 +2,33 @@
 // 101-136 and radar_pipeline/processors/clustering.py:49-115; native precedent
 // radar-pipeline-rs/src/processors/clustering.rs:209-325).
 //
-// Result contract (SURVEY.md section 8 N4 — the reference's labels are canonical):
+// Result contract (SURVEY.md section 8 N4 - the reference's labels are canonical):
 //   neighbour(p,q) <=> fl64 sum_d (double(p_d)-double(q_d))^2 <= eps^2  and  |t_p-t_q| <= eps_t (fl32)
 //   core(p) <=> |N(p)| >= min_samples (self included)
 //   cluster id = rank of the component's smallest core index; border = smallest id among its core
 //   neighbours; noise = -1.
 //
-// Pipeline (all on the caller's stream):
-//   bounds -> [host picks the grid] -> cell ids + counting sort into a dense (t, z, y, x) cell table
-//   -> neighbour count with early exit -> core flags -> lock-free min-root union-find over
-//   core-core edges -> component min original index -> rank (scan) -> labels -> border pass.
-// Cells are at least eps wide (and time bins at least eps_t wide, or exactly one frame when the
-// times are integers), so the 3^D x (2*tr+1) block of cells around a point holds all its
-// neighbours; the exact predicates are always evaluated, the grid is only a candidate filter.
+// Phases (each an entry point, so the time-sharded multi-GPU driver can exchange data in between;
+// rb_stdbscan runs them back to back):
+//   plan        bounds -> [host picks the grid] -> counting sort into a dense (t, z, y, x) bucket table
+//   cores       neighbour count with early exit -> core flags
+//   components  connected components of the core points -> per point the KEY of its component
+//               (smallest key among the component's core points; key = caller's global index)
+//   assign      given the final id of every core point: ids of border points (smallest id among core
+//               neighbours), noise = -1
+//
+// Two algorithms behind the same phases:
+//   TIGHT (integer times, grid fits the budget): spatial cells with a diagonal just under eps and unit
+//     time bins. Points of one spatial cell whose bins differ by <= floor(eps_t) are neighbours WITHOUT a
+//     distance test; core points of one bucket (cell, bin) are mutually connected, so the union-find runs
+//     over buckets: same-cell buckets inside the time window are merged directly, two buckets of
+//     different cells need ONE core-core pair within eps (searched by a warp, skipped when the buckets
+//     already share a root); border points read per-bucket labels and test only buckets that can lower
+//     their id. Dense regions cost almost no distance tests.
+//   GENERAL (non-integer times, eps 0, or a grid coarsened to fit memory): cells at least eps wide,
+//     exact predicates for every candidate pair, lock-free min-root union-find over core points.
+// The exact float64/float32 predicates of the reference decide every pair that is tested; the shortcuts
+// only skip tests whose outcome is implied.
 #include <float.h>
 #include <math.h>
 
@@ -23,6 +37,7 @@
 namespace {
 
 constexpr int DB_THREADS = 256;
+constexpr long long KEY_NONE = 0x7fffffffffffffffLL;
 
 struct DbGrid {
     double lo[3];
@@ -33,6 +48,8 @@ struct DbGrid {
     int nt;
     int tr;            // time-bin search radius
     int dim;
+    int R;             // spatial search radius in cells: 1 (cells >= eps wide) or 2 (tight cells)
+    int tight;
 };
 
 struct DbPoints {      // strided view of the caller's coordinates
@@ -137,7 +154,7 @@ __global__ void __launch_bounds__(DB_THREADS) db_scatter_kernel(DbPoints p, int 
     st[pos] = p.t[i];
 }
 
-// ---- neighbourhood walk ------------------------------------------------------------------------------
+// ---- shared device helpers -----------------------------------------------------------------------------
 struct Sorted {
     const float* x; const float* y; const float* z; const float* t;
     const int* cell; const int* cell_start;
@@ -157,9 +174,7 @@ __device__ __forceinline__ Pt<DIM> load_pt(const Sorted& s, int i) {
 }
 
 template <int DIM>
-__device__ __forceinline__ bool is_neighbour(const Pt<DIM>& a, const Pt<DIM>& b, double eps2, float eps_t) {
-    float dt = __fsub_rn(b.t, a.t);                       // T4:486, float32
-    if (!(fabsf(dt) <= eps_t)) return false;
+__device__ __forceinline__ bool near_enough(const Pt<DIM>& a, const Pt<DIM>& b, double eps2) {
     double d = (double)a.x - (double)b.x;                 // sklearn rdist: d += tmp*tmp, float64, no FMA
     double acc = __dmul_rn(d, d);
     if (DIM > 1) { d = (double)a.y - (double)b.y; acc = __dadd_rn(acc, __dmul_rn(d, d)); }
@@ -167,54 +182,29 @@ __device__ __forceinline__ bool is_neighbour(const Pt<DIM>& a, const Pt<DIM>& b,
     return acc <= eps2;
 }
 
-// Calls f(q) for every sorted index q in the cells around `cell`; f returns false to stop.
-template <int DIM, typename F>
-__device__ __forceinline__ void for_each_candidate(const DbGrid& g, const int* __restrict__ cell_start, int cell, F&& f) {
-    int cx = cell % g.n[0];
+template <int DIM>
+__device__ __forceinline__ bool is_neighbour(const Pt<DIM>& a, const Pt<DIM>& b, double eps2, float eps_t) {
+    float dt = __fsub_rn(b.t, a.t);                       // T4:486, float32
+    if (!(fabsf(dt) <= eps_t)) return false;
+    return near_enough<DIM>(a, b, eps2);
+}
+
+struct CellPos { int cx, cy, cz, tb; };
+__device__ __forceinline__ CellPos decode_cell(const DbGrid& g, int cell) {
+    CellPos c;
+    c.cx = cell % g.n[0];
     int rest = cell / g.n[0];
-    int cy = rest % g.n[1];
+    c.cy = rest % g.n[1];
     rest /= g.n[1];
-    int cz = rest % g.n[2];
-    int tb = rest / g.n[2];
-    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.n[0] - 1);
-    const int y0 = DIM > 1 ? max(cy - 1, 0) : 0, y1 = DIM > 1 ? min(cy + 1, g.n[1] - 1) : 0;
-    const int z0 = DIM > 2 ? max(cz - 1, 0) : 0, z1 = DIM > 2 ? min(cz + 1, g.n[2] - 1) : 0;
-    const int t0 = max(tb - g.tr, 0), t1 = min(tb + g.tr, g.nt - 1);
-    for (int tt = t0; tt <= t1; ++tt)
-        for (int zz = z0; zz <= z1; ++zz)
-            for (int yy = y0; yy <= y1; ++yy) {
-                int row = ((tt * g.n[2] + zz) * g.n[1] + yy) * g.n[0];
-                int b = cell_start[row + x0], e = cell_start[row + x1 + 1];
-                for (int q = b; q < e; ++q)
-                    if (!f(q)) return;
-            }
+    c.cz = rest % g.n[2];
+    c.tb = rest / g.n[2];
+    return c;
 }
 
 __device__ __forceinline__ void add_counter(unsigned long long* ctr, unsigned long long v) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
     if (rb_lane() == 0 && v) atomicAdd(ctr, v);
-}
-
-// core[p]: 1 = core, 0 = not core, 2 = not core and alone (no neighbour but itself)
-template <int DIM>
-__global__ void __launch_bounds__(DB_THREADS) db_count_kernel(Sorted s, DbGrid g, int n, double eps2, float eps_t,
-                                                             int min_samples, uint8_t* __restrict__ core,
-                                                             int* __restrict__ parent, unsigned long long* __restrict__ ctr) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long tests = 0;
-    if (p < n) {
-        Pt<DIM> a = load_pt<DIM>(s, p);
-        int cnt = 0;
-        for_each_candidate<DIM>(g, s.cell_start, s.cell[p], [&](int q) {
-            ++tests;
-            cnt += is_neighbour<DIM>(a, load_pt<DIM>(s, q), eps2, eps_t);
-            return cnt < min_samples || cnt < 2;          // keep going until core is certain
-        });
-        core[p] = cnt >= min_samples ? 1 : (cnt <= 1 ? 2 : 0);
-        parent[p] = p;
-    }
-    add_counter(ctr, tests);
 }
 
 __device__ __forceinline__ int uf_find(int* parent, int a) {
@@ -224,6 +214,17 @@ __device__ __forceinline__ int uf_find(int* parent, int a) {
         if (p == cur) return cur;
         int gp = rb_ld_relaxed_s32(parent + p);
         if (gp != p) parent[cur] = gp;                    // path halving; any ancestor is a valid parent
+        cur = p;
+    }
+}
+
+// read-only find for the finalising kernels: while they flatten (parent[x] = root) nothing else may write
+// parents, or a late path-halving store could replace a root by a stale ancestor
+__device__ __forceinline__ int uf_find_ro(const int* parent, int a) {
+    int cur = a;
+    while (true) {
+        int p = rb_ld_relaxed_s32(parent + cur);
+        if (p == cur) return cur;
         cur = p;
     }
 }
@@ -239,18 +240,73 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
     }
 }
 
+__device__ __forceinline__ long long point_key(const long long* __restrict__ gidx, int orig) {
+    return gidx ? gidx[orig] : (long long)orig;
+}
+
+// ======================================================================================================
+// GENERAL algorithm: exact predicates for every candidate, union-find over core points
+// ======================================================================================================
+// Calls f(q) for every sorted index q in the cells around `cell`; f returns false to stop.
+template <int DIM, typename F>
+__device__ __forceinline__ void for_each_candidate(const DbGrid& g, const int* __restrict__ cell_start, int cell, F&& f) {
+    const CellPos c = decode_cell(g, cell);
+    const int x0 = max(c.cx - 1, 0), x1 = min(c.cx + 1, g.n[0] - 1);
+    const int y0 = DIM > 1 ? max(c.cy - 1, 0) : 0, y1 = DIM > 1 ? min(c.cy + 1, g.n[1] - 1) : 0;
+    const int z0 = DIM > 2 ? max(c.cz - 1, 0) : 0, z1 = DIM > 2 ? min(c.cz + 1, g.n[2] - 1) : 0;
+    const int t0 = max(c.tb - g.tr, 0), t1 = min(c.tb + g.tr, g.nt - 1);
+    for (int tt = t0; tt <= t1; ++tt)
+        for (int zz = z0; zz <= z1; ++zz)
+            for (int yy = y0; yy <= y1; ++yy) {
+                int row = ((tt * g.n[2] + zz) * g.n[1] + yy) * g.n[0];
+                int b = cell_start[row + x0], e = cell_start[row + x1 + 1];
+                for (int q = b; q < e; ++q)
+                    if (!f(q)) return;
+            }
+}
+
+// core[p]: 1 = core, 0 = not core, 2 = not core and alone (no neighbour but itself)
 template <int DIM>
-__global__ void __launch_bounds__(DB_THREADS) db_union_kernel(Sorted s, DbGrid g, int n, double eps2, float eps_t,
-                                                             const uint8_t* __restrict__ core, int* __restrict__ parent,
-                                                             unsigned long long* __restrict__ ctr) {
+__global__ void __launch_bounds__(DB_THREADS) dbg_count_kernel(Sorted s, DbGrid g, int n, double eps2, float eps_t,
+                                                              int min_samples, uint8_t* __restrict__ core,
+                                                              unsigned long long* __restrict__ ctr) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long tests = 0;
+    if (p < n) {
+        Pt<DIM> a = load_pt<DIM>(s, p);
+        int cnt = 0;
+        for_each_candidate<DIM>(g, s.cell_start, s.cell[p], [&](int q) {
+            ++tests;
+            cnt += is_neighbour<DIM>(a, load_pt<DIM>(s, q), eps2, eps_t);
+            return cnt < min_samples || cnt < 2;          // keep going until core is certain
+        });
+        core[p] = cnt >= min_samples ? 1 : (cnt <= 1 ? 2 : 0);
+    }
+    add_counter(ctr, tests);
+}
+
+__global__ void __launch_bounds__(DB_THREADS) dbg_init_kernel(int n, int* __restrict__ parent, long long* __restrict__ minkey) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) { parent[p] = p; minkey[p] = KEY_NONE; }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(DB_THREADS) dbg_union_kernel(Sorted s, DbGrid g, int n, double eps2, float eps_t,
+                                                              const uint8_t* __restrict__ core, int* __restrict__ parent,
+                                                              unsigned long long* __restrict__ ctr) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long tests = 0;
     if (p < n && core[p] == 1) {
         Pt<DIM> a = load_pt<DIM>(s, p);
+        int my_root = p;                                  // a recent root of p: same root => nothing to do
         for_each_candidate<DIM>(g, s.cell_start, s.cell[p], [&](int q) {
             if (q < p && core[q] == 1) {                  // each core-core edge once
+                if (rb_ld_relaxed_s32(parent + q) == my_root) return true;
                 ++tests;
-                if (is_neighbour<DIM>(a, load_pt<DIM>(s, q), eps2, eps_t)) uf_union(parent, p, q);
+                if (is_neighbour<DIM>(a, load_pt<DIM>(s, q), eps2, eps_t)) {
+                    uf_union(parent, p, q);
+                    my_root = uf_find(parent, p);
+                }
             }
             return true;
         });
@@ -258,60 +314,314 @@ __global__ void __launch_bounds__(DB_THREADS) db_union_kernel(Sorted s, DbGrid g
     add_counter(ctr, tests);
 }
 
-__global__ void __launch_bounds__(DB_THREADS) db_minorig_kernel(int n, const uint8_t* __restrict__ core, int* __restrict__ parent,
-                                                               const int* __restrict__ sidx, int* __restrict__ minorig) {
+__global__ void __launch_bounds__(DB_THREADS) dbg_minkey_kernel(int n, const uint8_t* __restrict__ core, int* __restrict__ parent,
+                                                               const int* __restrict__ sidx, const long long* __restrict__ gidx,
+                                                               long long* __restrict__ minkey) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n || core[p] != 1) return;
-    int r = uf_find(parent, p);
+    int r = uf_find_ro(parent, p);
     parent[p] = r;
-    atomicMin(minorig + r, sidx[p]);
+    atomicMin(minkey + r, point_key(gidx, sidx[p]));
 }
 
-__global__ void __launch_bounds__(DB_THREADS) db_rootflag_kernel(int n, const uint8_t* __restrict__ core,
-                                                                const int* __restrict__ parent, const int* __restrict__ minorig,
-                                                                int* __restrict__ flags) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n || core[p] != 1 || parent[p] != p) return;
-    flags[minorig[p]] = 1;
-}
-
-__global__ void __launch_bounds__(DB_THREADS) db_label_kernel(int n, const uint8_t* __restrict__ core, const int* __restrict__ parent,
-                                                             const int* __restrict__ minorig, const int* __restrict__ rank,
-                                                             const int* __restrict__ sidx, int* __restrict__ slabel,
-                                                             int32_t* __restrict__ labels, uint8_t* __restrict__ core_out) {
+__global__ void __launch_bounds__(DB_THREADS) dbg_keyout_kernel(int n, const uint8_t* __restrict__ core, const int* __restrict__ parent,
+                                                               const int* __restrict__ sidx, const long long* __restrict__ minkey,
+                                                               long long* __restrict__ comp_key) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
-    int lab = -1;
-    if (core[p] == 1) lab = rank[minorig[parent[p]]];
-    slabel[p] = lab;
-    int o = sidx[p];
-    labels[o] = lab;
-    if (core_out) core_out[o] = core[p] == 1;
+    comp_key[sidx[p]] = core[p] == 1 ? minkey[parent[p]] : -1;
 }
 
 template <int DIM>
-__global__ void __launch_bounds__(DB_THREADS) db_border_kernel(Sorted s, DbGrid g, int n, double eps2, float eps_t,
-                                                              const uint8_t* __restrict__ core, const int* __restrict__ slabel,
-                                                              const int* __restrict__ sidx, int32_t* __restrict__ labels,
-                                                              unsigned long long* __restrict__ ctr) {
+__global__ void __launch_bounds__(DB_THREADS) dbg_border_kernel(Sorted s, DbGrid g, int n, double eps2, float eps_t,
+                                                               const uint8_t* __restrict__ core, const int* __restrict__ slabel,
+                                                               const int* __restrict__ sidx, int32_t* __restrict__ labels,
+                                                               unsigned long long* __restrict__ ctr) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long tests = 0;
-    if (p < n && core[p] == 0) {
-        Pt<DIM> a = load_pt<DIM>(s, p);
-        int best = INT_MAX;
-        for_each_candidate<DIM>(g, s.cell_start, s.cell[p], [&](int q) {
-            if (core[q] == 1) {
-                int lq = slabel[q];
-                if (lq < best) {                          // only a smaller id can change the answer
-                    ++tests;
-                    if (is_neighbour<DIM>(a, load_pt<DIM>(s, q), eps2, eps_t)) best = lq;
+    if (p < n) {
+        int out = core[p] == 1 ? slabel[p] : -1;
+        if (core[p] == 0) {
+            Pt<DIM> a = load_pt<DIM>(s, p);
+            int best = INT_MAX;
+            for_each_candidate<DIM>(g, s.cell_start, s.cell[p], [&](int q) {
+                if (core[q] == 1) {
+                    int lq = slabel[q];
+                    if (lq < best) {                          // only a smaller id can change the answer
+                        ++tests;
+                        if (is_neighbour<DIM>(a, load_pt<DIM>(s, q), eps2, eps_t)) best = lq;
+                    }
                 }
-            }
-            return best != 0;                             // id 0 cannot be beaten
-        });
-        if (best != INT_MAX) labels[sidx[p]] = best;
+                return best != 0;                             // id 0 cannot be beaten
+            });
+            if (best != INT_MAX) out = best;
+        }
+        labels[sidx[p]] = out;
     }
     add_counter(ctr, tests);
+}
+
+// ======================================================================================================
+// TIGHT algorithm: buckets = (time bin, spatial cell), cell diagonal < eps, unit time bins
+// ======================================================================================================
+struct Window {                    // cells to visit around a point / bucket
+    int x0, x1, y0, y1, z0, z1, t0, t1;
+};
+template <int DIM>
+__device__ __forceinline__ Window window_of(const DbGrid& g, const CellPos& c) {
+    Window w;
+    w.x0 = max(c.cx - g.R, 0); w.x1 = min(c.cx + g.R, g.n[0] - 1);
+    w.y0 = DIM > 1 ? max(c.cy - g.R, 0) : 0; w.y1 = DIM > 1 ? min(c.cy + g.R, g.n[1] - 1) : 0;
+    w.z0 = DIM > 2 ? max(c.cz - g.R, 0) : 0; w.z1 = DIM > 2 ? min(c.cz + g.R, g.n[2] - 1) : 0;
+    w.t0 = max(c.tb - g.tr, 0); w.t1 = min(c.tb + g.tr, g.nt - 1);
+    return w;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(DB_THREADS) dbt_count_kernel(Sorted s, DbGrid g, int n, double eps2, int min_samples,
+                                                              uint8_t* __restrict__ core, unsigned long long* __restrict__ ctr) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long tests = 0;
+    if (p < n) {
+        const int cell = s.cell[p];
+        const CellPos c = decode_cell(g, cell);
+        const Window w = window_of<DIM>(g, c);
+        const int per_t = g.n[0] * g.n[1] * g.n[2];
+        const int sp = cell - c.tb * per_t;
+        int cnt = 0;
+        // own spatial cell over the time window: neighbours by construction
+        for (int tt = w.t0; tt <= w.t1; ++tt) cnt += s.cell_start[tt * per_t + sp + 1] - s.cell_start[tt * per_t + sp];
+        if (cnt < min_samples) {
+            const Pt<DIM> a = load_pt<DIM>(s, p);
+            for (int tt = w.t0; tt <= w.t1 && cnt < min_samples; ++tt)
+                for (int zz = w.z0; zz <= w.z1 && cnt < min_samples; ++zz)
+                    for (int yy = w.y0; yy <= w.y1 && cnt < min_samples; ++yy) {
+                        const int row = ((tt * g.n[2] + zz) * g.n[1] + yy) * g.n[0];
+                        const bool own_row = zz == c.cz && yy == c.cy;
+                        // the row's cells x0..x1 are one contiguous range of sorted points; skip the own cell
+                        const int b = s.cell_start[row + w.x0], e = s.cell_start[row + w.x1 + 1];
+                        int hb = e, he = e;                                   // hole = the own cell's points (already counted)
+                        if (own_row) { hb = s.cell_start[row + c.cx]; he = s.cell_start[row + c.cx + 1]; }
+                        for (int q = b; q < hb && cnt < min_samples; ++q) {
+                            ++tests;
+                            cnt += near_enough<DIM>(a, load_pt<DIM>(s, q), eps2);
+                        }
+                        for (int q = he; q < e && cnt < min_samples; ++q) {
+                            ++tests;
+                            cnt += near_enough<DIM>(a, load_pt<DIM>(s, q), eps2);
+                        }
+                    }
+        }
+        core[p] = cnt >= min_samples ? 1 : (cnt <= 1 ? 2 : 0);
+    }
+    add_counter(ctr, tests);
+}
+
+__global__ void __launch_bounds__(DB_THREADS) dbt_bucket_init_kernel(int64_t n_cells, int* __restrict__ b_ncore, int* __restrict__ b_parent,
+                                                                    long long* __restrict__ b_minkey, int* __restrict__ n_cb) {
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b == 0) *n_cb = 0;
+    if (b < n_cells) { b_ncore[b] = 0; b_parent[b] = (int)b; b_minkey[b] = KEY_NONE; }
+    if (b == n_cells) b_ncore[b] = 0;                                        // scan sentinel
+}
+
+__global__ void __launch_bounds__(DB_THREADS) dbt_bucket_stats_kernel(int n, const uint8_t* __restrict__ core, const int* __restrict__ scell,
+                                                                     const int* __restrict__ sidx, const long long* __restrict__ gidx,
+                                                                     int* __restrict__ b_ncore, long long* __restrict__ b_minkey) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n || core[p] != 1) return;
+    const int b = scell[p];
+    atomicAdd(b_ncore + b, 1);
+    atomicMin(b_minkey + b, point_key(gidx, sidx[p]));
+}
+
+__global__ void __launch_bounds__(DB_THREADS) dbt_bucket_list_kernel(int64_t n_cells, const int* __restrict__ b_ncore,
+                                                                    int* __restrict__ cb_list, int* __restrict__ n_cb) {
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < n_cells && b_ncore[b] > 0) cb_list[atomicAdd(n_cb, 1)] = (int)b;
+}
+
+// One warp per bucket A that holds core points: connect it to every earlier bucket B (B < A) of its window.
+template <int DIM>
+__global__ void __launch_bounds__(DB_THREADS) dbt_union_kernel(Sorted s, DbGrid g, const int* __restrict__ cb_list,
+                                                              const int* __restrict__ n_cb, const uint8_t* __restrict__ core,
+                                                              const int* __restrict__ b_ncore, int* __restrict__ b_parent,
+                                                              double eps2, unsigned long long* __restrict__ ctr) {
+    const unsigned lane = rb_lane();
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int total = *n_cb;
+    unsigned long long tests = 0;
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += n_warps) {
+        const int A = cb_list[w];
+        const CellPos c = decode_cell(g, A);
+        const Window win = window_of<DIM>(g, c);
+        const int a0 = s.cell_start[A], a1 = s.cell_start[A + 1];
+        const int nx = win.x1 - win.x0 + 1, ny = win.y1 - win.y0 + 1, nz = win.z1 - win.z0 + 1, ntw = win.t1 - win.t0 + 1;
+        const int n_off = nx * ny * nz * ntw;
+        for (int o0 = 0; o0 < n_off; o0 += 32) {
+            // every lane looks at one bucket of the window; the warp then handles the ones that matter
+            int B = -1;
+            bool same_cell = false;
+            const int o = o0 + (int)lane;
+            if (o < n_off) {
+                int r = o;
+                const int xx = win.x0 + r % nx; r /= nx;
+                const int yy = win.y0 + r % ny; r /= ny;
+                const int zz = win.z0 + r % nz; r /= nz;
+                const int tt = win.t0 + r;
+                const int b = ((tt * g.n[2] + zz) * g.n[1] + yy) * g.n[0] + xx;
+                if (b < A && __ldg(b_ncore + b) > 0) { B = b; same_cell = xx == c.cx && yy == c.cy && zz == c.cz; }
+            }
+            if (B >= 0 && same_cell) { uf_union(b_parent, A, B); B = -1; }     // same cell inside the time window: connected
+            unsigned todo = __ballot_sync(0xffffffffu, B >= 0);
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int Bw = __shfl_sync(0xffffffffu, B, src);
+                int ra = 0, rb = 0;
+                if (lane == 0) { ra = uf_find(b_parent, A); rb = uf_find(b_parent, Bw); }
+                if (__shfl_sync(0xffffffffu, ra == rb, 0)) continue;
+                // one core-core pair within eps connects the two buckets
+                const int b0 = s.cell_start[Bw], b1 = s.cell_start[Bw + 1];
+                bool found = false;
+                for (int ia = a0; ia < a1 && !found; ++ia) {
+                    if (core[ia] != 1) continue;
+                    const Pt<DIM> pa = load_pt<DIM>(s, ia);
+                    for (int jb = b0; jb < b1; jb += 32) {
+                        const int q = jb + (int)lane;
+                        bool ok = false;
+                        if (q < b1 && core[q] == 1) { ++tests; ok = near_enough<DIM>(pa, load_pt<DIM>(s, q), eps2); }
+                        if (__any_sync(0xffffffffu, ok)) { found = true; break; }
+                    }
+                }
+                if (found && lane == 0) uf_union(b_parent, A, Bw);
+            }
+        }
+    }
+    add_counter(ctr, tests);
+}
+
+__global__ void __launch_bounds__(DB_THREADS) dbt_compmin_kernel(const int* __restrict__ cb_list, const int* __restrict__ n_cb,
+                                                                int* __restrict__ b_parent, long long* __restrict__ b_minkey) {
+    const int total = *n_cb;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int b = cb_list[i];
+        const int r = uf_find_ro(b_parent, b);
+        if (r != b) { b_parent[b] = r; atomicMin(b_minkey + r, b_minkey[b]); }
+    }
+}
+
+__global__ void __launch_bounds__(DB_THREADS) dbt_keyout_kernel(int n, const uint8_t* __restrict__ core, const int* __restrict__ scell,
+                                                               const int* __restrict__ sidx, const int* __restrict__ b_parent,
+                                                               const long long* __restrict__ b_minkey, long long* __restrict__ comp_key) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    long long k = -1;
+    if (core[p] == 1) { const int b = scell[p]; k = b_minkey[b_parent[b]]; }   // parents were flattened by dbt_compmin_kernel
+    comp_key[sidx[p]] = k;
+}
+
+// sorted copy of the core labels + the label of every bucket that holds cores (all its cores share it)
+__global__ void __launch_bounds__(DB_THREADS) db_gather_labels_kernel(int n, const uint8_t* __restrict__ core, const int* __restrict__ sidx,
+                                                                     const int* __restrict__ scell, const int32_t* __restrict__ core_label,
+                                                                     int* __restrict__ slabel, int* __restrict__ b_label) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    int lab = -1;
+    if (core[p] == 1) { lab = core_label[sidx[p]]; if (b_label) b_label[scell[p]] = lab; }
+    slabel[p] = lab;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(DB_THREADS) dbt_border_kernel(Sorted s, DbGrid g, int n, double eps2, const uint8_t* __restrict__ core,
+                                                               const int* __restrict__ slabel, const int* __restrict__ sidx,
+                                                               const int* __restrict__ b_ncore, const int* __restrict__ core_start,
+                                                               const int* __restrict__ b_label, int32_t* __restrict__ labels,
+                                                               unsigned long long* __restrict__ ctr) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long tests = 0;
+    if (p < n) {
+        int out = core[p] == 1 ? slabel[p] : -1;
+        if (core[p] == 0) {
+            const int cell = s.cell[p];
+            const CellPos c = decode_cell(g, cell);
+            const Window w = window_of<DIM>(g, c);
+            const int per_t = g.n[0] * g.n[1] * g.n[2];
+            const int sp = cell - c.tb * per_t;
+            int best = INT_MAX;
+            // cores of the own spatial cell inside the time window are neighbours
+            for (int tt = w.t0; tt <= w.t1; ++tt) {
+                const int b = tt * per_t + sp;
+                if (b_ncore[b] > 0) best = min(best, b_label[b]);
+            }
+            if (best != 0) {
+                const Pt<DIM> a = load_pt<DIM>(s, p);
+                for (int tt = w.t0; tt <= w.t1 && best != 0; ++tt)
+                    for (int zz = w.z0; zz <= w.z1 && best != 0; ++zz)
+                        for (int yy = w.y0; yy <= w.y1 && best != 0; ++yy) {
+                            const int row = ((tt * g.n[2] + zz) * g.n[1] + yy) * g.n[0];
+                            if (core_start[row + w.x1 + 1] == core_start[row + w.x0]) continue;      // no core in this row
+                            for (int xx = w.x0; xx <= w.x1; ++xx) {
+                                const int b = row + xx;
+                                if (b_ncore[b] == 0 || (xx == c.cx && yy == c.cy && zz == c.cz)) continue;
+                                const int lb = b_label[b];
+                                if (lb >= best) continue;                 // only a smaller id can change the answer
+                                for (int q = s.cell_start[b]; q < s.cell_start[b + 1]; ++q) {
+                                    if (core[q] != 1) continue;
+                                    ++tests;
+                                    if (near_enough<DIM>(a, load_pt<DIM>(s, q), eps2)) { best = lb; break; }
+                                }
+                            }
+                        }
+            }
+            if (best != INT_MAX) out = best;
+        }
+        labels[sidx[p]] = out;
+    }
+    add_counter(ctr, tests);
+}
+
+// ======================================================================================================
+// shared phase kernels
+// ======================================================================================================
+__global__ void __launch_bounds__(DB_THREADS) db_core_out_kernel(int n, const uint8_t* __restrict__ core, const int* __restrict__ sidx,
+                                                                uint8_t* __restrict__ core_out) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) core_out[sidx[p]] = core[p] == 1;
+}
+
+__global__ void __launch_bounds__(DB_THREADS) db_core_in_kernel(int n, const uint8_t* __restrict__ core_in, const int* __restrict__ sidx,
+                                                               uint8_t* __restrict__ core) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) core[p] = core_in[sidx[p]] ? 1 : (core[p] == 2 ? 2 : 0);
+}
+
+// single-GPU canonical numbering: the smallest core point of a component has key == its own index
+__global__ void __launch_bounds__(DB_THREADS) db_rootflag_kernel(int n, const long long* __restrict__ comp_key, int* __restrict__ flags) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = comp_key[i] == (long long)i;
+}
+
+__global__ void __launch_bounds__(DB_THREADS) db_rank_labels_kernel(int n, const long long* __restrict__ comp_key, const int* __restrict__ rank,
+                                                                   int32_t* __restrict__ labels) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long k = comp_key[i];
+    labels[i] = k >= 0 ? rank[k] : -1;
+}
+
+__global__ void __launch_bounds__(DB_THREADS) db_relabel_kernel(int64_t n, const long long* __restrict__ keys, const long long* __restrict__ table_keys,
+                                                               const int32_t* __restrict__ table_ids, int64_t m, int32_t* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long k = keys[i];
+    int32_t id = -1;
+    if (k >= 0 && m > 0) {
+        int64_t lo = 0, hi = m;                                   // first entry >= k
+        while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (table_keys[mid] < k) lo = mid + 1; else hi = mid; }
+        if (lo < m && table_keys[lo] == k) id = table_ids[lo];
+    }
+    out[i] = id;
 }
 
 template <typename T>
@@ -322,9 +632,10 @@ int scratch(rb_ctx* ctx, rb_slot slot, size_t count, T** out) {
     return rc;
 }
 
-// Host side: choose cell size / time binning so that the dense cell table stays affordable.
+// Host side: choose the grid. Tight cells when the times are integers and the bucket table fits the budget;
+// otherwise cells at least eps wide, coarsened until the table fits.
 int choose_grid(const float mn[4], const float mx[4], bool times_integer, int dim, int64_t n, double eps_space,
-                float eps_time, DbGrid* g, double* cell_out, double* wt_out) {
+                float eps_time, int mode_opt, DbGrid* g, double* cell_out, double* wt_out) {
     double ext[3] = {0, 0, 0};
     for (int k = 0; k < 3; ++k) { g->lo[k] = 0; g->n[k] = 1; }
     for (int k = 0; k < dim; ++k) {
@@ -334,23 +645,49 @@ int choose_grid(const float mn[4], const float mx[4], bool times_integer, int di
     }
     double text = (double)mx[3] - (double)mn[3];
     if (!(text >= 0) || !isfinite(text)) { rb_set_error("rb_stdbscan: non-finite times"); return RB_ERR_ARG; }
+    const double budget = fmin(fmax(16.0 * (double)n, 1048576.0), 134217728.0);
+    double et = (double)eps_time;
+    g->dim = dim;
+    g->tmin = mn[3];
+    g->tight = 0;
+    g->R = 1;
+
+    // ---- tight grid ---------------------------------------------------------------------------------
+    if (mode_opt != 1 && times_integer && eps_space > 0 && et >= 0) {
+        const double cell = eps_space * (1.0 - 1e-9) / sqrt((double)dim);
+        double total = 1;
+        for (int k = 0; k < dim; ++k) total *= floor(ext[k] / cell) + 1;
+        const double nt = floor(text) + 1;
+        total *= nt;
+        if (total <= budget) {
+            for (int k = 0; k < dim; ++k) g->n[k] = (int)(floor(ext[k] / cell) + 1);
+            g->nt = (int)nt;
+            g->inv_cell = 1.0 / cell;
+            g->inv_wt = 1.0;
+            g->tr = (int)fmin(floor(et), 1e6);
+            g->R = dim == 1 ? 1 : 2;                     // ceil(sqrt(dim)) cells cover eps
+            g->tight = 1;
+            *cell_out = cell;
+            *wt_out = 1.0;
+            return RB_OK;
+        }
+    }
+    if (mode_opt == 2) { rb_set_error("rb_stdbscan: tight grid required (dbscan_mode=2) but not applicable"); return RB_ERR_ARG; }
+
+    // ---- general grid ---------------------------------------------------------------------------------
     double max_ext = fmax(ext[0], fmax(ext[1], ext[2]));
     double cell = eps_space > 0 ? eps_space * (1.0 + 1e-7) : (max_ext > 0 ? max_ext / 1024.0 : 1.0);
     if (!(cell > 0) || !isfinite(cell)) cell = 1.0;
-    // time bins
     double wt; int tr;
-    bool unit_bins = false;
-    double et = (double)eps_time;
     if (!(et >= 0)) et = 0;                                 // negative eps_time: nothing matches anyway
     if (times_integer) {
-        wt = 1.0; unit_bins = true;
+        wt = 1.0;
         tr = (int)fmin(floor(et), 1e6);
     } else if (et > 0) {
         wt = et * (1.0 + 1e-6); tr = 1;
     } else {
         wt = text > 0 ? text / 256.0 : 1.0; tr = 0;         // equal times always share a bin
     }
-    const double budget = fmin(fmax(16.0 * (double)n, 1048576.0), 134217728.0);
     for (int iter = 0; iter < 200; ++iter) {
         double total = 1;
         for (int k = 0; k < dim; ++k) { double c = floor(ext[k] / cell) + 1; total *= c; }
@@ -366,7 +703,6 @@ int choose_grid(const float mn[4], const float mx[4], bool times_integer, int di
         for (int k = 0; k < dim; ++k) per_axis = fmax(per_axis, floor(ext[k] / cell) + 1);
         if (nt / (2.0 * tr + 1.0) > per_axis / 3.0 && nt > 1) {
             wt *= 2.0;
-            if (unit_bins) { unit_bins = false; }
             tr = (int)fmin(floor(et / wt) + 1, 1e6);
         } else {
             cell *= 2.0;
@@ -374,117 +710,281 @@ int choose_grid(const float mn[4], const float mx[4], bool times_integer, int di
         if (iter == 199) { rb_set_error("rb_stdbscan: could not fit a cell table"); return RB_ERR_ARG; }
     }
     g->inv_cell = 1.0 / cell;
-    g->tmin = mn[3];
     g->inv_wt = 1.0 / wt;
     g->tr = tr;
-    g->dim = dim;
     *cell_out = cell;
     *wt_out = wt;
     return RB_OK;
 }
 
+}  // namespace
+
+// ---- plan: everything the phases share, owned by the ctx ------------------------------------------------
+struct rb_db_plan {
+    bool valid = false;
+    int dim = 0;
+    int n = 0;
+    DbGrid g;
+    int64_t n_cells = 0;
+    double eps2 = 0, cell = 0, wt = 0;
+    float eps_t = 0;
+    int min_samples = 0;
+    bool have_cores = false, have_components = false;
+    // device arrays (scratch slots of the ctx)
+    int *cell_start = nullptr, *sidx = nullptr, *scell = nullptr, *parent = nullptr, *flags = nullptr, *rank = nullptr, *slabel = nullptr;
+    int *b_ncore = nullptr, *b_parent = nullptr, *b_label = nullptr, *core_start = nullptr, *cb_list = nullptr;
+    long long *minkey = nullptr, *b_minkey = nullptr, *comp_key = nullptr;
+    float *sx = nullptr, *sy = nullptr, *sz = nullptr, *st = nullptr;
+    uint8_t* core = nullptr;
+    int* d_misc = nullptr;                       // [0..15] bounds, then counters
+    unsigned long long* d_ctr = nullptr;         // count, union, border tests; [3] low word = n_clusters
+    int* d_ncb = nullptr;
+};
+
+void rb_db_plan_free(rb_ctx* ctx) {
+    delete ctx->db_plan;
+    ctx->db_plan = nullptr;
+}
+
+namespace {
+
+Sorted sorted_view(const rb_db_plan& P) { return Sorted{P.sx, P.sy, P.sz, P.st, P.scell, P.cell_start}; }
+
 template <int DIM>
-int run_dbscan(rb_ctx* ctx, const DbPoints& pts, int64_t n64, double eps_space, float eps_time, int min_samples,
-               int32_t* labels, uint8_t* core_out, int64_t* n_clusters, cudaStream_t stream) {
+int plan_build(rb_ctx* ctx, rb_db_plan& P, const DbPoints& pts, int64_t n64, double eps_space, float eps_time, int min_samples,
+               cudaStream_t stream) {
     const int n = (int)n64;
     const unsigned blocks = (unsigned)rb_div_up(n, DB_THREADS);
+    P.valid = false;
+    P.dim = DIM; P.n = n; P.eps2 = eps_space * eps_space; P.eps_t = eps_time; P.min_samples = min_samples;
+    P.have_cores = P.have_components = false;
 
     // 1. bounds -> host
-    int* d_bounds;
-    RB_TRY(scratch(ctx, RB_S_MISC, 64, &d_bounds));
-    unsigned long long* d_ctr = (unsigned long long*)(d_bounds + 16);      // 3 counters + n_clusters slot
-    db_bounds_init<<<1, 32, 0, stream>>>(d_bounds);
+    RB_TRY(scratch(ctx, RB_S_MISC, 64, &P.d_misc));
+    P.d_ctr = (unsigned long long*)(P.d_misc + 16);
+    P.d_ncb = P.d_misc + 32;
+    db_bounds_init<<<1, 32, 0, stream>>>(P.d_misc);
     RB_LAUNCH_CHECK(ctx);
-    RB_CUDA(cudaMemsetAsync(d_ctr, 0, sizeof(unsigned long long) * 4, stream));
+    RB_CUDA(cudaMemsetAsync(P.d_ctr, 0, sizeof(unsigned long long) * 4, stream));
     int bblocks = (int)(blocks < (unsigned)ctx->sm_count * 8 ? blocks : (unsigned)ctx->sm_count * 8);
-    db_bounds_kernel<<<bblocks, DB_THREADS, 0, stream>>>(pts, DIM, n64, d_bounds);
+    db_bounds_kernel<<<bblocks, DB_THREADS, 0, stream>>>(pts, DIM, n64, P.d_misc);
     RB_LAUNCH_CHECK(ctx);
     int* h = (int*)ctx->pinned;
-    RB_CUDA(cudaMemcpyAsync(h, d_bounds, sizeof(int) * 9, cudaMemcpyDeviceToHost, stream));
+    RB_CUDA(cudaMemcpyAsync(h, P.d_misc, sizeof(int) * 9, cudaMemcpyDeviceToHost, stream));
     RB_CUDA(cudaStreamSynchronize(stream));
     float mn[4], mx[4];
     for (int k = 0; k < 4; ++k) { mn[k] = ord2f(h[k]); mx[k] = ord2f(h[4 + k]); }
-    bool times_integer = h[8] == 0;
+    const bool times_integer = h[8] == 0;
 
     // 2. grid
-    DbGrid g;
-    double cell, wt;
-    RB_TRY(choose_grid(mn, mx, times_integer, DIM, n64, eps_space, eps_time, &g, &cell, &wt));
-    const int64_t n_cells = (int64_t)g.n[0] * g.n[1] * g.n[2] * g.nt;
+    RB_TRY(choose_grid(mn, mx, times_integer, DIM, n64, eps_space, eps_time, ctx->opt_dbscan_mode, &P.g, &P.cell, &P.wt));
+    const DbGrid& g = P.g;
+    P.n_cells = (int64_t)g.n[0] * g.n[1] * g.n[2] * g.nt;
 
-    // 3. counting sort into the cell table
-    int *cell_id, *slot, *cell_start, *sidx, *scell, *parent, *minorig, *flags, *rank, *slabel;
-    float *sx, *sy, *sz, *st;
-    uint8_t* core;
+    // 3. counting sort into the bucket table
+    int *cell_id, *slot;
     RB_TRY(scratch(ctx, RB_S_CELL_ID, (size_t)n, &cell_id));
     RB_TRY(scratch(ctx, RB_S_CELL_FILL, (size_t)n, &slot));
-    RB_TRY(scratch(ctx, RB_S_CELL_START, (size_t)n_cells + 1, &cell_start));
-    RB_TRY(scratch(ctx, RB_S_SORT_IDX, (size_t)n * 2, &sidx));
-    scell = sidx + n;
-    RB_TRY(scratch(ctx, RB_S_SX, (size_t)n, &sx));
-    RB_TRY(scratch(ctx, RB_S_SY, (size_t)n, &sy));
-    RB_TRY(scratch(ctx, RB_S_SZ, (size_t)n, &sz));
-    RB_TRY(scratch(ctx, RB_S_ST, (size_t)n, &st));
-    RB_TRY(scratch(ctx, RB_S_CORE, (size_t)n, &core));
-    RB_TRY(scratch(ctx, RB_S_PARENT, (size_t)n, &parent));
-    RB_TRY(scratch(ctx, RB_S_MINORIG, (size_t)n, &minorig));
-    RB_TRY(scratch(ctx, RB_S_FLAGS, (size_t)n, &flags));
-    RB_TRY(scratch(ctx, RB_S_RANK, (size_t)n, &rank));
-    RB_TRY(scratch(ctx, RB_S_SLABEL, (size_t)n, &slabel));
+    RB_TRY(scratch(ctx, RB_S_CELL_START, (size_t)P.n_cells + 1, &P.cell_start));
+    RB_TRY(scratch(ctx, RB_S_SORT_IDX, (size_t)n * 2, &P.sidx));
+    P.scell = P.sidx + n;
+    RB_TRY(scratch(ctx, RB_S_SX, (size_t)n, &P.sx));
+    RB_TRY(scratch(ctx, RB_S_SY, (size_t)n, &P.sy));
+    RB_TRY(scratch(ctx, RB_S_SZ, (size_t)n, &P.sz));
+    RB_TRY(scratch(ctx, RB_S_ST, (size_t)n, &P.st));
+    RB_TRY(scratch(ctx, RB_S_CORE, (size_t)n, &P.core));
+    RB_TRY(scratch(ctx, RB_S_PARENT, (size_t)n, &P.parent));
+    RB_TRY(scratch(ctx, RB_S_MINORIG, (size_t)n, &P.minkey));
+    RB_TRY(scratch(ctx, RB_S_FLAGS, (size_t)n + 1, &P.flags));
+    RB_TRY(scratch(ctx, RB_S_RANK, (size_t)n + 1, &P.rank));
+    RB_TRY(scratch(ctx, RB_S_SLABEL, (size_t)n, &P.slabel));
+    RB_TRY(scratch(ctx, RB_S_COMP_KEY, (size_t)n, &P.comp_key));
+    if (g.tight) {
+        RB_TRY(scratch(ctx, RB_S_B_NCORE, (size_t)P.n_cells + 1, &P.b_ncore));
+        RB_TRY(scratch(ctx, RB_S_B_PARENT, (size_t)P.n_cells, &P.b_parent));
+        RB_TRY(scratch(ctx, RB_S_B_LABEL, (size_t)P.n_cells, &P.b_label));
+        RB_TRY(scratch(ctx, RB_S_B_MINKEY, (size_t)P.n_cells, &P.b_minkey));
+        RB_TRY(scratch(ctx, RB_S_CORE_START, (size_t)P.n_cells + 1, &P.core_start));
+        RB_TRY(scratch(ctx, RB_S_CB_LIST, (size_t)(P.n_cells < n ? P.n_cells : n) + 1, &P.cb_list));
+    }
+    RB_CUDA(cudaMemsetAsync(P.cell_start, 0, sizeof(int) * ((size_t)P.n_cells + 1), stream));
+    db_cell_kernel<<<blocks, DB_THREADS, 0, stream>>>(pts, g, n64, cell_id, slot, P.cell_start);
+    RB_LAUNCH_CHECK(ctx);
+    RB_TRY(rb_exclusive_scan_i32(ctx, P.cell_start, P.cell_start, P.n_cells + 1, nullptr, stream));
+    db_scatter_kernel<<<blocks, DB_THREADS, 0, stream>>>(pts, DIM, n64, cell_id, slot, P.cell_start, P.sidx, P.scell, P.sx, P.sy, P.sz,
+                                                        P.st);
+    RB_LAUNCH_CHECK(ctx);
+    P.valid = true;
+    return RB_OK;
+}
 
-    RB_CUDA(cudaMemsetAsync(cell_start, 0, sizeof(int) * ((size_t)n_cells + 1), stream));
-    db_cell_kernel<<<blocks, DB_THREADS, 0, stream>>>(pts, g, n64, cell_id, slot, cell_start);
+template <int DIM>
+int phase_cores(rb_ctx* ctx, rb_db_plan& P, cudaStream_t stream) {
+    const unsigned blocks = (unsigned)rb_div_up(P.n, DB_THREADS);
+    const Sorted s = sorted_view(P);
+    if (P.g.tight) dbt_count_kernel<DIM><<<blocks, DB_THREADS, 0, stream>>>(s, P.g, P.n, P.eps2, P.min_samples, P.core, P.d_ctr + 0);
+    else dbg_count_kernel<DIM><<<blocks, DB_THREADS, 0, stream>>>(s, P.g, P.n, P.eps2, P.eps_t, P.min_samples, P.core, P.d_ctr + 0);
     RB_LAUNCH_CHECK(ctx);
-    RB_TRY(rb_exclusive_scan_i32(ctx, cell_start, cell_start, n_cells + 1, nullptr, stream));
-    db_scatter_kernel<<<blocks, DB_THREADS, 0, stream>>>(pts, DIM, n64, cell_id, slot, cell_start, sidx, scell, sx, sy, sz, st);
-    RB_LAUNCH_CHECK(ctx);
+    P.have_cores = true;
+    P.have_components = false;
+    return RB_OK;
+}
 
-    // 4. neighbour count -> core flags
-    Sorted s{sx, sy, sz, st, scell, cell_start};
-    const double eps2 = eps_space * eps_space;
-    db_count_kernel<DIM><<<blocks, DB_THREADS, 0, stream>>>(s, g, n, eps2, eps_time, min_samples, core, parent, d_ctr + 0);
-    RB_LAUNCH_CHECK(ctx);
+template <int DIM>
+int phase_components(rb_ctx* ctx, rb_db_plan& P, const long long* gidx, cudaStream_t stream) {
+    const int n = P.n;
+    const unsigned blocks = (unsigned)rb_div_up(n, DB_THREADS);
+    const Sorted s = sorted_view(P);
+    if (P.g.tight) {
+        const unsigned cblocks = (unsigned)rb_div_up(P.n_cells + 1, DB_THREADS);
+        dbt_bucket_init_kernel<<<cblocks, DB_THREADS, 0, stream>>>(P.n_cells, P.b_ncore, P.b_parent, P.b_minkey, P.d_ncb);
+        RB_LAUNCH_CHECK(ctx);
+        dbt_bucket_stats_kernel<<<blocks, DB_THREADS, 0, stream>>>(n, P.core, P.scell, P.sidx, gidx, P.b_ncore, P.b_minkey);
+        RB_LAUNCH_CHECK(ctx);
+        dbt_bucket_list_kernel<<<cblocks, DB_THREADS, 0, stream>>>(P.n_cells, P.b_ncore, P.cb_list, P.d_ncb);
+        RB_LAUNCH_CHECK(ctx);
+        RB_TRY(rb_exclusive_scan_i32(ctx, P.b_ncore, P.core_start, P.n_cells + 1, nullptr, stream));
+        const int64_t max_buckets = P.n_cells < n ? P.n_cells : n;
+        const int64_t want = rb_div_up(max_buckets * 32, DB_THREADS);
+        const unsigned ublocks = (unsigned)(want < (int64_t)ctx->sm_count * 8 ? (want > 0 ? want : 1) : (int64_t)ctx->sm_count * 8);
+        dbt_union_kernel<DIM><<<ublocks, DB_THREADS, 0, stream>>>(s, P.g, P.cb_list, P.d_ncb, P.core, P.b_ncore, P.b_parent, P.eps2,
+                                                                  P.d_ctr + 1);
+        RB_LAUNCH_CHECK(ctx);
+        const int64_t want2 = rb_div_up(max_buckets, DB_THREADS);
+        const unsigned mblocks = (unsigned)(want2 < (int64_t)ctx->sm_count * 8 ? (want2 > 0 ? want2 : 1) : (int64_t)ctx->sm_count * 8);
+        dbt_compmin_kernel<<<mblocks, DB_THREADS, 0, stream>>>(P.cb_list, P.d_ncb, P.b_parent, P.b_minkey);
+        RB_LAUNCH_CHECK(ctx);
+        dbt_keyout_kernel<<<blocks, DB_THREADS, 0, stream>>>(n, P.core, P.scell, P.sidx, P.b_parent, P.b_minkey, P.comp_key);
+        RB_LAUNCH_CHECK(ctx);
+    } else {
+        dbg_init_kernel<<<blocks, DB_THREADS, 0, stream>>>(n, P.parent, P.minkey);
+        RB_LAUNCH_CHECK(ctx);
+        dbg_union_kernel<DIM><<<blocks, DB_THREADS, 0, stream>>>(s, P.g, n, P.eps2, P.eps_t, P.core, P.parent, P.d_ctr + 1);
+        RB_LAUNCH_CHECK(ctx);
+        dbg_minkey_kernel<<<blocks, DB_THREADS, 0, stream>>>(n, P.core, P.parent, P.sidx, gidx, P.minkey);
+        RB_LAUNCH_CHECK(ctx);
+        dbg_keyout_kernel<<<blocks, DB_THREADS, 0, stream>>>(n, P.core, P.parent, P.sidx, P.minkey, P.comp_key);
+        RB_LAUNCH_CHECK(ctx);
+    }
+    P.have_components = true;
+    return RB_OK;
+}
 
-    // 5. union-find over core-core edges, canonical numbering
-    db_union_kernel<DIM><<<blocks, DB_THREADS, 0, stream>>>(s, g, n, eps2, eps_time, core, parent, d_ctr + 1);
+template <int DIM>
+int phase_assign(rb_ctx* ctx, rb_db_plan& P, const int32_t* core_label, int32_t* labels, cudaStream_t stream) {
+    const int n = P.n;
+    const unsigned blocks = (unsigned)rb_div_up(n, DB_THREADS);
+    const Sorted s = sorted_view(P);
+    db_gather_labels_kernel<<<blocks, DB_THREADS, 0, stream>>>(n, P.core, P.sidx, P.scell, core_label, P.slabel,
+                                                              P.g.tight ? P.b_label : nullptr);
     RB_LAUNCH_CHECK(ctx);
-    RB_CUDA(cudaMemsetAsync(minorig, 0x7f, sizeof(int) * (size_t)n, stream));
-    RB_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)n, stream));
-    db_minorig_kernel<<<blocks, DB_THREADS, 0, stream>>>(n, core, parent, sidx, minorig);
+    if (P.g.tight)
+        dbt_border_kernel<DIM><<<blocks, DB_THREADS, 0, stream>>>(s, P.g, n, P.eps2, P.core, P.slabel, P.sidx, P.b_ncore, P.core_start,
+                                                                  P.b_label, labels, P.d_ctr + 2);
+    else
+        dbg_border_kernel<DIM><<<blocks, DB_THREADS, 0, stream>>>(s, P.g, n, P.eps2, P.eps_t, P.core, P.slabel, P.sidx, labels,
+                                                                  P.d_ctr + 2);
     RB_LAUNCH_CHECK(ctx);
-    db_rootflag_kernel<<<blocks, DB_THREADS, 0, stream>>>(n, core, parent, minorig, flags);
-    RB_LAUNCH_CHECK(ctx);
-    int* d_total = (int*)(d_ctr + 3);
-    RB_TRY(rb_exclusive_scan_i32(ctx, flags, rank, n, d_total, stream));
-    db_label_kernel<<<blocks, DB_THREADS, 0, stream>>>(n, core, parent, minorig, rank, sidx, slabel, labels, core_out);
-    RB_LAUNCH_CHECK(ctx);
+    return RB_OK;
+}
 
-    // 6. border points
-    db_border_kernel<DIM><<<blocks, DB_THREADS, 0, stream>>>(s, g, n, eps2, eps_time, core, slabel, sidx, labels, d_ctr + 2);
-    RB_LAUNCH_CHECK(ctx);
+#define DB_DISPATCH(P, call)                                  \
+    ((P).dim == 3 ? call<3> : (P).dim == 2 ? call<2> : call<1>)
 
-    // 7. stats + cluster count to the host
+int fetch_stats(rb_ctx* ctx, rb_db_plan& P, int64_t* n_clusters, cudaStream_t stream) {
     unsigned long long* hc = (unsigned long long*)ctx->pinned;
-    RB_CUDA(cudaMemcpyAsync(hc, d_ctr, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, stream));
+    RB_CUDA(cudaMemcpyAsync(hc, P.d_ctr, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, stream));
     RB_CUDA(cudaStreamSynchronize(stream));
     rb_dbscan_stats& stt = ctx->last_stats;
     memset(&stt, 0, sizeof stt);
-    stt.n_points = n;
-    stt.n_cells = n_cells;
+    stt.n_points = P.n;
+    stt.n_cells = P.n_cells;
     stt.n_clusters = (int64_t)(int)(hc[3] & 0xffffffffu);
     stt.n_core = -1;
     stt.pair_tests_count = (int64_t)hc[0];
     stt.pair_tests_union = (int64_t)hc[1];
     stt.pair_tests_border = (int64_t)hc[2];
-    stt.cell_size = cell;
-    stt.time_bin = wt;
-    stt.dims[0] = g.n[0]; stt.dims[1] = g.n[1]; stt.dims[2] = g.n[2]; stt.dims[3] = g.nt;
-    stt.time_radius = g.tr;
+    stt.cell_size = P.cell;
+    stt.time_bin = P.wt;
+    stt.dims[0] = P.g.n[0]; stt.dims[1] = P.g.n[1]; stt.dims[2] = P.g.n[2]; stt.dims[3] = P.g.nt;
+    stt.time_radius = P.g.tr;
+    stt.tight = P.g.tight;
     if (n_clusters) *n_clusters = stt.n_clusters;
     return RB_OK;
 }
 
 }  // namespace
+
+extern "C" int rb_stdbscan_plan(rb_ctx* ctx, const float* x, const float* y, const float* z, int64_t stride,
+                                const float* times, int64_t n, double eps_space, float eps_time, int min_samples,
+                                void* stream_) {
+    RB_REQUIRE(ctx, "ctx is NULL");
+    RB_REQUIRE(n > 0 && n < ((int64_t)1 << 31) - 1, "point count out of range (1 .. 2^31-2)");
+    RB_REQUIRE(x && times, "NULL argument");
+    RB_REQUIRE(stride >= 1, "stride must be >= 1");
+    RB_REQUIRE(!(z && !y), "z without y");
+    RB_REQUIRE(eps_space >= 0 && isfinite(eps_space), "eps_space must be finite and >= 0");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!ctx->db_plan) ctx->db_plan = new rb_db_plan();
+    rb_db_plan& P = *ctx->db_plan;
+    DbPoints pts{x, y, z, stride, times};
+    if (z) return plan_build<3>(ctx, P, pts, n, eps_space, eps_time, min_samples, stream);
+    if (y) return plan_build<2>(ctx, P, pts, n, eps_space, eps_time, min_samples, stream);
+    return plan_build<1>(ctx, P, pts, n, eps_space, eps_time, min_samples, stream);
+}
+
+extern "C" int rb_stdbscan_cores(rb_ctx* ctx, uint8_t* core_out, void* stream_) {
+    RB_REQUIRE(ctx && ctx->db_plan && ctx->db_plan->valid, "rb_stdbscan_cores: no plan (call rb_stdbscan_plan first)");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    rb_db_plan& P = *ctx->db_plan;
+    RB_TRY(DB_DISPATCH(P, phase_cores)(ctx, P, stream));
+    if (core_out) {
+        db_core_out_kernel<<<(unsigned)rb_div_up(P.n, DB_THREADS), DB_THREADS, 0, stream>>>(P.n, P.core, P.sidx, core_out);
+        RB_LAUNCH_CHECK(ctx);
+    }
+    return RB_OK;
+}
+
+extern "C" int rb_stdbscan_set_cores(rb_ctx* ctx, const uint8_t* core_in, void* stream_) {
+    RB_REQUIRE(ctx && ctx->db_plan && ctx->db_plan->valid && ctx->db_plan->have_cores, "rb_stdbscan_set_cores: run rb_stdbscan_cores first");
+    RB_REQUIRE(core_in, "core_in is NULL");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    rb_db_plan& P = *ctx->db_plan;
+    db_core_in_kernel<<<(unsigned)rb_div_up(P.n, DB_THREADS), DB_THREADS, 0, stream>>>(P.n, core_in, P.sidx, P.core);
+    RB_LAUNCH_CHECK(ctx);
+    P.have_components = false;
+    return RB_OK;
+}
+
+extern "C" int rb_stdbscan_components(rb_ctx* ctx, const int64_t* global_index, int64_t* comp_key, void* stream_) {
+    RB_REQUIRE(ctx && ctx->db_plan && ctx->db_plan->valid && ctx->db_plan->have_cores, "rb_stdbscan_components: run rb_stdbscan_cores first");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    rb_db_plan& P = *ctx->db_plan;
+    RB_TRY(DB_DISPATCH(P, phase_components)(ctx, P, (const long long*)global_index, stream));
+    if (comp_key) RB_CUDA(cudaMemcpyAsync(comp_key, P.comp_key, sizeof(int64_t) * (size_t)P.n, cudaMemcpyDeviceToDevice, stream));
+    return RB_OK;
+}
+
+extern "C" int rb_stdbscan_assign(rb_ctx* ctx, const int32_t* core_label, int32_t* labels, void* stream_) {
+    RB_REQUIRE(ctx && ctx->db_plan && ctx->db_plan->valid && ctx->db_plan->have_cores, "rb_stdbscan_assign: run rb_stdbscan_cores first");
+    RB_REQUIRE(core_label && labels, "NULL argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    rb_db_plan& P = *ctx->db_plan;
+    return DB_DISPATCH(P, phase_assign)(ctx, P, core_label, labels, stream);
+}
+
+extern "C" int rb_relabel(rb_ctx* ctx, const int64_t* keys, int64_t n, const int64_t* table_keys, const int32_t* table_ids,
+                          int64_t m, int32_t* out, void* stream_) {
+    RB_REQUIRE(ctx, "ctx is NULL");
+    RB_REQUIRE(n >= 0 && m >= 0, "negative size");
+    if (n == 0) return RB_OK;
+    RB_REQUIRE(keys && out && (m == 0 || (table_keys && table_ids)), "NULL argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    db_relabel_kernel<<<(unsigned)rb_div_up(n, DB_THREADS), DB_THREADS, 0, stream>>>(n, (const long long*)keys, (const long long*)table_keys,
+                                                                                    table_ids, m, out);
+    RB_LAUNCH_CHECK(ctx);
+    return RB_OK;
+}
 
 extern "C" int rb_stdbscan(rb_ctx* ctx, const float* x, const float* y, const float* z, int64_t stride,
                            const float* times, int64_t n, double eps_space, float eps_time, int min_samples,
@@ -493,15 +993,22 @@ extern "C" int rb_stdbscan(rb_ctx* ctx, const float* x, const float* y, const fl
     RB_REQUIRE(n >= 0 && n < ((int64_t)1 << 31) - 1, "point count out of range");
     if (n_clusters) *n_clusters = 0;
     if (n == 0) return RB_OK;
-    RB_REQUIRE(x && times && labels, "NULL argument");
-    RB_REQUIRE(stride >= 1, "stride must be >= 1");
-    RB_REQUIRE(!(z && !y), "z without y");
-    RB_REQUIRE(eps_space >= 0 && isfinite(eps_space), "eps_space must be finite and >= 0");
+    RB_REQUIRE(labels, "labels is NULL");
     cudaStream_t stream = (cudaStream_t)stream_;
-    DbPoints pts{x, y, z, stride, times};
-    if (z) return run_dbscan<3>(ctx, pts, n, eps_space, eps_time, min_samples, labels, core, n_clusters, stream);
-    if (y) return run_dbscan<2>(ctx, pts, n, eps_space, eps_time, min_samples, labels, core, n_clusters, stream);
-    return run_dbscan<1>(ctx, pts, n, eps_space, eps_time, min_samples, labels, core, n_clusters, stream);
+    RB_TRY(rb_stdbscan_plan(ctx, x, y, z, stride, times, n, eps_space, eps_time, min_samples, stream_));
+    rb_db_plan& P = *ctx->db_plan;
+    RB_TRY(rb_stdbscan_cores(ctx, core, stream_));
+    RB_TRY(rb_stdbscan_components(ctx, nullptr, nullptr, stream_));
+    // canonical numbering: rank of every component's smallest core index
+    const unsigned blocks = (unsigned)rb_div_up(P.n, DB_THREADS);
+    db_rootflag_kernel<<<blocks, DB_THREADS, 0, stream>>>(P.n, P.comp_key, P.flags);
+    RB_LAUNCH_CHECK(ctx);
+    int* d_total = (int*)(P.d_ctr + 3);
+    RB_TRY(rb_exclusive_scan_i32(ctx, P.flags, P.rank, P.n, d_total, stream));
+    db_rank_labels_kernel<<<blocks, DB_THREADS, 0, stream>>>(P.n, P.comp_key, P.rank, labels);
+    RB_LAUNCH_CHECK(ctx);
+    RB_TRY(rb_stdbscan_assign(ctx, labels, labels, stream_));        // in place: core labels are copied before any write
+    return fetch_stats(ctx, P, n_clusters, stream);
 }
 
 extern "C" int rb_stdbscan_last_stats(rb_ctx* ctx, rb_dbscan_stats* out) {

@@ -268,6 +268,64 @@ def stdbscan(x: torch.Tensor, y: Optional[torch.Tensor], z: Optional[torch.Tenso
     return labels, ncl.value
 
 
+class StDbscanPhases:
+    """ST-DBSCAN in phases (``rb_stdbscan_plan`` / ``_cores`` / ``_set_cores`` / ``_components`` /
+    ``_assign``) for callers that exchange data in between — the time-sharded multi-GPU driver.
+    Points are SoA tensors (stride 1) or views into one row-major ``[N,D]`` tensor (stride D)."""
+
+    def __init__(self, x: torch.Tensor, y: Optional[torch.Tensor], z: Optional[torch.Tensor], times: torch.Tensor,
+                 eps_space: float, eps_time: float, min_samples: int, stride: int = 1, n: Optional[int] = None):
+        self.ctx = context(x.device.index)
+        self.n = times.numel() if n is None else int(n)
+        self.device = x.device
+        for name, t in (("x", x), ("y", y), ("z", z), ("times", times)):
+            if t is not None and (not t.is_cuda or t.dtype != torch.float32):
+                raise RadarB200Error(f"{name} must be a float32 CUDA tensor")
+        if self.n > 0:
+            check(self.ctx.lib.rb_stdbscan_plan(self.ctx.handle, ptr(x), ptr(y), ptr(z), int(stride), ptr(times), self.n,
+                                                float(eps_space), float(np.float32(eps_time)), int(min_samples),
+                                                stream_ptr()), "rb_stdbscan_plan")
+
+    def cores(self) -> torch.Tensor:
+        core = torch.empty(max(self.n, 1), dtype=torch.uint8, device=self.device)[:self.n]
+        if self.n > 0:
+            check(self.ctx.lib.rb_stdbscan_cores(self.ctx.handle, ptr(core), stream_ptr()), "rb_stdbscan_cores")
+        return core
+
+    def set_cores(self, core: torch.Tensor) -> None:
+        if self.n > 0:
+            check(self.ctx.lib.rb_stdbscan_set_cores(self.ctx.handle, ptr(_dev(core, torch.uint8, "core")), stream_ptr()),
+                  "rb_stdbscan_set_cores")
+
+    def components(self, global_index: Optional[torch.Tensor] = None) -> torch.Tensor:
+        key = torch.empty(max(self.n, 1), dtype=torch.int64, device=self.device)[:self.n]
+        if self.n > 0:
+            gi = None if global_index is None else _dev(global_index, torch.int64, "global_index")
+            check(self.ctx.lib.rb_stdbscan_components(self.ctx.handle, ptr(gi), ptr(key), stream_ptr()),
+                  "rb_stdbscan_components")
+        return key
+
+    def assign(self, core_label: torch.Tensor) -> torch.Tensor:
+        labels = torch.empty(max(self.n, 1), dtype=torch.int32, device=self.device)[:self.n]
+        if self.n > 0:
+            check(self.ctx.lib.rb_stdbscan_assign(self.ctx.handle, ptr(_dev(core_label, torch.int32, "core_label")),
+                                                  ptr(labels), stream_ptr()), "rb_stdbscan_assign")
+        return labels
+
+
+def relabel(keys: torch.Tensor, table_keys: torch.Tensor, table_ids: torch.Tensor) -> torch.Tensor:
+    """``out[i] = table_ids[j]`` where ``table_keys[j] == keys[i]`` (sorted int64 table); -1 otherwise."""
+    ctx = context(keys.device.index)
+    keys = _dev(keys, torch.int64, "keys")
+    out = torch.empty(max(keys.numel(), 1), dtype=torch.int32, device=keys.device)[:keys.numel()]
+    if keys.numel():
+        tk = _dev(table_keys, torch.int64, "table_keys")
+        ti = _dev(table_ids, torch.int32, "table_ids")
+        check(ctx.lib.rb_relabel(ctx.handle, ptr(keys), keys.numel(), ptr(tk), ptr(ti), tk.numel(), ptr(out), stream_ptr()),
+              "rb_relabel")
+    return out
+
+
 def stdbscan_stats(device: Optional[int] = None) -> dict:
     ctx = context(device)
     st = _lib.DbscanStats()

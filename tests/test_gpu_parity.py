@@ -258,7 +258,18 @@ def test_device_pipeline_vs_golden(gpu):
 
 
 # ------------------------------------------------------------------------------- a7: ST-DBSCAN
-def test_stdbscan_random_cases_vs_reference_golden(gpu):
+@pytest.fixture(params=["auto", "general"])
+def db_mode(request, gpu):
+    """Run the ST-DBSCAN tests on both algorithms: auto (tight-cell buckets whenever the times are integers
+    and the table fits) and the general point-level one."""
+    from radar_point_cloud_tracking_b200 import _lib
+    ctx = _lib.context(0)
+    ctx.set_option("dbscan_mode", 0 if request.param == "auto" else 1)
+    yield request.param
+    ctx.set_option("dbscan_mode", 0)
+
+
+def test_stdbscan_random_cases_vs_reference_golden(gpu, db_mode):
     from radar_point_cloud_tracking_b200.clustering import st_dbscan
     g = golden("stdbscan_random")
     for k in range(24):
@@ -267,7 +278,7 @@ def test_stdbscan_random_cases_vs_reference_golden(gpu):
         assert got.dtype == np.int32 and np.array_equal(got, g[f"c{k}_labels"]), k
 
 
-def test_stdbscan_package_3d_case_vs_golden(gpu):
+def test_stdbscan_package_3d_case_vs_golden(gpu, db_mode):
     from radar_point_cloud_tracking_b200.clustering import st_dbscan
     g = golden("package")
     spec3 = syn.SweepSpec(**CLUSTER3D_SPEC)
@@ -279,7 +290,7 @@ def test_stdbscan_package_3d_case_vs_golden(gpu):
     assert np.array_equal(st_dbscan(np.concatenate(pts), np.concatenate(tms), 5.0, 1.0, 10), g["cluster3d_labels"])
 
 
-def test_stdbscan_known_answers(gpu):
+def test_stdbscan_known_answers(gpu, db_mode):
     """radar-pipeline-rs/src/processors/clustering.rs:502-597 + edge cases."""
     from radar_point_cloud_tracking_b200.clustering import st_dbscan
     sq = [[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0]]
@@ -305,7 +316,7 @@ def test_stdbscan_known_answers(gpu):
 
 @pytest.mark.parametrize("n,frames,eps_s,eps_t,ms,dim", [(60000, 40, 8.0, 2.0, 15, 2), (40000, 3, 5.0, 1.0, 10, 3),
                                                           (30000, 200, 3.0, 0.5, 4, 2), (20000, 6, 6.0, 2.5, 8, 2)])
-def test_stdbscan_vs_c_oracle_medium(gpu, n, frames, eps_s, eps_t, ms, dim):
+def test_stdbscan_vs_c_oracle_medium(gpu, db_mode, n, frames, eps_s, eps_t, ms, dim):
     """Larger seeded problems against the C oracle: identical labels and core sets."""
     rng = np.random.default_rng(n + frames)
     span = 400.0
@@ -327,9 +338,49 @@ def test_stdbscan_vs_c_oracle_medium(gpu, n, frames, eps_s, eps_t, ms, dim):
     assert ncl == want.max() + 1
     st = gpu.stdbscan_stats()
     assert st["n_points"] == n and st["pair_tests_count"] > 0
+    if db_mode == "general" or eps_t != int(eps_t):
+        assert st["tight"] == 0
+    elif dim == 2:
+        assert st["tight"] == 1                      # (the 3-D case exceeds the bucket budget at this n)
 
 
-def test_stdbscan_sparse_frame_ids_and_coarsening(gpu):
+def test_stdbscan_phases_and_global_keys(gpu, db_mode):
+    """The phase entry points reproduce rb_stdbscan; component keys follow the caller's global indices;
+    overriding core flags changes the components accordingly (what the sharded driver relies on)."""
+    rng = np.random.default_rng(77)
+    n = 30000
+    coords = (rng.random((n, 2)) * 300).astype(np.float32)
+    centres = (rng.random((25, 2)) * 300).astype(np.float32)
+    coords[: n // 2] = (centres[rng.integers(0, 25, n // 2)] + rng.normal(0, 2.5, (n // 2, 2))).astype(np.float32)
+    times = rng.integers(0, 12, n).astype(np.float32)
+    want, want_core = st_dbscan_c(coords, times, 6.0, 2.0, 12)
+    d = torch.device("cuda:0")
+    flat = torch.from_numpy(coords).to(d).view(-1)
+    ph = gpu.StDbscanPhases(flat, flat[1:], None, torch.from_numpy(times).to(d), 6.0, 2.0, 12, stride=2, n=n)
+    core = ph.cores()
+    assert np.array_equal(core.cpu().numpy().astype(bool), want_core)
+    gidx = torch.arange(n, dtype=torch.int64, device=d) * 3 + 1000          # any increasing global numbering
+    key = ph.components(gidx).cpu().numpy()
+    assert np.array_equal(key >= 0, want_core)
+    # key = smallest global index among the component's cores  <=>  canonical label order
+    for lab in range(want.max() + 1):
+        members = np.flatnonzero((want == lab) & want_core)
+        assert np.all(key[members] == members.min() * 3 + 1000)
+    uniq = np.unique(key[key >= 0])
+    table_k = torch.from_numpy(uniq).to(d)
+    table_i = torch.arange(len(uniq), dtype=torch.int32, device=d)
+    core_label = gpu.relabel(torch.from_numpy(key).to(d), table_k, table_i)
+    labels = ph.assign(core_label).cpu().numpy()
+    assert np.array_equal(labels, want)
+    # demote every core point of cluster 0 that lives at t >= 6: keys/labels follow the new core set
+    mod_core = want_core.copy()
+    mod_core[(want == 0) & (times >= 6)] = False
+    ph.set_cores(torch.from_numpy(mod_core.astype(np.uint8)).to(d))
+    key2 = ph.components(None).cpu().numpy()
+    assert np.array_equal(key2 >= 0, mod_core)
+
+
+def test_stdbscan_sparse_frame_ids_and_coarsening(gpu, db_mode):
     """Frame ids with huge gaps and a tiny eps over a wide extent force the grid to coarsen."""
     from radar_point_cloud_tracking_b200.clustering import st_dbscan
     rng = np.random.default_rng(1)
