@@ -307,6 +307,7 @@ def run_ours(args):
                                "note": "whole rb_spoke_to_points call (3 launches) timed with CUDA events inside the "
                                        "timed region; bytes = echo + spoke tables + 16 B per kept point"}},
         "stdbscan": {"pair_tests_per_step": st["pair_tests_count"] + st["pair_tests_union"] + st["pair_tests_border"],
+                     "pair_tests": [st["pair_tests_count"], st["pair_tests_union"], st["pair_tests_border"]], "tight": st["tight"],
                      "cells": st["n_cells"], "dims": st["dims"], "time_radius": st["time_radius"]},
         "gpu_launches": launches,
         "clocks": clocks.summary(),

@@ -97,11 +97,18 @@ __global__ void __launch_bounds__(DB_THREADS) db_bounds_kernel(DbPoints p, int d
         mx[k] = __reduce_max_sync(0xffffffffu, mx[k]);
     }
     nonint = __any_sync(0xffffffffu, nonint);
+    __shared__ int s_mn[4], s_mx[4], s_non;
+    if (threadIdx.x < 4) { s_mn[threadIdx.x] = INT_MAX; s_mx[threadIdx.x] = INT_MIN; }
+    if (threadIdx.x == 0) s_non = 0;
+    __syncthreads();
     if (rb_lane() == 0) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { atomicMin(out + k, mn[k]); atomicMax(out + 4 + k, mx[k]); }
-        if (nonint) atomicOr(out + 8, 1);
+        for (int k = 0; k < 4; ++k) { atomicMin(s_mn + k, mn[k]); atomicMax(s_mx + k, mx[k]); }
+        if (nonint) atomicOr(&s_non, 1);
     }
+    __syncthreads();
+    if (threadIdx.x < 4) { atomicMin(out + threadIdx.x, s_mn[threadIdx.x]); atomicMax(out + 4 + threadIdx.x, s_mx[threadIdx.x]); }
+    if (threadIdx.x == 0 && s_non) atomicOr(out + 8, 1);
 }
 
 __global__ void db_bounds_init(int* out) {
@@ -435,18 +442,120 @@ __global__ void __launch_bounds__(DB_THREADS) dbt_bucket_stats_kernel(int n, con
     atomicMin(b_minkey + b, point_key(gidx, sidx[p]));
 }
 
+// list of the buckets that hold core points; b_label[b] temporarily holds the bucket's slot in the list
 __global__ void __launch_bounds__(DB_THREADS) dbt_bucket_list_kernel(int64_t n_cells, const int* __restrict__ b_ncore,
-                                                                    int* __restrict__ cb_list, int* __restrict__ n_cb) {
+                                                                    int* __restrict__ cb_list, int* __restrict__ n_cb,
+                                                                    int* __restrict__ cb_slot, int* __restrict__ cb_bbox) {
     int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < n_cells && b_ncore[b] > 0) cb_list[atomicAdd(n_cb, 1)] = (int)b;
+    if (b < n_cells && b_ncore[b] > 0) {
+        const int slot = atomicAdd(n_cb, 1);
+        cb_list[slot] = (int)b;
+        cb_slot[b] = slot;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { cb_bbox[slot * 6 + k] = INT_MAX; cb_bbox[slot * 6 + 3 + k] = INT_MIN; }
+    }
 }
 
-// One warp per bucket A that holds core points: connect it to every earlier bucket B (B < A) of its window.
+// bounding box of the core points of every listed bucket (order-preserving int encoding of the floats)
+template <int DIM>
+__global__ void __launch_bounds__(DB_THREADS) dbt_bucket_bbox_kernel(Sorted s, int n, const uint8_t* __restrict__ core,
+                                                                    const int* __restrict__ cb_slot, int* __restrict__ cb_bbox) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n || core[p] != 1) return;
+    int* bb = cb_bbox + (size_t)cb_slot[s.cell[p]] * 6;
+    const int ox = f2ord(s.x[p]);
+    atomicMin(bb + 0, ox); atomicMax(bb + 3, ox);
+    if (DIM > 1) { const int oy = f2ord(s.y[p]); atomicMin(bb + 1, oy); atomicMax(bb + 4, oy); }
+    if (DIM > 2) { const int oz = f2ord(s.z[p]); atomicMin(bb + 2, oz); atomicMax(bb + 5, oz); }
+}
+
+struct BBox { float lo[3], hi[3]; };
+template <int DIM>
+__device__ __forceinline__ BBox load_bbox(const int* __restrict__ cb_bbox, int slot) {
+    BBox b;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        b.lo[k] = k < DIM ? ord2f(__ldg(cb_bbox + (size_t)slot * 6 + k)) : 0.f;
+        b.hi[k] = k < DIM ? ord2f(__ldg(cb_bbox + (size_t)slot * 6 + 3 + k)) : 0.f;
+    }
+    return b;
+}
+// squared gap between two boxes / a point and a box, in the arithmetic of near_enough (float64, no FMA): a lower
+// bound of every pair distance it covers, so "gap > eps^2" proves that no pair can pass the exact test
+template <int DIM>
+__device__ __forceinline__ double box_gap2(const BBox& a, const BBox& b) {
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+        double d = fmax(fmax((double)a.lo[k] - (double)b.hi[k], (double)b.lo[k] - (double)a.hi[k]), 0.0);
+        acc = __dadd_rn(acc, __dmul_rn(d, d));
+    }
+    return acc;
+}
+template <int DIM>
+__device__ __forceinline__ double point_gap2(const Pt<DIM>& p, const BBox& b) {
+    const float v[3] = {p.x, p.y, p.z};
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+        double d = fmax(fmax((double)b.lo[k] - (double)v[k], (double)v[k] - (double)b.hi[k]), 0.0);
+        acc = __dadd_rn(acc, __dmul_rn(d, d));
+    }
+    return acc;
+}
+
+// Same spatial cell, other time bins: all cores are neighbours; linking a bucket to the NEAREST earlier bin
+// (inside the time window) that holds cores is enough - that bucket links further back itself. The links form
+// chains along time, so no union-find is needed here: parent = that bucket; dbt_flatten_kernel then points
+// every bucket at the head of its chain.
+__global__ void __launch_bounds__(DB_THREADS) dbt_link_time_kernel(DbGrid g, const int* __restrict__ cb_list, const int* __restrict__ n_cb,
+                                                                  const int* __restrict__ b_ncore, int* __restrict__ b_parent) {
+    const int total = *n_cb;
+    const int per_t = g.n[0] * g.n[1] * g.n[2];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int A = cb_list[i];
+        const int tb = A / per_t;
+        const int t0 = max(tb - g.tr, 0);
+        for (int tt = tb - 1; tt >= t0; --tt) {
+            const int b = A - (tb - tt) * per_t;
+            if (b_ncore[b] > 0) { b_parent[A] = b; break; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(DB_THREADS) dbt_flatten_kernel(const int* __restrict__ cb_list, const int* __restrict__ n_cb,
+                                                                int* __restrict__ b_parent) {
+    const int total = *n_cb;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int b = cb_list[i];
+        const int r = uf_find_ro(b_parent, b);
+        if (r != b) b_parent[b] = r;                  // only roots are written: concurrent read-only finds stay valid
+    }
+}
+
+// One warp per bucket A that holds core points: connect it to the earlier buckets (B < A) in the OTHER cells of
+// its window: every lane takes one bucket of the window, resolves its root and drops it when it already
+//    shares A's root (the common case, done for 32 buckets at once); the warp then searches the remaining
+//    ones for one core-core pair within eps - cells at Chebyshev distance 1 before the far ones, so that the
+//    far ones are usually connected through a near one by the time they are looked at.
+// root lookup through the L1-cached path, for FILTERING only: a cached parent may be stale, but sets only ever
+// merge, so "same root" read from stale data is still true; "different" is re-checked with uf_find.
+__device__ __forceinline__ int uf_find_cached(const int* __restrict__ parent, int a) {
+    int cur = a;
+    while (true) {
+        int p = __ldca(parent + cur);
+        if (p == cur) return cur;
+        cur = p;
+    }
+}
+
 template <int DIM>
 __global__ void __launch_bounds__(DB_THREADS) dbt_union_kernel(Sorted s, DbGrid g, const int* __restrict__ cb_list,
                                                               const int* __restrict__ n_cb, const uint8_t* __restrict__ core,
                                                               const int* __restrict__ b_ncore, int* __restrict__ b_parent,
+                                                              const int* __restrict__ cb_slot, const int* __restrict__ cb_bbox,
                                                               double eps2, unsigned long long* __restrict__ ctr) {
+    constexpr int MAX_SLOTS = DIM == 3 ? 4 : 4;              // offsets per lane: ceil((2R+1)^DIM * (2tr+1) / 32) handled in chunks
     const unsigned lane = rb_lane();
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     const int total = *n_cb;
@@ -458,43 +567,77 @@ __global__ void __launch_bounds__(DB_THREADS) dbt_union_kernel(Sorted s, DbGrid 
         const int a0 = s.cell_start[A], a1 = s.cell_start[A + 1];
         const int nx = win.x1 - win.x0 + 1, ny = win.y1 - win.y0 + 1, nz = win.z1 - win.z0 + 1, ntw = win.t1 - win.t0 + 1;
         const int n_off = nx * ny * nz * ntw;
-        for (int o0 = 0; o0 < n_off; o0 += 32) {
-            // every lane looks at one bucket of the window; the warp then handles the ones that matter
-            int B = -1;
-            bool same_cell = false;
-            const int o = o0 + (int)lane;
-            if (o < n_off) {
-                int r = o;
-                const int xx = win.x0 + r % nx; r /= nx;
-                const int yy = win.y0 + r % ny; r /= ny;
-                const int zz = win.z0 + r % nz; r /= nz;
-                const int tt = win.t0 + r;
-                const int b = ((tt * g.n[2] + zz) * g.n[1] + yy) * g.n[0] + xx;
-                if (b < A && __ldg(b_ncore + b) > 0) { B = b; same_cell = xx == c.cx && yy == c.cy && zz == c.cz; }
+        const int root_a = uf_find_cached(b_parent, A);
+        const BBox box_a = load_bbox<DIM>(cb_bbox, w);
+        for (int base = 0; base < n_off; base += 32 * MAX_SLOTS) {
+            // ---- gather: every lane looks at up to MAX_SLOTS buckets of the window (independent loads) ----
+            int cand[MAX_SLOTS];
+#pragma unroll
+            for (int k = 0; k < MAX_SLOTS; ++k) {
+                cand[k] = -1;
+                const int o = base + k * 32 + (int)lane;
+                if (o < n_off) {
+                    int r = o;
+                    const int xx = win.x0 + r % nx; r /= nx;
+                    const int yy = win.y0 + r % ny; r /= ny;
+                    const int zz = win.z0 + r % nz; r /= nz;
+                    const int tt = win.t0 + r;
+                    const int cheb = max(abs(xx - c.cx), max(abs(yy - c.cy), abs(zz - c.cz)));
+                    const int bkt = ((tt * g.n[2] + zz) * g.n[1] + yy) * g.n[0] + xx;
+                    if (cheb > 0 && bkt < A && __ldg(b_ncore + bkt) > 0) cand[k] = bkt | (cheb > 1 ? 0x40000000 : 0);
+                }
             }
-            if (B >= 0 && same_cell) { uf_union(b_parent, A, B); B = -1; }     // same cell inside the time window: connected
-            unsigned todo = __ballot_sync(0xffffffffu, B >= 0);
-            while (todo) {
-                const int src = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const int Bw = __shfl_sync(0xffffffffu, B, src);
-                int ra = 0, rb = 0;
-                if (lane == 0) { ra = uf_find(b_parent, A); rb = uf_find(b_parent, Bw); }
-                if (__shfl_sync(0xffffffffu, ra == rb, 0)) continue;
-                // one core-core pair within eps connects the two buckets
-                const int b0 = s.cell_start[Bw], b1 = s.cell_start[Bw + 1];
-                bool found = false;
-                for (int ia = a0; ia < a1 && !found; ++ia) {
-                    if (core[ia] != 1) continue;
-                    const Pt<DIM> pa = load_pt<DIM>(s, ia);
-                    for (int jb = b0; jb < b1; jb += 32) {
-                        const int q = jb + (int)lane;
-                        bool ok = false;
-                        if (q < b1 && core[q] == 1) { ++tests; ok = near_enough<DIM>(pa, load_pt<DIM>(s, q), eps2); }
-                        if (__any_sync(0xffffffffu, ok)) { found = true; break; }
+            // ---- filter: already connected (cached roots), or the boxes of the core points are more than eps apart ----
+#pragma unroll
+            for (int k = 0; k < MAX_SLOTS; ++k) {
+                if (cand[k] < 0) continue;
+                const int bk = cand[k] & 0x3fffffff;
+                if (uf_find_cached(b_parent, bk) == root_a) { cand[k] = -1; continue; }
+                if (box_gap2<DIM>(box_a, load_bbox<DIM>(cb_bbox, __ldg(cb_slot + bk))) > eps2) cand[k] = -1;
+            }
+            // ---- the rest: exact check, then one core-core pair within eps connects the two buckets;
+            //      cells at Chebyshev distance 1 first ----
+            for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+                for (int k = 0; k < MAX_SLOTS; ++k) {
+                    const bool mine = cand[k] >= 0 && ((cand[k] >> 30) & 1) == pass;
+                    unsigned todo = __ballot_sync(0xffffffffu, mine);
+                    while (todo) {
+                        const int src = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const int Bw = __shfl_sync(0xffffffffu, cand[k], src) & 0x3fffffff;
+                        int same = 0;
+                        if (lane == 0) same = uf_find(b_parent, A) == uf_find(b_parent, Bw);
+                        if (__shfl_sync(0xffffffffu, same, 0)) continue;
+                        const int b0 = s.cell_start[Bw], b1 = s.cell_start[Bw + 1];
+                        const BBox box_b = load_bbox<DIM>(cb_bbox, __ldg(cb_slot + Bw));
+                        bool found = false;
+                        for (int ia0 = a0; ia0 < a1 && !found; ia0 += 32) {
+                            // 32 points of A at a time: keep the core points that are within eps of B's box
+                            const int ia_l = ia0 + (int)lane;
+                            Pt<DIM> mine_a = {};
+                            bool use = false;
+                            if (ia_l < a1 && core[ia_l] == 1) { mine_a = load_pt<DIM>(s, ia_l); use = point_gap2<DIM>(mine_a, box_b) <= eps2; }
+                            unsigned act = __ballot_sync(0xffffffffu, use);
+                            while (act && !found) {
+                                const int la = __ffs(act) - 1;
+                                act &= act - 1;
+                                Pt<DIM> pa;
+                                pa.x = __shfl_sync(0xffffffffu, mine_a.x, la);
+                                pa.y = DIM > 1 ? __shfl_sync(0xffffffffu, mine_a.y, la) : 0.f;
+                                pa.z = DIM > 2 ? __shfl_sync(0xffffffffu, mine_a.z, la) : 0.f;
+                                pa.t = 0.f;
+                                for (int jb = b0; jb < b1; jb += 32) {
+                                    const int q = jb + (int)lane;
+                                    bool ok = false;
+                                    if (q < b1 && core[q] == 1) { ++tests; ok = near_enough<DIM>(pa, load_pt<DIM>(s, q), eps2); }
+                                    if (__any_sync(0xffffffffu, ok)) { found = true; break; }
+                                }
+                            }
+                        }
+                        if (found && lane == 0) uf_union(b_parent, A, Bw);
                     }
                 }
-                if (found && lane == 0) uf_union(b_parent, A, Bw);
             }
         }
     }
@@ -733,6 +876,7 @@ struct rb_db_plan {
     // device arrays (scratch slots of the ctx)
     int *cell_start = nullptr, *sidx = nullptr, *scell = nullptr, *parent = nullptr, *flags = nullptr, *rank = nullptr, *slabel = nullptr;
     int *b_ncore = nullptr, *b_parent = nullptr, *b_label = nullptr, *core_start = nullptr, *cb_list = nullptr;
+    int *cb_slot = nullptr, *cb_bbox = nullptr;
     long long *minkey = nullptr, *b_minkey = nullptr, *comp_key = nullptr;
     float *sx = nullptr, *sy = nullptr, *sz = nullptr, *st = nullptr;
     uint8_t* core = nullptr;
@@ -766,7 +910,8 @@ int plan_build(rb_ctx* ctx, rb_db_plan& P, const DbPoints& pts, int64_t n64, dou
     db_bounds_init<<<1, 32, 0, stream>>>(P.d_misc);
     RB_LAUNCH_CHECK(ctx);
     RB_CUDA(cudaMemsetAsync(P.d_ctr, 0, sizeof(unsigned long long) * 4, stream));
-    int bblocks = (int)(blocks < (unsigned)ctx->sm_count * 8 ? blocks : (unsigned)ctx->sm_count * 8);
+    const unsigned want_b = (unsigned)rb_div_up(n, DB_THREADS * 4);
+    int bblocks = (int)(want_b < (unsigned)ctx->sm_count * 4 ? want_b : (unsigned)ctx->sm_count * 4);
     db_bounds_kernel<<<bblocks, DB_THREADS, 0, stream>>>(pts, DIM, n64, P.d_misc);
     RB_LAUNCH_CHECK(ctx);
     int* h = (int*)ctx->pinned;
@@ -805,7 +950,9 @@ int plan_build(rb_ctx* ctx, rb_db_plan& P, const DbPoints& pts, int64_t n64, dou
         RB_TRY(scratch(ctx, RB_S_B_LABEL, (size_t)P.n_cells, &P.b_label));
         RB_TRY(scratch(ctx, RB_S_B_MINKEY, (size_t)P.n_cells, &P.b_minkey));
         RB_TRY(scratch(ctx, RB_S_CORE_START, (size_t)P.n_cells + 1, &P.core_start));
-        RB_TRY(scratch(ctx, RB_S_CB_LIST, (size_t)(P.n_cells < n ? P.n_cells : n) + 1, &P.cb_list));
+        RB_TRY(scratch(ctx, RB_S_CB_LIST, (size_t)(P.n_cells < n ? P.n_cells : n) * 7 + 8, &P.cb_list));
+        P.cb_bbox = P.cb_list + (size_t)(P.n_cells < n ? P.n_cells : n) + 1;
+        P.cb_slot = P.b_label;                   // the label array is free until the assign phase
     }
     RB_CUDA(cudaMemsetAsync(P.cell_start, 0, sizeof(int) * ((size_t)P.n_cells + 1), stream));
     db_cell_kernel<<<blocks, DB_THREADS, 0, stream>>>(pts, g, n64, cell_id, slot, P.cell_start);
@@ -841,17 +988,23 @@ int phase_components(rb_ctx* ctx, rb_db_plan& P, const long long* gidx, cudaStre
         RB_LAUNCH_CHECK(ctx);
         dbt_bucket_stats_kernel<<<blocks, DB_THREADS, 0, stream>>>(n, P.core, P.scell, P.sidx, gidx, P.b_ncore, P.b_minkey);
         RB_LAUNCH_CHECK(ctx);
-        dbt_bucket_list_kernel<<<cblocks, DB_THREADS, 0, stream>>>(P.n_cells, P.b_ncore, P.cb_list, P.d_ncb);
+        dbt_bucket_list_kernel<<<cblocks, DB_THREADS, 0, stream>>>(P.n_cells, P.b_ncore, P.cb_list, P.d_ncb, P.cb_slot, P.cb_bbox);
+        RB_LAUNCH_CHECK(ctx);
+        dbt_bucket_bbox_kernel<DIM><<<blocks, DB_THREADS, 0, stream>>>(s, n, P.core, P.cb_slot, P.cb_bbox);
         RB_LAUNCH_CHECK(ctx);
         RB_TRY(rb_exclusive_scan_i32(ctx, P.b_ncore, P.core_start, P.n_cells + 1, nullptr, stream));
         const int64_t max_buckets = P.n_cells < n ? P.n_cells : n;
         const int64_t want = rb_div_up(max_buckets * 32, DB_THREADS);
         const unsigned ublocks = (unsigned)(want < (int64_t)ctx->sm_count * 8 ? (want > 0 ? want : 1) : (int64_t)ctx->sm_count * 8);
-        dbt_union_kernel<DIM><<<ublocks, DB_THREADS, 0, stream>>>(s, P.g, P.cb_list, P.d_ncb, P.core, P.b_ncore, P.b_parent, P.eps2,
-                                                                  P.d_ctr + 1);
-        RB_LAUNCH_CHECK(ctx);
         const int64_t want2 = rb_div_up(max_buckets, DB_THREADS);
         const unsigned mblocks = (unsigned)(want2 < (int64_t)ctx->sm_count * 8 ? (want2 > 0 ? want2 : 1) : (int64_t)ctx->sm_count * 8);
+        dbt_link_time_kernel<<<mblocks, DB_THREADS, 0, stream>>>(P.g, P.cb_list, P.d_ncb, P.b_ncore, P.b_parent);
+        RB_LAUNCH_CHECK(ctx);
+        dbt_flatten_kernel<<<mblocks, DB_THREADS, 0, stream>>>(P.cb_list, P.d_ncb, P.b_parent);
+        RB_LAUNCH_CHECK(ctx);
+        dbt_union_kernel<DIM><<<ublocks, DB_THREADS, 0, stream>>>(s, P.g, P.cb_list, P.d_ncb, P.core, P.b_ncore, P.b_parent, P.cb_slot,
+                                                                  P.cb_bbox, P.eps2, P.d_ctr + 1);
+        RB_LAUNCH_CHECK(ctx);
         dbt_compmin_kernel<<<mblocks, DB_THREADS, 0, stream>>>(P.cb_list, P.d_ncb, P.b_parent, P.b_minkey);
         RB_LAUNCH_CHECK(ctx);
         dbt_keyout_kernel<<<blocks, DB_THREADS, 0, stream>>>(n, P.core, P.scell, P.sidx, P.b_parent, P.b_minkey, P.comp_key);
