@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=64, help="frames per rank and step")
+    ap.add_argument("--frames-per-step", type=int, default=128, help="frames per rank and step")
     ap.add_argument("--spokes", type=int, default=2048)
     ap.add_argument("--bins", type=int, default=1024)
     ap.add_argument("--seed", type=int, default=2025)
@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0)
+    ap.add_argument("--shard-profile", action="store_true", help="N>1: print per-stage wall-clock of the sharded driver to stderr")
     return ap.parse_args()
 
 
@@ -279,6 +280,12 @@ def run_ours(args):
                "ms_per_step": ms_e / e_steps}
         del host_echo
 
+    if args.shard_profile and world > 1:
+        pipe.profile, pipe.timings = True, {}
+        for _ in range(3):
+            pipe.run_device(echo, d_c, d_s, d_r, frame_ids)
+        pipe.profile = False
+        sys.stderr.write("rank %d shard stages (ms/step): %s\n" % (rank, {k: round(v / 3 * 1e3, 3) for k, v in pipe.timings.items()}))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -347,10 +354,30 @@ def run_reference(args):
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # exactly ONE line on stdout: libraries under us (NCCL's version banner, for one) write to fd 1, so fd 1
+    # points at stderr while the benchmark runs and is restored for the JSON line
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    buf = []
+    try:
+        import builtins
+        real_print = builtins.print
+        builtins.print = lambda *a, **k: buf.append(" ".join(str(x) for x in a)) if k.get("file") in (None, sys.stdout) else real_print(*a, **k)
+        try:
+            if args.impl == "reference":
+                run_reference(args)
+            else:
+                run_ours(args)
+        finally:
+            builtins.print = real_print
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    for line in buf:
+        print(line)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

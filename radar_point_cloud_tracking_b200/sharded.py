@@ -38,30 +38,35 @@ from .device import PointBatch
 
 
 # ------------------------------------------------------------------------------------------ stitching (host)
-def stitch_components(link_gidx: np.ndarray, link_key: np.ndarray, keys: np.ndarray
+def stitch_components(seg_keys: Sequence[Sequence[np.ndarray]], keys: Sequence[np.ndarray]
                       ) -> Tuple[np.ndarray, np.ndarray, int]:
     """Global cluster numbering from the ranks' local components.
 
-    ``keys``: every local component key of every rank (key = smallest global core index the rank saw
-    in that component). ``link_*``: for every copy of a boundary-zone core point (its owner's copy and
-    the neighbour's halo copy) the point's global index and the key of the local component it is in.
-    Copies of one point tie their components together. Returns ``(table_keys sorted, table_ids,
-    n_clusters)`` where the id of a component is the rank of its smallest global core index among
-    all components — the reference's numbering."""
+    ``keys[r]``: the distinct local component keys of rank r (key = smallest global core index the rank
+    saw in that component). ``seg_keys[r]`` = four arrays with the local key of every CORE point of rank r's
+    boundary zones, each in point order: ``[left halo, own first frames, own last frames, right halo]``.
+    Rank r's "own last frames" and rank r+1's "left halo" are the same points with the same core flags, in
+    the same order (likewise "right halo" / "own first frames"), so the two key arrays pair up position by
+    position: each pair ties two local components together. Returns ``(table_keys sorted, table_ids,
+    n_clusters)`` where the id of a component is the rank of its smallest global core index among all
+    components — the reference's numbering."""
     from scipy.sparse import coo_matrix
     from scipy.sparse.csgraph import connected_components
 
-    link_gidx = np.asarray(link_gidx, dtype=np.int64)
-    link_key = np.asarray(link_key, dtype=np.int64)
-    uniq = np.unique(np.concatenate([np.asarray(keys, dtype=np.int64), link_key]))
+    uniq = np.unique(np.concatenate([np.asarray(k, dtype=np.int64) for k in keys] + [np.zeros(0, np.int64)]))
     m = len(uniq)
     if m == 0:
         return uniq, np.zeros(0, np.int32), 0
-    node = np.searchsorted(uniq, link_key)
-    order = np.argsort(link_gidx, kind="stable")
-    g, nd = link_gidx[order], node[order]
-    same = g[1:] == g[:-1]
-    a, b = nd[:-1][same], nd[1:][same]
+    pa, pb = [np.zeros(0, np.int64)], [np.zeros(0, np.int64)]
+    for r in range(len(seg_keys) - 1):
+        for mine, theirs in ((seg_keys[r][2], seg_keys[r + 1][0]), (seg_keys[r][3], seg_keys[r + 1][1])):
+            if len(mine) != len(theirs):
+                raise RadarB200Error("stitch: boundary zones of neighbouring ranks do not match")
+            pa.append(np.asarray(mine, dtype=np.int64)); pb.append(np.asarray(theirs, dtype=np.int64))
+    a = np.searchsorted(uniq, np.concatenate(pa))
+    b = np.searchsorted(uniq, np.concatenate(pb))
+    pair = np.unique(a * m + b)                                 # few distinct component pairs
+    a, b = pair // m, pair % m
     graph = coo_matrix((np.ones(len(a), np.int8), (a, b)), shape=(m, m))
     ncomp, comp = connected_components(graph, directed=False)
     first = np.full(ncomp, m, dtype=np.int64)
@@ -90,8 +95,15 @@ class CudaEngine:
     def bounds(self, x, y) -> torch.Tensor:
         return self.dev.bounds(x, y)
 
+    def _edges(self, xe: np.ndarray, ye: np.ndarray):
+        key = (xe.tobytes(), ye.tobytes())
+        if getattr(self, "_edge_key", None) != key:              # one upload per distinct grid
+            both = torch.from_numpy(np.concatenate([xe, ye])).to(self.device)
+            self._edge_key, self._edge_dev = key, (both[:len(xe)], both[len(xe):])
+        return self._edge_dev
+
     def land_accumulate(self, batch: PointBatch, xe: np.ndarray, ye: np.ndarray):
-        d_xe, d_ye = torch.from_numpy(xe).to(self.device), torch.from_numpy(ye).to(self.device)
+        d_xe, d_ye = self._edges(xe, ye)
         n = batch.n
         if n == 0:
             return (torch.zeros((len(xe) - 1, len(ye) - 1), dtype=torch.int32, device=self.device),
@@ -102,7 +114,7 @@ class CudaEngine:
         return self.dev.land_cells(count, isum, built, persistence, min_intensity)
 
     def land_filter(self, batch: PointBatch, xe, ye, land) -> PointBatch:
-        d_xe, d_ye = torch.from_numpy(xe).to(self.device), torch.from_numpy(ye).to(self.device)
+        d_xe, d_ye = self._edges(xe, ye)
         return self.dev.land_filter(batch, d_xe, d_ye, land)
 
     def expand_frame_times(self, frame_off, frame_ids, n):
@@ -155,36 +167,35 @@ class ShardedDetection:
             from .pipeline import DetectionPipeline
             self.base = DetectionPipeline(self.cfg, self.device.index)       # spoke tables + ctx for the bench
         self._cap_hint = 0
+        self._gain_cache = None
+        self.profile = False               # True: synchronise and record wall-clock per stage in self.timings
+        self.timings = {}
+        self._t_last = None
+
+    def _tick(self, name: Optional[str]) -> None:
+        """Stage timer (diagnostics): time since the previous tick is booked under ``name``."""
+        if not self.profile:
+            return
+        import time
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+        now = time.perf_counter()
+        if name is not None and self._t_last is not None:
+            self.timings[name] = self.timings.get(name, 0.0) + (now - self._t_last)
+        self._t_last = now
 
     # ---- small collective helpers (tensors live on the engine's device) -----------------------------
     def _t(self, values, dtype) -> torch.Tensor:
         return torch.tensor(values, dtype=dtype, device=self.device)
 
-    def _all_reduce(self, t: torch.Tensor, op) -> torch.Tensor:
-        if self.world > 1:
-            dist.all_reduce(t, op=op, group=self.group)
-        return t
-
-    def _all_gather_i64(self, value: int) -> np.ndarray:
+    def _all_gather_vec(self, vec: np.ndarray, dtype=torch.float64) -> np.ndarray:
+        """All-gather one small fixed-length vector per rank -> ``[world, len]`` on the host (ONE collective)."""
+        mine = torch.from_numpy(np.ascontiguousarray(vec)).to(dtype).to(self.device)
         if self.world == 1:
-            return np.array([value], dtype=np.int64)
-        out = torch.zeros(self.world, dtype=torch.int64, device=self.device)
-        dist.all_gather_into_tensor(out, self._t([value], torch.int64), group=self.group)
+            return mine.cpu().numpy()[None]
+        out = torch.empty((self.world, mine.numel()), dtype=dtype, device=self.device)
+        dist.all_gather_into_tensor(out, mine[None], group=self.group)
         return out.cpu().numpy()
-
-    def _gather_varlen(self, t: torch.Tensor) -> Optional[List[np.ndarray]]:
-        """Gather 1-D int64 tensors of different lengths to rank 0 (returns the list there, else None)."""
-        sizes = self._all_gather_i64(t.numel())
-        if self.world == 1:
-            return [t.cpu().numpy()]
-        cap = int(sizes.max())
-        pad = torch.zeros(max(cap, 1), dtype=torch.int64, device=self.device)
-        pad[:t.numel()] = t
-        bufs = [torch.zeros_like(pad) for _ in range(self.world)] if self.rank == 0 else None
-        dist.gather(pad, bufs, dst=0, group=self.group)
-        if self.rank != 0:
-            return None
-        return [b[:int(s)].cpu().numpy() for b, s in zip(bufs, sizes)]
 
     def _exchange(self, to_left: Optional[torch.Tensor], to_right: Optional[torch.Tensor],
                   n_from_left: int, n_from_right: int, dtype, width: int = 1):
@@ -214,34 +225,41 @@ class ShardedDetection:
         cfg, eng = self.cfg, self.engine
         F, G, S, E = echo.shape
         ids = np.asarray(frame_ids, dtype=np.int64)
-        sweep_gain = self._t(list(cfg.gains) * F, torch.int32)
-        raw = eng.spoke_to_points(echo.reshape(F * G, S, E), cos_tab, sin_tab, range_res, sweep_gain,
+        self._tick(None)
+        if self._gain_cache is None or self._gain_cache.numel() != F * G:
+            self._gain_cache = self._t(list(cfg.gains) * F, torch.int32)
+        raw = eng.spoke_to_points(echo.reshape(F * G, S, E), cos_tab, sin_tab, range_res, self._gain_cache,
                                   cfg.intensity_threshold, cfg.point_stride, G, cap=self._cap_hint or None)
         self._cap_hint = max(self._cap_hint, int(raw.n * 1.25) + 1024)
+        self._tick("spoke")
 
         # ---- land / stationary persistence filter over ALL ranks' frames --------------------------
+        # collective 1: [frames built, points, xmin, xmax, ymin, ymax] of every rank (float64 holds them exactly)
         pts, land, edges = raw, None, None
         if cfg.land_filter:
             raw_off = raw.frame_off.cpu().numpy()
-            stats = self._all_reduce(self._t([int(np.count_nonzero(np.diff(raw_off))), raw.n], torch.int64), dist.ReduceOp.SUM)
-            built, n_all = (int(v) for v in stats.cpu().numpy())
+            mine = np.zeros(6, dtype=np.float64)
+            mine[0], mine[1] = np.count_nonzero(np.diff(raw_off)), raw.n
+            if raw.n > 0:
+                mine[2:] = eng.bounds(raw.x[:raw.n], raw.y[:raw.n]).cpu().numpy().astype(np.float64)
+            allv = self._all_gather_vec(mine)
+            built, n_all = int(allv[:, 0].sum()), int(allv[:, 1].sum())
             if n_all > 0 and built > cfg.land_min_frames:
-                if raw.n > 0:
-                    b = eng.bounds(raw.x[:raw.n], raw.y[:raw.n]).to(torch.float32)
-                    packed = torch.stack([b[0], -b[1], b[2], -b[3]])
-                else:
-                    packed = torch.full((4,), float("inf"), dtype=torch.float32, device=self.device)
-                packed = self._all_reduce(packed, dist.ReduceOp.MIN).cpu().numpy()
-                b4 = np.array([packed[0], -packed[1], packed[2], -packed[3]], dtype=np.float32)
+                have = allv[allv[:, 1] > 0]
+                b4 = np.array([have[:, 2].min(), have[:, 3].max(), have[:, 4].min(), have[:, 5].max()], dtype=np.float32)
                 xe, ye = trk.grid_edges_from_bounds(b4, cfg.land_resolution)
                 count, isum = eng.land_accumulate(raw, xe, ye)
-                self._all_reduce(count, dist.ReduceOp.SUM)
-                self._all_reduce(isum, dist.ReduceOp.SUM)
+                if self.world > 1:
+                    # collective 2: counts and sums in ONE float64 all-reduce (counts < 2^53 stay exact)
+                    grids = torch.stack([count.to(torch.float64), isum])
+                    dist.all_reduce(grids, op=dist.ReduceOp.SUM, group=self.group)
+                    count, isum = grids[0].to(torch.int32), grids[1].contiguous()
                 land = eng.land_cells(count, isum, built, cfg.land_persistence, cfg.land_min_intensity)
                 if raw.n > 0:
                     pts = eng.land_filter(raw, xe, ye, land)
                 edges = (xe, ye)
 
+        self._tick("land")
         labels = torch.empty(0, dtype=torch.int32, device=self.device)
         n_clusters, halo = 0, (0, 0)
         if cluster:
@@ -253,49 +271,54 @@ class ShardedDetection:
         F = len(ids)
         n_own = pts.n
         h = int(math.floor(cfg.eps_time)) if cfg.eps_time >= 0 else 0
-        hh = min(h, F)
         if self.world > 1 and h > F:
             raise RadarB200Error(f"time shard of {F} frames is shorter than the eps_time halo ({h} frames)")
+        hh = min(h, F)
         off = pts.frame_off.cpu().numpy().astype(np.int64)
-        counts = self._all_gather_i64(n_own)
-        gbase = int(counts[:self.rank].sum())                      # global index of my first owned point
         lo_end, hi_start = int(off[hh]), int(off[F - hh])          # owned points [0, lo_end) go left, [hi_start, n) right
 
-        # ---- halo: headers (frame ids + per-frame counts + global base), then x/y ---------------------
-        def header(first_frame: int, start: int) -> torch.Tensor:
-            fr = np.arange(first_frame, first_frame + hh)
-            return self._t([gbase + start] + [int(ids[f]) for f in fr] + [int(off[f + 1] - off[f]) for f in fr], torch.int64)[None]
-
-        hl, hr = self._exchange(header(0, 0) if hh else None, header(F - hh, hi_start) if hh else None,
-                                (1 + 2 * hh) if hh else 0, (1 + 2 * hh) if hh else 0, torch.int64)
-        def parse(hd):
-            if hd is None:
-                return 0, np.zeros(0, np.int64), np.zeros(0, np.int64)
-            v = hd[0].cpu().numpy()
-            return int(v[0]), v[1:1 + hh], v[1 + hh:1 + 2 * hh]
-        lbase, lids, lcnt = parse(hl)
-        rbase, rids, rcnt = parse(hr)
+        # collective 3: per rank [points owned, start of the last-hh-frames zone, ids and per-frame counts of the
+        # first hh and last hh frames] -> global index bases and both neighbours' halo layouts at once
+        mine = np.concatenate([[n_own, hi_start], ids[:hh], np.diff(off)[:hh], ids[F - hh:], np.diff(off)[F - hh:]]).astype(np.int64)
+        meta = self._all_gather_vec(mine, torch.int64)
+        bases = np.concatenate([[0], np.cumsum(meta[:, 0])])
+        gbase = int(bases[self.rank])
+        lids = lcnt = rids = rcnt = np.zeros(0, np.int64)
+        lbase = rbase = 0
+        if self.rank > 0 and hh:                                    # left halo = the left neighbour's LAST hh frames
+            m = meta[self.rank - 1]
+            lids, lcnt, lbase = m[2 + 2 * hh:2 + 3 * hh], m[2 + 3 * hh:2 + 4 * hh], int(bases[self.rank - 1] + m[1])
+        if self.rank < self.world - 1 and hh:                       # right halo = the right neighbour's FIRST hh frames
+            m = meta[self.rank + 1]
+            rids, rcnt, rbase = m[2:2 + hh], m[2 + hh:2 + 2 * hh], int(bases[self.rank + 1])
         nl, nr = int(lcnt.sum()), int(rcnt.sum())
+        n_loc = nl + n_own + nr
+        if int(meta[:, 0].sum()) == 0:
+            return torch.empty(0, dtype=torch.int32, device=self.device), 0, (nl, nr)
+
         xy = torch.stack([pts.x[:n_own], pts.y[:n_own]]) if n_own else torch.zeros((2, 0), dtype=torch.float32, device=self.device)
         xl, xr = self._exchange(xy[:, :lo_end], xy[:, hi_start:], nl, nr, torch.float32, width=2)
+        self._tick("halo")
 
         # ---- local problem: [left halo | owned | right halo], times = frame ids --------------------------
-        parts_x = [t[0] for t in (xl,) if t is not None] + [xy[0]] + [t[0] for t in (xr,) if t is not None]
-        parts_y = [t[1] for t in (xl,) if t is not None] + [xy[1]] + [t[1] for t in (xr,) if t is not None]
-        X, Y = torch.cat(parts_x), torch.cat(parts_y)
-        n_loc = nl + n_own + nr
-        if n_loc == 0 or self._all_gather_i64(n_loc).sum() == 0:
-            return torch.empty(0, dtype=torch.int32, device=self.device), 0, (nl, nr)
+        XY = torch.cat([t for t in (xl, xy, xr) if t is not None], dim=1)
+        X, Y = XY[0].contiguous(), XY[1].contiguous()
         all_ids = np.concatenate([lids, ids, rids]).astype(np.float32)
         all_cnt = np.concatenate([lcnt, np.diff(off), rcnt]).astype(np.int64)
-        loc_off = self._t(np.concatenate([[0], np.cumsum(all_cnt)]).tolist(), torch.int64)
-        times = eng.expand_frame_times(loc_off, torch.from_numpy(all_ids).to(self.device), n_loc)
-        gidx = torch.cat([torch.arange(lbase, lbase + nl, dtype=torch.int64, device=self.device),
-                          torch.arange(gbase, gbase + n_own, dtype=torch.int64, device=self.device),
-                          torch.arange(rbase, rbase + nr, dtype=torch.int64, device=self.device)])
+        head = np.concatenate([[0], np.cumsum(all_cnt)]).astype(np.int64)
+        aux = torch.from_numpy(np.concatenate([head, all_ids.astype(np.int64)])).to(self.device)      # one upload
+        loc_off = aux[:len(head)]
+        times = eng.expand_frame_times(loc_off, aux[len(head):].to(torch.float32), n_loc) if n_loc else \
+            torch.zeros(0, dtype=torch.float32, device=self.device)
+        gidx = torch.arange(n_loc, dtype=torch.int64, device=self.device)
+        gidx[:nl] += lbase
+        gidx[nl:nl + n_own] += gbase - nl
+        gidx[nl + n_own:] += rbase - nl - n_own
+        self._tick("prep")
 
         ph = eng.phases(X, Y, times, cfg.eps_space, cfg.eps_time, cfg.min_samples) if n_loc else None
         core = ph.cores() if n_loc else torch.zeros(0, dtype=torch.uint8, device=self.device)
+        self._tick("plan+cores")
         # ---- exact core flags of the halo points come from their owners ----------------------------------
         own_core = core[nl:nl + n_own]
         cl, cr = self._exchange(own_core[None, :lo_end], own_core[None, hi_start:], nl, nr, torch.uint8)
@@ -308,40 +331,65 @@ class ShardedDetection:
             key = ph.components(gidx)
         else:
             key = torch.zeros(0, dtype=torch.int64, device=self.device)
+        self._tick("core-exchange+components")
 
         # ---- stitch on rank 0 ---------------------------------------------------------------------------------
-        zone = torch.zeros(n_loc, dtype=torch.bool, device=self.device)
-        zone[:nl + lo_end] = True                                   # left halo + my first frames
-        zone[nl + hi_start:] = True                                 # my last frames + right halo
-        link = zone & (key >= 0)
-        comp_keys = torch.unique(key[key >= 0]) if n_loc else key
-        g_gidx = self._gather_varlen(gidx[link])
-        g_key = self._gather_varlen(key[link])
-        g_all = self._gather_varlen(comp_keys)
-        if self.rank == 0:
-            tk, ti, ncl = stitch_components(np.concatenate(g_gidx), np.concatenate(g_key), np.concatenate(g_all))
-            meta = self._t([len(tk), ncl], torch.int64)
+        # what rank 0 needs from me: the local key of every CORE point of my four boundary zones (left halo, own
+        # first frames, own last frames, right halo - they pair up with the neighbours' zones by position) and my
+        # distinct component keys (= keys of the points that ARE their component's smallest core).
+        # One device->host read, then collectives 4 (sizes) and 5 (packed gather).
+        if n_loc:
+            zones = ((0, nl), (nl, nl + lo_end), (nl + hi_start, nl + n_own), (nl + n_own, n_loc))
+            is_core = key >= 0
+            seg_counts = [int(c) for c in torch.stack([is_core[a:b].sum() for a, b in zones]).cpu().numpy()]
+            parts = [key[a:b][is_core[a:b]] for a, b in zones] + [key[key == gidx]]
+            flat = torch.cat(parts).cpu().numpy()
+            segs = np.split(flat, np.cumsum(seg_counts))
+            my_segs, my_keys = segs[:4], segs[4]
         else:
-            meta = torch.zeros(2, dtype=torch.int64, device=self.device)
-        if self.world > 1:
-            dist.broadcast(meta, src=0, group=self.group)
-        m, ncl = (int(v) for v in meta.cpu().numpy())
-        if self.rank == 0:
-            table_k = torch.from_numpy(tk).to(self.device)
-            table_i = torch.from_numpy(ti).to(self.device)
+            my_segs, my_keys = [np.zeros(0, np.int64)] * 4, np.zeros(0, np.int64)
+        self._tick("select")
+        packed = np.concatenate(list(my_segs) + [my_keys]).astype(np.int64)
+        sizes = self._all_gather_vec(np.array([len(x) for x in my_segs] + [len(my_keys)], dtype=np.int64), torch.int64)
+        cap_keys = int(sizes[:, 4].sum())
+        table = np.zeros(2 + 2 * cap_keys, dtype=np.int64)
+        if self.world == 1:
+            tk, ti, ncl = stitch_components([my_segs], [my_keys])
         else:
-            table_k = torch.zeros(m, dtype=torch.int64, device=self.device)
-            table_i = torch.zeros(m, dtype=torch.int32, device=self.device)
-        if self.world > 1 and m > 0:
-            dist.broadcast(table_k, src=0, group=self.group)
-            dist.broadcast(table_i, src=0, group=self.group)
+            cap = int(sizes.sum(axis=1).max())
+            pad = torch.zeros(max(cap, 1), dtype=torch.int64, device=self.device)
+            pad[:len(packed)] = torch.from_numpy(packed).to(self.device)
+            bufs = [torch.empty_like(pad) for _ in range(self.world)] if self.rank == 0 else None
+            dist.gather(pad, bufs, dst=0, group=self.group)
+            self._tick("gather")
+            if self.rank == 0:
+                got = torch.stack(bufs).cpu().numpy()
+                all_segs, all_keys = [], []
+                for r in range(self.world):
+                    pieces = np.split(got[r, :int(sizes[r].sum())], np.cumsum(sizes[r])[:-1])
+                    all_segs.append(pieces[:4]); all_keys.append(pieces[4])
+                tk, ti, ncl = stitch_components(all_segs, all_keys)
+                table[0], table[1] = len(tk), ncl
+                table[2:2 + len(tk)] = tk
+                table[2 + cap_keys:2 + cap_keys + len(tk)] = ti
+            self._tick("stitch")
+            # collective 6: the key -> id table
+            t_table = torch.from_numpy(table).to(self.device)
+            dist.broadcast(t_table, src=0, group=self.group)
+            table = t_table.cpu().numpy()
+            m, ncl = int(table[0]), int(table[1])
+            tk, ti = table[2:2 + m], table[2 + cap_keys:2 + cap_keys + m].astype(np.int32)
+            self._tick("broadcast")
 
         # ---- labels of the owned points -------------------------------------------------------------------------
         if n_loc == 0:
-            return torch.empty(0, dtype=torch.int32, device=self.device), ncl, (nl, nr)
-        core_label = eng.relabel(key, table_k, table_i)
+            return torch.empty(0, dtype=torch.int32, device=self.device), int(ncl), (nl, nr)
+        core_label = eng.relabel(key, torch.from_numpy(np.ascontiguousarray(tk)).to(self.device),
+                                 torch.from_numpy(np.ascontiguousarray(ti, dtype=np.int32)).to(self.device))
         labels = ph.assign(core_label)
-        return labels[nl:nl + n_own].contiguous(), ncl, (nl, nr)
+        out = labels[nl:nl + n_own].contiguous()
+        self._tick("relabel+assign")
+        return out, int(ncl), (nl, nr)
 
     # ---- host entry (mirrors DetectionPipeline.run_host for this rank's block) -------------------------------
     def run_host(self, echo, angle_units, scale, frame_ids: Sequence[int], pinned: Optional[torch.Tensor] = None) -> dict:

@@ -229,9 +229,11 @@ def test_sharded_equals_single_process(tmp_path, world, cfg_kw):
 
 
 def test_stitch_components_known_answer():
-    # rank 0 sees components keyed 5 and 40; rank 1 sees 38 (same cluster as 40 through point 41) and 90
-    tk, ti, n = stitch_components(link_gidx=np.array([41, 41, 60]), link_key=np.array([40, 38, 90]),
-                                  keys=np.array([5, 40, 38, 90]))
+    e = np.zeros(0, np.int64)
+    # rank 0 sees components keyed 5 and 40; rank 1 sees 38 (the same cluster as 40: rank 0's last-zone core point
+    # keyed 40 is rank 1's left-halo point keyed 38) and 90
+    segs = [[e, e, np.array([40]), np.array([40, 40])], [np.array([38]), np.array([38, 38]), e, e]]
+    tk, ti, n = stitch_components(segs, [np.array([5, 40]), np.array([38, 90])])
     assert list(tk) == [5, 38, 40, 90] and list(ti) == [0, 1, 1, 2] and n == 3
-    tk, ti, n = stitch_components(np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.int64))
+    tk, ti, n = stitch_components([[e, e, e, e]], [e])
     assert len(tk) == 0 and n == 0
