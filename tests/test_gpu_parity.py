@@ -439,3 +439,96 @@ def test_abi_error_paths(gpu):
     n = C.c_int64(7)
     assert ctx.lib.rb_stdbscan(ctx.handle, None, None, None, 1, None, 0, 1.0, 1.0, 1, None, None, C.byref(n), None) == 0
     assert n.value == 0 and ctx.launch_count() > 0
+
+
+# ------------------------------------------------------------------------------- scale / stress properties
+def test_stdbscan_dense_clutter_both_algorithms_vs_oracle(gpu):
+    """Dense clutter (every point has hundreds of neighbours, BASELINE config 4 in miniature): the tight-cell
+    algorithm decides most pairs without a distance test; labels and core flags must still equal the C oracle
+    and the general algorithm, point for point."""
+    from radar_point_cloud_tracking_b200 import _lib
+    rng = np.random.default_rng(404)
+    n, frames = 50000, 4
+    coords = (rng.random((n, 2)) * 220).astype(np.float32)                 # ~1 point / m^2 / frame-ish
+    coords[:4000] = (rng.random((4000, 2)) * 40 + 400).astype(np.float32)    # a second, detached dense patch
+    coords[4000:4200] = (rng.random((200, 2)) * 3000 + 1000).astype(np.float32)   # isolated noise
+    times = rng.integers(0, frames, n).astype(np.float32)
+    want, want_core = st_dbscan_c(coords, times, 12.0, 2.0, 15)
+    assert want_core.mean() > 0.9 and want.max() >= 1
+    d = torch.device("cuda:0")
+    flat = torch.from_numpy(coords).to(d).view(-1)
+    ctx = _lib.context(0)
+    tests = {}
+    for mode in (0, 1):
+        ctx.set_option("dbscan_mode", mode)
+        try:
+            lab, core, ncl = gpu.stdbscan(flat, flat[1:], None, torch.from_numpy(times).to(d), 12.0, 2.0, 15, stride=2, n=n,
+                                          want_core=True)
+        finally:
+            ctx.set_option("dbscan_mode", 0)
+        st = gpu.stdbscan_stats()
+        assert st["tight"] == (1 if mode == 0 else 0)
+        tests[mode] = st["pair_tests_count"] + st["pair_tests_union"] + st["pair_tests_border"]
+        assert np.array_equal(core.cpu().numpy().astype(bool), want_core)
+        assert np.array_equal(lab.cpu().numpy(), want)
+    assert tests[0] * 5 < tests[1]                      # the shortcuts really skip most of the pair tests
+
+
+def test_land_filter_full_size_vs_torch_float64(gpu):
+    """24 full-size fused frames (2048 x 1024 x 3 gains): count grid, land mask and filtered points against a
+    torch float64 restatement (bucketize(right=True) == np.digitize) on the same device-resident points."""
+    from radar_point_cloud_tracking_b200.pipeline import DetectionConfig, DetectionPipeline
+    spec = syn.SweepSpec(seed=77, frames=24)
+    pipe = DetectionPipeline(DetectionConfig(), 0)
+    echo = gpu.synth_echo(spec)
+    c, s, r = pipe.spoke_tables(spec.angle_units(), spec.scale(), spec.frames, spec.bins)
+    d = echo.device
+    res = pipe.run_device(echo, *(torch.from_numpy(t).to(d) for t in (c, s, r)), cluster=False)
+    raw, pts = res.raw, res.points
+    n = raw.n
+    assert n > 200_000 and res.land is not None and 0 < pts.n < n
+    xe, ye = (torch.from_numpy(e).to(d) for e in res.edges)
+    x64, y64 = raw.x[:n].double(), raw.y[:n].double()
+    ix = (torch.bucketize(x64, xe, right=True) - 1).clamp(0, len(xe) - 2)
+    iy = (torch.bucketize(y64, ye, right=True) - 1).clamp(0, len(ye) - 2)
+    cell = ix * (len(ye) - 1) + iy
+    cells = (len(xe) - 1) * (len(ye) - 1)
+    count = torch.bincount(cell, minlength=cells)
+    isum = torch.zeros(cells, dtype=torch.float64, device=d).index_add_(0, cell, raw.inten[:n].double())
+    assert torch.equal(count.view(res.count.shape).to(torch.int32), res.count)
+    assert torch.equal(isum.view(res.isum.shape), res.isum)                 # integer-valued echoes: exact in any order
+    frames_built = int(np.count_nonzero(np.diff(raw.frame_off.cpu().numpy())))
+    mean = torch.where(count > 0, isum / count.clamp(min=1), torch.zeros_like(isum))
+    land = ((count.double() / max(frames_built, 1)) >= 0.8) & (mean >= 100)
+    assert torch.equal(land.view(res.land.shape), res.land.bool()) and bool(land.any())
+    keep = ~land[cell]
+    assert pts.n == int(keep.sum())
+    assert torch.equal(pts.x[:pts.n], raw.x[:n][keep]) and torch.equal(pts.inten[:pts.n], raw.inten[:n][keep])
+    assert torch.equal(pts.gain[:pts.n], raw.gain[:n][keep])
+    off = raw.frame_off
+    want_off = torch.cat([torch.zeros(1, dtype=torch.int64, device=d), keep.cumsum(0)])[off]
+    assert torch.equal(pts.frame_off, want_off)
+
+
+def test_pipeline_is_deterministic_at_scale(gpu):
+    """Atomics decide only WHICH thread links two components first, never the result: two runs over 48
+    full-size frames give identical points and labels; labels are canonical (ids appear in index order)."""
+    from radar_point_cloud_tracking_b200.pipeline import DetectionConfig, DetectionPipeline
+    spec = syn.SweepSpec(seed=5, frames=48)
+    pipe = DetectionPipeline(DetectionConfig(), 0)
+    echo = gpu.synth_echo(spec)
+    c, s, r = pipe.spoke_tables(spec.angle_units(), spec.scale(), spec.frames, spec.bins)
+    tabs = [torch.from_numpy(t).to(echo.device) for t in (c, s, r)]
+    a = pipe.run_device(echo, *tabs)
+    b = pipe.run_device(echo, *tabs)
+    assert a.points.n == b.points.n and a.n_clusters == b.n_clusters > 3
+    assert torch.equal(a.labels, b.labels) and torch.equal(a.points.x[:a.points.n], b.points.x[:b.points.n])
+    lab = a.labels.cpu().numpy()
+    first = [int(np.flatnonzero(lab == k)[0]) for k in range(a.n_clusters)]
+    # the first CORE point of cluster k precedes that of cluster k+1; border points may come earlier, so check
+    # through the ids' first occurrences being "almost sorted" is not enough - recompute from the core flags
+    core = gpu.StDbscanPhases(a.points.x, a.points.y, None,
+                              gpu.expand_frame_times(a.points.frame_off, torch.arange(spec.frames, dtype=torch.float32, device=echo.device),
+                                                     a.points.n), 8.0, 2.0, 15, n=a.points.n).cores().cpu().numpy().astype(bool)
+    first_core = [int(np.flatnonzero((lab == k) & core)[0]) for k in range(a.n_clusters)]
+    assert first_core == sorted(first_core) and len(first) == a.n_clusters
