@@ -163,6 +163,14 @@ typedef struct rb_dbscan_stats {
 } rb_dbscan_stats;
 int rb_stdbscan_last_stats(rb_ctx* ctx, rb_dbscan_stats* out);
 
+/* Optional knowledge of the caller about the points of an ST-DBSCAN call: a box that contains every coordinate
+ * and time (lo/hi = x, y, z, t; any superset is fine) and whether all times are integers. With a hint the plan
+ * phase needs no bounds pass and does not sync. */
+typedef struct rb_stdbscan_hint {
+    float lo[4], hi[4];
+    int32_t times_integer;
+} rb_stdbscan_hint;
+
 /* ---- a7 in phases (what rb_stdbscan runs back to back) -------------------------------------------
  * For callers that must exchange data between the phases - the time-sharded multi-GPU driver
  * (SURVEY.md section 8 e): every rank clusters its own frames plus a floor(eps_time)-frame halo,
@@ -188,12 +196,68 @@ int rb_stdbscan_last_stats(rb_ctx* ctx, rb_dbscan_stats* out);
 int rb_stdbscan_plan(rb_ctx* ctx, const float* x, const float* y, const float* z, int64_t stride,
                      const float* times, int64_t n, double eps_space, float eps_time, int min_samples,
                      void* stream);
+int rb_stdbscan_plan_hinted(rb_ctx* ctx, const float* x, const float* y, const float* z, int64_t stride,
+                            const float* times, int64_t n, double eps_space, float eps_time, int min_samples,
+                            const rb_stdbscan_hint* hint /* host, may be NULL */, void* stream);
 int rb_stdbscan_cores(rb_ctx* ctx, uint8_t* core_out, void* stream);
 int rb_stdbscan_set_cores(rb_ctx* ctx, const uint8_t* core_in, void* stream);
 int rb_stdbscan_components(rb_ctx* ctx, const int64_t* global_index, int64_t* comp_key, void* stream);
 int rb_stdbscan_assign(rb_ctx* ctx, const int32_t* core_label, int32_t* labels, void* stream);
 int rb_relabel(rb_ctx* ctx, const int64_t* keys, int64_t n, const int64_t* table_keys,
                const int32_t* table_ids, int64_t m, int32_t* out, void* stream);
+
+/* ---- the whole hot path for one block of frames in ONE call ----------------------------------------
+ * What run_pipeline does between "CSV parsed" and "labels known" (T4:941-977) for F frames of G gains:
+ * spoke-to-point + gain concat (a1, a2) -> if frames_built > land_min_frames: occupancy grid over the block,
+ * land cells, land filter (a4-a6; the np.arange edges are reproduced on the host side of the library) ->
+ * ST-DBSCAN over the (filtered) points with time = frame id (a7). All launches, the two small read-backs in
+ * between (point count + bounds; filtered count) and the final counter read-back happen inside the library.
+ *
+ *   echo [F*G][S][E], cos/sin/range_res [F*G][S], sweep_gain int32[F*G]: device, as rb_spoke_to_points
+ *   frame_ids: HOST float32[F]
+ * Outputs (device unless noted), all with capacity buf->cap points:
+ *   raw points x,y,inten,gain + frame_off int64[F+1]; filtered points fx,fy,finten,fgain + f_frame_off[F+1]
+ *   (when the land filter did not run, res->filtered_is_raw = 1 and the f* arrays are not written: use the raw
+ *   ones); labels int32; land grids count/isum/land with capacity max_cells; edges: HOST double arrays with
+ *   capacity max_edges each.
+ * Returns RB_ERR_CAPACITY (and the needed sizes in *res) when cap / max_cells / max_edges are too small. Syncs. */
+typedef struct rb_detect_params {
+    int32_t n_frames, gains_per_frame, n_spokes, n_bins;
+    float intensity_threshold;
+    int32_t point_stride;
+    int32_t land_filter;            /* 0 = skip a4-a6 */
+    int32_t land_min_frames;        /* the reference filters only when len(frames) > 10 (T4:954) */
+    double land_resolution, land_persistence, land_min_intensity;
+    double eps_space;
+    float eps_time;
+    int32_t min_samples;
+    int32_t cluster;                /* 0 = stop after the land filter */
+} rb_detect_params;
+
+typedef struct rb_detect_buffers {
+    float *x, *y, *inten; int32_t* gain; int64_t* frame_off;
+    float *fx, *fy, *finten; int32_t* fgain; int64_t* f_frame_off;
+    int32_t* labels;
+    int64_t cap;
+    int32_t* count; double* isum; uint8_t* land; int64_t max_cells;
+    double *x_edges, *y_edges; int32_t max_edges;             /* host */
+} rb_detect_buffers;
+
+typedef struct rb_detect_result {                            /* host */
+    int64_t n_raw, n_points, n_clusters;
+    int32_t frames_built, land_applied, filtered_is_raw;
+    int32_t n_x_edges, n_y_edges;
+    float bounds[4];                                          /* x_min, x_max, y_min, y_max of the raw points */
+} rb_detect_result;
+
+int rb_detect_block(rb_ctx* ctx, const float* echo, const float* cos_tab, const float* sin_tab, const float* range_res,
+                    const int32_t* sweep_gain, const float* frame_ids, const rb_detect_params* prm,
+                    const rb_detect_buffers* buf, rb_detect_result* res, void* stream);
+
+/* np.arange(lo, fl32(hi + step), step) as build_occupancy_grid computes its edges (T4:372-373: float32 scalar
+ * bounds, float64 result): out[0] = lo, out[1] = lo + step, out[i] = lo + i*(out[1] - lo). Host function.
+ * Returns the number of edges (> cap: nothing written beyond cap). */
+int64_t rb_arange_edges(float lo, float hi, double step, double* out, int64_t cap);
 
 /* ---- test/bench infrastructure (not part of the reference surface) ---------------------------
  * Device twin of radar_point_cloud_tracking_b200.synthetic.synth_echo: fills echo[W][S][E] for

@@ -23,6 +23,31 @@ class DbscanStats(C.Structure):
                 ("cell_size", c_f64), ("time_bin", c_f64), ("dims", c_i32 * 4), ("time_radius", c_i32), ("tight", c_i32)]
 
 
+class StdbscanHint(C.Structure):
+    _fields_ = [("lo", c_f32 * 4), ("hi", c_f32 * 4), ("times_integer", c_i32)]
+
+
+class DetectParams(C.Structure):
+    _fields_ = [("n_frames", c_i32), ("gains_per_frame", c_i32), ("n_spokes", c_i32), ("n_bins", c_i32),
+                ("intensity_threshold", c_f32), ("point_stride", c_i32), ("land_filter", c_i32), ("land_min_frames", c_i32),
+                ("land_resolution", c_f64), ("land_persistence", c_f64), ("land_min_intensity", c_f64),
+                ("eps_space", c_f64), ("eps_time", c_f32), ("min_samples", c_i32), ("cluster", c_i32)]
+
+
+class DetectBuffers(C.Structure):
+    _fields_ = [("x", c_vp), ("y", c_vp), ("inten", c_vp), ("gain", c_vp), ("frame_off", c_vp),
+                ("fx", c_vp), ("fy", c_vp), ("finten", c_vp), ("fgain", c_vp), ("f_frame_off", c_vp),
+                ("labels", c_vp), ("cap", c_i64),
+                ("count", c_vp), ("isum", c_vp), ("land", c_vp), ("max_cells", c_i64),
+                ("x_edges", c_vp), ("y_edges", c_vp), ("max_edges", c_i32)]
+
+
+class DetectResult(C.Structure):
+    _fields_ = [("n_raw", c_i64), ("n_points", c_i64), ("n_clusters", c_i64),
+                ("frames_built", c_i32), ("land_applied", c_i32), ("filtered_is_raw", c_i32),
+                ("n_x_edges", c_i32), ("n_y_edges", c_i32), ("bounds", c_f32 * 4)]
+
+
 #: name -> (restype, argtypes); must list every symbol of include/radarb200.h
 SIGNATURES = {
     "rb_version": (c_i32, []),
@@ -46,11 +71,15 @@ SIGNATURES = {
                             c_vp, c_vp, C.POINTER(c_i64), c_vp]),
     "rb_stdbscan_last_stats": (c_i32, [c_vp, C.POINTER(DbscanStats)]),
     "rb_stdbscan_plan": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_f64, c_f32, c_i32, c_vp]),
+    "rb_stdbscan_plan_hinted": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_f64, c_f32, c_i32, C.POINTER(StdbscanHint), c_vp]),
     "rb_stdbscan_cores": (c_i32, [c_vp, c_vp, c_vp]),
     "rb_stdbscan_set_cores": (c_i32, [c_vp, c_vp, c_vp]),
     "rb_stdbscan_components": (c_i32, [c_vp, c_vp, c_vp, c_vp]),
     "rb_stdbscan_assign": (c_i32, [c_vp, c_vp, c_vp, c_vp]),
     "rb_relabel": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "rb_detect_block": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.POINTER(DetectParams), C.POINTER(DetectBuffers),
+                                C.POINTER(DetectResult), c_vp]),
+    "rb_arange_edges": (c_i64, [c_f32, c_f32, c_f64, c_vp, c_i64]),
     "rb_synth_echo": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "rb_set_option": (c_i32, [c_vp, C.c_char_p, c_i64]),
     "rb_get_info": (c_i64, [c_vp, C.c_char_p]),

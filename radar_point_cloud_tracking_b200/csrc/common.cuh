@@ -38,6 +38,7 @@ enum rb_slot {
     RB_S_MISC,
     RB_S_FUSE_GRID,
     RB_S_COMP_KEY,          // dbscan: component key per point (original order)
+    RB_S_PIPE, RB_S_PIPE_EDGES, RB_S_PIPE_TIMES,   // rb_detect_block: sweep bases + bounds, device edges, times
     RB_S_B_NCORE, RB_S_B_PARENT, RB_S_B_LABEL, RB_S_B_MINKEY, RB_S_CORE_START, RB_S_CB_LIST,   // dbscan, tight: per-bucket arrays
     RB_S_COUNT
 };
@@ -143,3 +144,11 @@ __device__ __forceinline__ int rb_ld_relaxed_s32(const int* p) {
 // device-wide exclusive scan of int32 -> int32 (n < 2^31); total written to *total_out (device, optional)
 int rb_exclusive_scan_i32(rb_ctx* ctx, const int32_t* in, int32_t* out, int64_t n,
                           int32_t* total_out, cudaStream_t stream);
+
+// ST-DBSCAN without the final counter read-back (dbscan.cu); with a hint nothing in it syncs
+int rb_stdbscan_enqueue(rb_ctx* ctx, const float* x, const float* y, const float* z, int64_t stride, const float* times,
+                        int64_t n, double eps_space, float eps_time, int min_samples, int32_t* labels, uint8_t* core,
+                        const rb_stdbscan_hint* hint, void* stream);
+int rb_stdbscan_fetch_stats(rb_ctx* ctx, int64_t* n_clusters, void* stream);
+// bounds of the first *n_dev points (n_dev on the device, at most n_max): no host knowledge of n needed (land.cu)
+int rb_bounds_devn(rb_ctx* ctx, const float* x, const float* y, const int64_t* n_dev, int64_t n_max, float* out4, cudaStream_t stream);

@@ -896,7 +896,7 @@ Sorted sorted_view(const rb_db_plan& P) { return Sorted{P.sx, P.sy, P.sz, P.st, 
 
 template <int DIM>
 int plan_build(rb_ctx* ctx, rb_db_plan& P, const DbPoints& pts, int64_t n64, double eps_space, float eps_time, int min_samples,
-               cudaStream_t stream) {
+               cudaStream_t stream, const rb_stdbscan_hint* hint = nullptr) {
     const int n = (int)n64;
     const unsigned blocks = (unsigned)rb_div_up(n, DB_THREADS);
     P.valid = false;
@@ -907,19 +907,27 @@ int plan_build(rb_ctx* ctx, rb_db_plan& P, const DbPoints& pts, int64_t n64, dou
     RB_TRY(scratch(ctx, RB_S_MISC, 64, &P.d_misc));
     P.d_ctr = (unsigned long long*)(P.d_misc + 16);
     P.d_ncb = P.d_misc + 32;
-    db_bounds_init<<<1, 32, 0, stream>>>(P.d_misc);
-    RB_LAUNCH_CHECK(ctx);
     RB_CUDA(cudaMemsetAsync(P.d_ctr, 0, sizeof(unsigned long long) * 4, stream));
-    const unsigned want_b = (unsigned)rb_div_up(n, DB_THREADS * 4);
-    int bblocks = (int)(want_b < (unsigned)ctx->sm_count * 4 ? want_b : (unsigned)ctx->sm_count * 4);
-    db_bounds_kernel<<<bblocks, DB_THREADS, 0, stream>>>(pts, DIM, n64, P.d_misc);
-    RB_LAUNCH_CHECK(ctx);
-    int* h = (int*)ctx->pinned;
-    RB_CUDA(cudaMemcpyAsync(h, P.d_misc, sizeof(int) * 9, cudaMemcpyDeviceToHost, stream));
-    RB_CUDA(cudaStreamSynchronize(stream));
     float mn[4], mx[4];
-    for (int k = 0; k < 4; ++k) { mn[k] = ord2f(h[k]); mx[k] = ord2f(h[4 + k]); }
-    const bool times_integer = h[8] == 0;
+    bool times_integer;
+    if (hint) {
+        // the caller knows a box that contains every point and time (any superset is fine: the grid is only a
+        // candidate filter) - no bounds pass, no sync
+        for (int k = 0; k < 4; ++k) { mn[k] = hint->lo[k]; mx[k] = hint->hi[k]; }
+        times_integer = hint->times_integer != 0;
+    } else {
+        db_bounds_init<<<1, 32, 0, stream>>>(P.d_misc);
+        RB_LAUNCH_CHECK(ctx);
+        const unsigned want_b = (unsigned)rb_div_up(n, DB_THREADS * 4);
+        int bblocks = (int)(want_b < (unsigned)ctx->sm_count * 4 ? want_b : (unsigned)ctx->sm_count * 4);
+        db_bounds_kernel<<<bblocks, DB_THREADS, 0, stream>>>(pts, DIM, n64, P.d_misc);
+        RB_LAUNCH_CHECK(ctx);
+        int* h = (int*)ctx->pinned;
+        RB_CUDA(cudaMemcpyAsync(h, P.d_misc, sizeof(int) * 9, cudaMemcpyDeviceToHost, stream));
+        RB_CUDA(cudaStreamSynchronize(stream));
+        for (int k = 0; k < 4; ++k) { mn[k] = ord2f(h[k]); mx[k] = ord2f(h[4 + k]); }
+        times_integer = h[8] == 0;
+    }
 
     // 2. grid
     RB_TRY(choose_grid(mn, mx, times_integer, DIM, n64, eps_space, eps_time, ctx->opt_dbscan_mode, &P.g, &P.cell, &P.wt));
@@ -1068,9 +1076,19 @@ int fetch_stats(rb_ctx* ctx, rb_db_plan& P, int64_t* n_clusters, cudaStream_t st
 
 }  // namespace
 
+int rb_stdbscan_plan_hinted(rb_ctx* ctx, const float* x, const float* y, const float* z, int64_t stride,
+                            const float* times, int64_t n, double eps_space, float eps_time, int min_samples,
+                            const rb_stdbscan_hint* hint, void* stream_);
+
 extern "C" int rb_stdbscan_plan(rb_ctx* ctx, const float* x, const float* y, const float* z, int64_t stride,
                                 const float* times, int64_t n, double eps_space, float eps_time, int min_samples,
                                 void* stream_) {
+    return rb_stdbscan_plan_hinted(ctx, x, y, z, stride, times, n, eps_space, eps_time, min_samples, nullptr, stream_);
+}
+
+extern "C" int rb_stdbscan_plan_hinted(rb_ctx* ctx, const float* x, const float* y, const float* z, int64_t stride,
+                                       const float* times, int64_t n, double eps_space, float eps_time, int min_samples,
+                                       const rb_stdbscan_hint* hint, void* stream_) {
     RB_REQUIRE(ctx, "ctx is NULL");
     RB_REQUIRE(n > 0 && n < ((int64_t)1 << 31) - 1, "point count out of range (1 .. 2^31-2)");
     RB_REQUIRE(x && times, "NULL argument");
@@ -1081,9 +1099,9 @@ extern "C" int rb_stdbscan_plan(rb_ctx* ctx, const float* x, const float* y, con
     if (!ctx->db_plan) ctx->db_plan = new rb_db_plan();
     rb_db_plan& P = *ctx->db_plan;
     DbPoints pts{x, y, z, stride, times};
-    if (z) return plan_build<3>(ctx, P, pts, n, eps_space, eps_time, min_samples, stream);
-    if (y) return plan_build<2>(ctx, P, pts, n, eps_space, eps_time, min_samples, stream);
-    return plan_build<1>(ctx, P, pts, n, eps_space, eps_time, min_samples, stream);
+    if (z) return plan_build<3>(ctx, P, pts, n, eps_space, eps_time, min_samples, stream, hint);
+    if (y) return plan_build<2>(ctx, P, pts, n, eps_space, eps_time, min_samples, stream, hint);
+    return plan_build<1>(ctx, P, pts, n, eps_space, eps_time, min_samples, stream, hint);
 }
 
 extern "C" int rb_stdbscan_cores(rb_ctx* ctx, uint8_t* core_out, void* stream_) {
@@ -1139,16 +1157,12 @@ extern "C" int rb_relabel(rb_ctx* ctx, const int64_t* keys, int64_t n, const int
     return RB_OK;
 }
 
-extern "C" int rb_stdbscan(rb_ctx* ctx, const float* x, const float* y, const float* z, int64_t stride,
-                           const float* times, int64_t n, double eps_space, float eps_time, int min_samples,
-                           int32_t* labels, uint8_t* core, int64_t* n_clusters, void* stream_) {
-    RB_REQUIRE(ctx, "ctx is NULL");
-    RB_REQUIRE(n >= 0 && n < ((int64_t)1 << 31) - 1, "point count out of range");
-    if (n_clusters) *n_clusters = 0;
-    if (n == 0) return RB_OK;
-    RB_REQUIRE(labels, "labels is NULL");
+// everything of rb_stdbscan except reading the counters back: with a hint nothing here syncs
+int rb_stdbscan_enqueue(rb_ctx* ctx, const float* x, const float* y, const float* z, int64_t stride, const float* times,
+                        int64_t n, double eps_space, float eps_time, int min_samples, int32_t* labels, uint8_t* core,
+                        const rb_stdbscan_hint* hint, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    RB_TRY(rb_stdbscan_plan(ctx, x, y, z, stride, times, n, eps_space, eps_time, min_samples, stream_));
+    RB_TRY(rb_stdbscan_plan_hinted(ctx, x, y, z, stride, times, n, eps_space, eps_time, min_samples, hint, stream_));
     rb_db_plan& P = *ctx->db_plan;
     RB_TRY(rb_stdbscan_cores(ctx, core, stream_));
     RB_TRY(rb_stdbscan_components(ctx, nullptr, nullptr, stream_));
@@ -1160,8 +1174,24 @@ extern "C" int rb_stdbscan(rb_ctx* ctx, const float* x, const float* y, const fl
     RB_TRY(rb_exclusive_scan_i32(ctx, P.flags, P.rank, P.n, d_total, stream));
     db_rank_labels_kernel<<<blocks, DB_THREADS, 0, stream>>>(P.n, P.comp_key, P.rank, labels);
     RB_LAUNCH_CHECK(ctx);
-    RB_TRY(rb_stdbscan_assign(ctx, labels, labels, stream_));        // in place: core labels are copied before any write
-    return fetch_stats(ctx, P, n_clusters, stream);
+    return rb_stdbscan_assign(ctx, labels, labels, stream_);         // in place: core labels are copied before any write
+}
+
+int rb_stdbscan_fetch_stats(rb_ctx* ctx, int64_t* n_clusters, void* stream_) {
+    RB_REQUIRE(ctx && ctx->db_plan && ctx->db_plan->valid, "no ST-DBSCAN plan");
+    return fetch_stats(ctx, *ctx->db_plan, n_clusters, (cudaStream_t)stream_);
+}
+
+extern "C" int rb_stdbscan(rb_ctx* ctx, const float* x, const float* y, const float* z, int64_t stride,
+                           const float* times, int64_t n, double eps_space, float eps_time, int min_samples,
+                           int32_t* labels, uint8_t* core, int64_t* n_clusters, void* stream_) {
+    RB_REQUIRE(ctx, "ctx is NULL");
+    RB_REQUIRE(n >= 0 && n < ((int64_t)1 << 31) - 1, "point count out of range");
+    if (n_clusters) *n_clusters = 0;
+    if (n == 0) return RB_OK;
+    RB_REQUIRE(labels, "labels is NULL");
+    RB_TRY(rb_stdbscan_enqueue(ctx, x, y, z, stride, times, n, eps_space, eps_time, min_samples, labels, core, nullptr, stream_));
+    return rb_stdbscan_fetch_stats(ctx, n_clusters, stream_);
 }
 
 extern "C" int rb_stdbscan_last_stats(rb_ctx* ctx, rb_dbscan_stats* out) {

@@ -51,7 +51,9 @@ __device__ __forceinline__ Bounds4 block_reduce_bounds(Bounds4 b) {
 }
 
 __global__ void __launch_bounds__(LD_THREADS) bounds_partial(const float* __restrict__ x, const float* __restrict__ y,
-                                                            int64_t n, Bounds4* __restrict__ partial) {
+                                                            int64_t n, const int64_t* __restrict__ n_dev,
+                                                            Bounds4* __restrict__ partial) {
+    if (n_dev) n = *n_dev < n ? *n_dev : n;
     Bounds4 b{FLT_MAX, -FLT_MAX, FLT_MAX, -FLT_MAX};
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float xv = x[i], yv = y[i];
@@ -264,7 +266,20 @@ extern "C" int rb_bounds(rb_ctx* ctx, const float* x, const float* y, int64_t n,
                                                                                  : (int64_t)ctx->sm_count * 8);
     void* partial;
     RB_TRY(rb_scratch_get(ctx, RB_S_REDUCE, sizeof(Bounds4) * (size_t)blocks, &partial));
-    bounds_partial<<<blocks, LD_THREADS, 0, stream>>>(x, y, n, (Bounds4*)partial);
+    bounds_partial<<<blocks, LD_THREADS, 0, stream>>>(x, y, n, nullptr, (Bounds4*)partial);
+    RB_LAUNCH_CHECK(ctx);
+    bounds_final<<<1, LD_THREADS, 0, stream>>>((const Bounds4*)partial, blocks, out4);
+    RB_LAUNCH_CHECK(ctx);
+    return RB_OK;
+}
+
+int rb_bounds_devn(rb_ctx* ctx, const float* x, const float* y, const int64_t* n_dev, int64_t n_max, float* out4, cudaStream_t stream) {
+    if (n_max <= 0) return RB_OK;
+    int blocks = (int)(rb_div_up(n_max, LD_THREADS * 8) < (int64_t)ctx->sm_count * 4 ? rb_div_up(n_max, LD_THREADS * 8)
+                                                                                     : (int64_t)ctx->sm_count * 4);
+    void* partial;
+    RB_TRY(rb_scratch_get(ctx, RB_S_REDUCE, sizeof(Bounds4) * (size_t)blocks, &partial));
+    bounds_partial<<<blocks, LD_THREADS, 0, stream>>>(x, y, n_max, n_dev, (Bounds4*)partial);
     RB_LAUNCH_CHECK(ctx);
     bounds_final<<<1, LD_THREADS, 0, stream>>>((const Bounds4*)partial, blocks, out4);
     RB_LAUNCH_CHECK(ctx);

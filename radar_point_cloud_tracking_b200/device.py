@@ -335,6 +335,51 @@ def stdbscan_stats(device: Optional[int] = None) -> dict:
     return d
 
 
+# --------------------------------------------------------------------------------------- whole block, one call
+RB_ERR_CAPACITY = -3
+
+
+def arange_edges(lo: float, hi: float, step: float) -> np.ndarray:
+    """The library's host-side restatement of ``np.arange(lo32, lo32.dtype.type(hi32 + step), step)`` (T4:372-373)."""
+    lib = _lib.load()
+    n = int(lib.rb_arange_edges(float(np.float32(lo)), float(np.float32(hi)), float(step), None, 0))
+    out = np.empty(max(n, 0), dtype=np.float64)
+    if n > 0:
+        lib.rb_arange_edges(float(np.float32(lo)), float(np.float32(hi)), float(step), out.ctypes.data, n)
+    return out
+
+
+def detect_block(echo: torch.Tensor, cos_tab: torch.Tensor, sin_tab: torch.Tensor, range_res: torch.Tensor,
+                 sweep_gain: torch.Tensor, frame_ids: np.ndarray, params: "_lib.DetectParams", cap: int,
+                 max_edges: int, max_cells: int):
+    """``rb_detect_block``: the whole hot path for ``echo[F*G,S,E]`` in one library call.
+    Returns ``(rc, result struct, buffers dict)``; rc is 0 or ``RB_ERR_CAPACITY`` (the struct then holds the
+    sizes that are needed); anything else raises."""
+    ctx = context(echo.device.index)
+    dev = echo.device
+    F = int(params.n_frames)
+    f32 = lambda n: torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+    i32 = lambda n: torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    t = dict(x=f32(cap), y=f32(cap), inten=f32(cap), gain=i32(cap), frame_off=torch.empty(F + 1, dtype=torch.int64, device=dev),
+             fx=f32(cap), fy=f32(cap), finten=f32(cap), fgain=i32(cap), f_frame_off=torch.empty(F + 1, dtype=torch.int64, device=dev),
+             labels=i32(cap), count=i32(max_cells), isum=torch.empty(max(max_cells, 1), dtype=torch.float64, device=dev),
+             land=torch.empty(max(max_cells, 1), dtype=torch.uint8, device=dev))
+    xe = np.empty(max(max_edges, 1), dtype=np.float64)
+    ye = np.empty(max(max_edges, 1), dtype=np.float64)
+    buf = _lib.DetectBuffers(**{k: ptr(v) for k, v in t.items()}, cap=int(cap), max_cells=int(max_cells),
+                             x_edges=xe.ctypes.data, y_edges=ye.ctypes.data, max_edges=int(max_edges))
+    res = _lib.DetectResult()
+    ids = np.ascontiguousarray(frame_ids, dtype=np.float32)
+    rc = ctx.lib.rb_detect_block(ctx.handle, ptr(_dev(echo, torch.float32, "echo")), ptr(_dev(cos_tab, torch.float32, "cos_tab")),
+                                 ptr(_dev(sin_tab, torch.float32, "sin_tab")), ptr(_dev(range_res, torch.float32, "range_res")),
+                                 ptr(_dev(sweep_gain, torch.int32, "sweep_gain")), ids.ctypes.data, C.byref(params), C.byref(buf),
+                                 C.byref(res), stream_ptr())
+    if rc not in (0, RB_ERR_CAPACITY):
+        check(rc, "rb_detect_block")
+    t["x_edges"], t["y_edges"] = xe, ye
+    return rc, res, t
+
+
 # --------------------------------------------------------------------------------------- synthetic input
 def synth_echo(spec, first_frame: int = 0, n_frames: Optional[int] = None, device=None,
                out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -107,6 +107,8 @@ class DetectionPipeline:
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         self.ctx = context(self.device.index)
         self._cap_hint = 0
+        self._grid_hint = (256, 32768)                 # land grid capacity: edges per axis, cells
+        self._gain_cache = None
 
     # ---- host-side tables ---------------------------------------------------------------------
     def spoke_tables(self, angle_units: np.ndarray, scale: np.ndarray, n_frames: int, n_bins: int):
@@ -127,7 +129,55 @@ class DetectionPipeline:
     # ---- device path ----------------------------------------------------------------------------
     def run_device(self, echo: torch.Tensor, cos_tab: torch.Tensor, sin_tab: torch.Tensor, range_res: torch.Tensor,
                    frame_ids: Optional[Sequence[int]] = None, cluster: bool = True) -> DetectionResult:
-        """``echo[F,G,S,E]`` float32 already on the device; tables ``[F*G,S]`` on the device."""
+        """``echo[F,G,S,E]`` float32 already on the device; tables ``[F*G,S]`` on the device.
+        One library call (``rb_detect_block``): every launch and the small read-backs in between happen in the
+        native driver, not in Python."""
+        from . import _lib
+
+        cfg = self.cfg
+        F, G, S, E = echo.shape
+        if G != len(cfg.gains):
+            raise RadarB200Error("echo gain dimension does not match config.gains")
+        d = echo.device
+        ids = np.arange(F, dtype=np.int64) if frame_ids is None else np.asarray(frame_ids, dtype=np.int64)
+        if self._gain_cache is None or self._gain_cache.numel() != F * G or self._gain_cache.device != d:
+            self._gain_cache = torch.tensor(list(cfg.gains) * F, dtype=torch.int32, device=d)
+        prm = _lib.DetectParams(n_frames=F, gains_per_frame=G, n_spokes=S, n_bins=E,
+                                intensity_threshold=float(cfg.intensity_threshold), point_stride=int(cfg.point_stride),
+                                land_filter=int(bool(cfg.land_filter)), land_min_frames=int(cfg.land_min_frames),
+                                land_resolution=float(cfg.land_resolution), land_persistence=float(cfg.land_persistence),
+                                land_min_intensity=float(cfg.land_min_intensity), eps_space=float(cfg.eps_space),
+                                eps_time=float(np.float32(cfg.eps_time)), min_samples=int(cfg.min_samples), cluster=int(bool(cluster)))
+        cap = self._cap_hint or dev.default_capacity(F * G, S, E, cfg.point_stride)
+        echo3 = echo.view(F * G, S, E)
+        for _ in range(4):
+            max_edges, max_cells = self._grid_hint
+            rc, res, t = dev.detect_block(echo3, cos_tab, sin_tab, range_res, self._gain_cache, ids, prm, cap, max_edges, max_cells)
+            if rc == 0:
+                break
+            if res.n_raw > cap:                                    # too many points for the capacity guess
+                cap = int(res.n_raw * 1.1) + 1024
+            else:                                                  # the land grid is larger than the guess
+                ne = max(res.n_x_edges, res.n_y_edges) + 8
+                self._grid_hint = (max(ne, max_edges), max(int(res.n_x_edges) * int(res.n_y_edges) + 64, max_cells))
+        else:
+            raise RadarB200Error("rb_detect_block: capacity negotiation did not converge")
+        self._cap_hint = max(self._cap_hint, int(res.n_raw * 1.25) + 1024)
+        n_raw, n_pts = int(res.n_raw), int(res.n_points)
+        raw = dev.PointBatch(t["x"], t["y"], t["inten"], t["gain"], t["frame_off"], n_raw)
+        pts = raw if res.filtered_is_raw else dev.PointBatch(t["fx"], t["fy"], t["finten"], t["fgain"], t["f_frame_off"], n_pts)
+        land = edges = count = isum = None
+        if res.land_applied:
+            nx, ny = res.n_x_edges - 1, res.n_y_edges - 1
+            edges = (t["x_edges"][:res.n_x_edges].copy(), t["y_edges"][:res.n_y_edges].copy())
+            count, isum, land = (t[k][:nx * ny].view(nx, ny) for k in ("count", "isum", "land"))
+        labels = t["labels"][:n_pts] if (cluster and n_pts > 0) else torch.empty(0, dtype=torch.int32, device=d)
+        return DetectionResult(ids, raw, pts, labels, int(res.n_clusters), land, edges, count, isum)
+
+    def run_device_staged(self, echo: torch.Tensor, cos_tab: torch.Tensor, sin_tab: torch.Tensor, range_res: torch.Tensor,
+                          frame_ids: Optional[Sequence[int]] = None, cluster: bool = True) -> DetectionResult:
+        """The same path driven stage by stage from Python through the per-function entry points (the calls the
+        drop-in shims of :mod:`tracker` make). Kept for cross-checking the native driver."""
         cfg = self.cfg
         F, G, S, E = echo.shape
         if G != len(cfg.gains):

@@ -114,3 +114,17 @@ def test_synthetic_generator_is_deterministic():
     a, b = syn.synth_echo(spec), syn.synth_echo(spec)
     assert np.array_equal(a, b) and a.dtype == np.float32 and a.min() >= 0 and a.max() <= 255
     assert np.array_equal(a, np.rint(a))
+
+
+def test_native_arange_edges_match_numpy():
+    """rb_arange_edges (host code of the library, used by rb_detect_block) == np.arange on float32 scalar
+    bounds, bit for bit - length rule and fill rule of numpy (T4:372-373)."""
+    from radar_point_cloud_tracking_b200 import device as dev
+    rng = np.random.default_rng(3)
+    for _ in range(2000):
+        lo, hi = np.sort(rng.normal(0, 400, 2)).astype(np.float32)
+        step = float(rng.choice([5.0, 1.0, 2.5, 0.7, 3.3, 10.0]))
+        ref = np.arange(lo, hi + step, step)
+        got = dev.arange_edges(lo, hi, step)
+        assert ref.dtype == np.float64 and np.array_equal(ref, got)
+    assert len(dev.arange_edges(3.0, 3.0, 5.0)) == 1 and len(dev.arange_edges(0.0, 10.0, 5.0)) == 3

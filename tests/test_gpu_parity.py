@@ -532,3 +532,31 @@ def test_pipeline_is_deterministic_at_scale(gpu):
                                                      a.points.n), 8.0, 2.0, 15, n=a.points.n).cores().cpu().numpy().astype(bool)
     first_core = [int(np.flatnonzero((lab == k) & core)[0]) for k in range(a.n_clusters)]
     assert first_core == sorted(first_core) and len(first) == a.n_clusters
+
+
+@pytest.mark.parametrize("kw", [{}, {"land_filter": False}, {"eps_time": 0.5, "min_samples": 6}])
+def test_native_block_driver_equals_staged_path(gpu, kw):
+    """rb_detect_block (one call, native host driver, hinted ST-DBSCAN plan) against the same path driven stage
+    by stage through the per-function entry points: identical raw points, grids, mask, filtered points, labels."""
+    from radar_point_cloud_tracking_b200.pipeline import DetectionConfig, DetectionPipeline
+    spec = syn.SweepSpec(seed=19, frames=14, spokes=384, bins=1024, clutter_p=0.006, land_blobs=3, buoys=3, boats=3)
+    pipe = DetectionPipeline(DetectionConfig(**kw), 0)
+    echo = gpu.synth_echo(spec)
+    c, s, r = pipe.spoke_tables(spec.angle_units(), spec.scale(), spec.frames, spec.bins)
+    tabs = [torch.from_numpy(t).to(echo.device) for t in (c, s, r)]
+    ids = np.arange(100, 100 + spec.frames)
+    a = pipe.run_device(echo, *tabs, frame_ids=ids)
+    b = pipe.run_device_staged(echo, *tabs, frame_ids=ids)
+    assert a.raw.n == b.raw.n > 0 and a.points.n == b.points.n and a.n_clusters == b.n_clusters
+    for f in ("x", "y", "inten", "gain"):
+        assert torch.equal(getattr(a.raw, f)[:a.raw.n], getattr(b.raw, f)[:b.raw.n])
+        assert torch.equal(getattr(a.points, f)[:a.points.n], getattr(b.points, f)[:b.points.n])
+    assert torch.equal(a.raw.frame_off, b.raw.frame_off) and torch.equal(a.points.frame_off, b.points.frame_off)
+    assert torch.equal(a.labels, b.labels)
+    if kw.get("land_filter", True):
+        assert np.array_equal(a.edges[0], b.edges[0]) and np.array_equal(a.edges[1], b.edges[1])
+        assert torch.equal(a.count, b.count) and torch.equal(a.isum, b.isum) and torch.equal(a.land, b.land)
+    else:
+        assert a.land is None and a.points.n == a.raw.n
+    empty = pipe.run_device(torch.zeros_like(echo), *tabs)              # nothing above the threshold
+    assert empty.raw.n == 0 and empty.points.n == 0 and empty.n_clusters == 0 and empty.labels.numel() == 0
