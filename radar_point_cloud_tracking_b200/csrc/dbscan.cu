@@ -328,7 +328,8 @@ __global__ void __launch_bounds__(DB_THREADS) dbg_minkey_kernel(int n, const uin
     if (p >= n || core[p] != 1) return;
     int r = uf_find_ro(parent, p);
     parent[p] = r;
-    atomicMin(minkey + r, point_key(gidx, sidx[p]));
+    const long long k = point_key(gidx, sidx[p]);
+    if (k < *(volatile long long*)(minkey + r)) atomicMin(minkey + r, k);
 }
 
 __global__ void __launch_bounds__(DB_THREADS) dbg_keyout_kernel(int n, const uint8_t* __restrict__ core, const int* __restrict__ parent,
@@ -555,71 +556,104 @@ __global__ void __launch_bounds__(DB_THREADS) dbt_union_kernel(Sorted s, DbGrid 
                                                               const int* __restrict__ b_ncore, int* __restrict__ b_parent,
                                                               const int* __restrict__ cb_slot, const int* __restrict__ cb_bbox,
                                                               double eps2, unsigned long long* __restrict__ ctr) {
-    constexpr int MAX_SLOTS = DIM == 3 ? 4 : 4;              // offsets per lane: ceil((2R+1)^DIM * (2tr+1) / 32) handled in chunks
+    // tight grids search (2R+1)^DIM cells with R = 2 (R = 1 in 1-D): compile-time side length, so the offset
+    // of a lane needs no division by run-time values
+    constexpr int SIDE = DIM == 1 ? 3 : 5;
+    constexpr int R = SIDE / 2;
+    constexpr int SPATIAL = DIM == 1 ? SIDE : (DIM == 2 ? SIDE * SIDE : SIDE * SIDE * SIDE);
+    constexpr int SMALL_PAIR = 96;                                  // |A| * |B| up to which ONE lane searches the pair
     const unsigned lane = rb_lane();
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     const int total = *n_cb;
+    // offsets are numbered (dt, dz, dy, dx) with dx fastest - the order of the bucket index - so the first half
+    // of them are exactly the buckets that precede the centre: every unordered pair is looked at once
+    const int n_half = (SPATIAL * (2 * g.tr + 1)) / 2;
+    const int nxy = g.n[0] * g.n[1];
     unsigned long long tests = 0;
     for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += n_warps) {
         const int A = cb_list[w];
         const CellPos c = decode_cell(g, A);
-        const Window win = window_of<DIM>(g, c);
         const int a0 = s.cell_start[A], a1 = s.cell_start[A + 1];
-        const int nx = win.x1 - win.x0 + 1, ny = win.y1 - win.y0 + 1, nz = win.z1 - win.z0 + 1, ntw = win.t1 - win.t0 + 1;
-        const int n_off = nx * ny * nz * ntw;
         const int root_a = uf_find_cached(b_parent, A);
         const BBox box_a = load_bbox<DIM>(cb_bbox, w);
-        for (int base = 0; base < n_off; base += 32 * MAX_SLOTS) {
-            // ---- gather: every lane looks at up to MAX_SLOTS buckets of the window (independent loads) ----
-            int cand[MAX_SLOTS];
-#pragma unroll
-            for (int k = 0; k < MAX_SLOTS; ++k) {
-                cand[k] = -1;
-                const int o = base + k * 32 + (int)lane;
-                if (o < n_off) {
-                    int r = o;
-                    const int xx = win.x0 + r % nx; r /= nx;
-                    const int yy = win.y0 + r % ny; r /= ny;
-                    const int zz = win.z0 + r % nz; r /= nz;
-                    const int tt = win.t0 + r;
-                    const int cheb = max(abs(xx - c.cx), max(abs(yy - c.cy), abs(zz - c.cz)));
-                    const int bkt = ((tt * g.n[2] + zz) * g.n[1] + yy) * g.n[0] + xx;
-                    if (cheb > 0 && bkt < A && __ldg(b_ncore + bkt) > 0) cand[k] = bkt | (cheb > 1 ? 0x40000000 : 0);
+        for (int base = 0; base < n_half; base += 32) {
+            // ---- one bucket of the half window per lane ----
+            int B = -1;
+            bool far = false;
+            const int o = base + (int)lane;
+            if (o < n_half) {
+                int r = o;
+                const int dx = r % SIDE - R; r /= SIDE;
+                int dy = 0, dz = 0;
+                if (DIM > 1) { dy = r % SIDE - R; r /= SIDE; }
+                if (DIM > 2) { dz = r % SIDE - R; r /= SIDE; }
+                const int dt = r - g.tr;
+                const int xx = c.cx + dx, yy = c.cy + dy, zz = c.cz + dz, tt = c.tb + dt;
+                if ((dx | dy | dz) != 0 && xx >= 0 && xx < g.n[0] && yy >= 0 && yy < g.n[1] && zz >= 0 && zz < g.n[2] && tt >= 0) {
+                    const int bkt = A + dt * (nxy * g.n[2]) + dz * nxy + dy * g.n[0] + dx;
+                    if (__ldg(b_ncore + bkt) > 0) { B = bkt; far = max(abs(dx), max(abs(dy), abs(dz))) > 1; }
                 }
             }
-            // ---- filter: already connected (cached roots), or the boxes of the core points are more than eps apart ----
-#pragma unroll
-            for (int k = 0; k < MAX_SLOTS; ++k) {
-                if (cand[k] < 0) continue;
-                const int bk = cand[k] & 0x3fffffff;
-                if (uf_find_cached(b_parent, bk) == root_a) { cand[k] = -1; continue; }
-                if (box_gap2<DIM>(box_a, load_bbox<DIM>(cb_bbox, __ldg(cb_slot + bk))) > eps2) cand[k] = -1;
+            // ---- already connected? (cached roots: a stale "same" is still true) ----
+            if (B >= 0 && uf_find_cached(b_parent, B) == root_a) B = -1;
+            if (!__any_sync(0xffffffffu, B >= 0)) continue;
+            // ---- boxes of the core points more than eps apart: no pair can exist ----
+            BBox box_b = {};
+            int b0 = 0, b1 = 0;
+            if (B >= 0) {
+                box_b = load_bbox<DIM>(cb_bbox, __ldg(cb_slot + B));
+                if (box_gap2<DIM>(box_a, box_b) > eps2) B = -1;
+                else { b0 = s.cell_start[B]; b1 = s.cell_start[B + 1]; }
             }
-            // ---- the rest: exact check, then one core-core pair within eps connects the two buckets;
-            //      cells at Chebyshev distance 1 first ----
+            // ---- small pairs: the lane searches its pair alone, 32 pairs in parallel ----
+            if (B >= 0 && (a1 - a0) * (b1 - b0) <= SMALL_PAIR) {
+                bool found = false;
+                for (int ia = a0; ia < a1 && !found; ++ia) {
+                    if (core[ia] != 1) continue;
+                    const Pt<DIM> pa = load_pt<DIM>(s, ia);
+                    if (point_gap2<DIM>(pa, box_b) > eps2) continue;
+                    for (int jb = b0; jb < b1; ++jb) {
+                        if (core[jb] != 1) continue;
+                        ++tests;
+                        if (near_enough<DIM>(pa, load_pt<DIM>(s, jb), eps2)) { found = true; break; }
+                    }
+                }
+                if (found) uf_union(b_parent, A, B);
+                B = -1;
+            }
+            // ---- big pairs: the whole warp, 32 x 32 points in registers at a time; near cells first ----
             for (int pass = 0; pass < 2; ++pass) {
+                unsigned todo = __ballot_sync(0xffffffffu, B >= 0 && (int)far == pass);
+                while (todo) {
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int Bw = __shfl_sync(0xffffffffu, B, src);
+                    int same = 0;
+                    if (lane == 0) same = uf_find(b_parent, A) == uf_find(b_parent, Bw);
+                    if (__shfl_sync(0xffffffffu, same, 0)) continue;
+                    const int w0 = __shfl_sync(0xffffffffu, b0, src), w1 = __shfl_sync(0xffffffffu, b1, src);
+                    BBox bb;
 #pragma unroll
-                for (int k = 0; k < MAX_SLOTS; ++k) {
-                    const bool mine = cand[k] >= 0 && ((cand[k] >> 30) & 1) == pass;
-                    unsigned todo = __ballot_sync(0xffffffffu, mine);
-                    while (todo) {
-                        const int src = __ffs(todo) - 1;
-                        todo &= todo - 1;
-                        const int Bw = __shfl_sync(0xffffffffu, cand[k], src) & 0x3fffffff;
-                        int same = 0;
-                        if (lane == 0) same = uf_find(b_parent, A) == uf_find(b_parent, Bw);
-                        if (__shfl_sync(0xffffffffu, same, 0)) continue;
-                        const int b0 = s.cell_start[Bw], b1 = s.cell_start[Bw + 1];
-                        const BBox box_b = load_bbox<DIM>(cb_bbox, __ldg(cb_slot + Bw));
-                        bool found = false;
-                        for (int ia0 = a0; ia0 < a1 && !found; ia0 += 32) {
-                            // 32 points of A at a time: keep the core points that are within eps of B's box
-                            const int ia_l = ia0 + (int)lane;
-                            Pt<DIM> mine_a = {};
-                            bool use = false;
-                            if (ia_l < a1 && core[ia_l] == 1) { mine_a = load_pt<DIM>(s, ia_l); use = point_gap2<DIM>(mine_a, box_b) <= eps2; }
-                            unsigned act = __ballot_sync(0xffffffffu, use);
-                            while (act && !found) {
+                    for (int k = 0; k < 3; ++k) {
+                        bb.lo[k] = __shfl_sync(0xffffffffu, box_b.lo[k], src);
+                        bb.hi[k] = __shfl_sync(0xffffffffu, box_b.hi[k], src);
+                    }
+                    bool found = false;
+                    for (int ia0 = a0; ia0 < a1 && !found; ia0 += 32) {
+                        const int ia_l = ia0 + (int)lane;
+                        Pt<DIM> mine_a = {};
+                        bool use_a = false;
+                        if (ia_l < a1 && core[ia_l] == 1) { mine_a = load_pt<DIM>(s, ia_l); use_a = point_gap2<DIM>(mine_a, bb) <= eps2; }
+                        const unsigned act_a = __ballot_sync(0xffffffffu, use_a);
+                        if (!act_a) continue;
+                        for (int jb0 = w0; jb0 < w1 && !found; jb0 += 32) {
+                            const int jb_l = jb0 + (int)lane;
+                            Pt<DIM> mine_b = {};
+                            bool use_b = false;
+                            if (jb_l < w1 && core[jb_l] == 1) { mine_b = load_pt<DIM>(s, jb_l); use_b = point_gap2<DIM>(mine_b, box_a) <= eps2; }
+                            if (!__any_sync(0xffffffffu, use_b)) continue;
+                            unsigned act = act_a;
+                            while (act) {
                                 const int la = __ffs(act) - 1;
                                 act &= act - 1;
                                 Pt<DIM> pa;
@@ -627,16 +661,13 @@ __global__ void __launch_bounds__(DB_THREADS) dbt_union_kernel(Sorted s, DbGrid 
                                 pa.y = DIM > 1 ? __shfl_sync(0xffffffffu, mine_a.y, la) : 0.f;
                                 pa.z = DIM > 2 ? __shfl_sync(0xffffffffu, mine_a.z, la) : 0.f;
                                 pa.t = 0.f;
-                                for (int jb = b0; jb < b1; jb += 32) {
-                                    const int q = jb + (int)lane;
-                                    bool ok = false;
-                                    if (q < b1 && core[q] == 1) { ++tests; ok = near_enough<DIM>(pa, load_pt<DIM>(s, q), eps2); }
-                                    if (__any_sync(0xffffffffu, ok)) { found = true; break; }
-                                }
+                                bool ok = false;
+                                if (use_b) { ++tests; ok = near_enough<DIM>(pa, mine_b, eps2); }
+                                if (__any_sync(0xffffffffu, ok)) { found = true; break; }
                             }
                         }
-                        if (found && lane == 0) uf_union(b_parent, A, Bw);
                     }
+                    if (found && lane == 0) uf_union(b_parent, A, Bw);
                 }
             }
         }
@@ -650,7 +681,12 @@ __global__ void __launch_bounds__(DB_THREADS) dbt_compmin_kernel(const int* __re
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int b = cb_list[i];
         const int r = uf_find_ro(b_parent, b);
-        if (r != b) { b_parent[b] = r; atomicMin(b_minkey + r, b_minkey[b]); }
+        if (r != b) {
+            b_parent[b] = r;
+            const long long k = b_minkey[b];
+            // most buckets do not hold their component's smallest key: look before paying for a contended atomic
+            if (k < *(volatile long long*)(b_minkey + r)) atomicMin(b_minkey + r, k);
+        }
     }
 }
 
