@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--clutter-p", type=float, default=0.003)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--streams", type=int, default=2, help="N=1: blocks in flight (host threads x CUDA streams) for `value`")
     ap.add_argument("--cpu-frames", type=int, default=64, help="frames per CPU worker in the reference/cpu_baseline sample")
     ap.add_argument("--shard-profile", action="store_true", help="N>1: print per-stage wall-clock of the sharded driver to stderr")
     return ap.parse_args()
@@ -239,20 +240,32 @@ def run_ours(args):
         return ms, ctx.launch_count() - l0
 
     # ---- device-resident throughput -----------------------------------------------------------------
-    spoke_events = []
-    dev.SPOKE_EVENTS = spoke_events            # pipeline records (start, end) events around the spoke kernel
     results = []
+    overlapped = None
     with ClockSampler(device.index) as clocks:
-        ms, launches = timed(lambda: pipe.run_device(echo, d_c, d_s, d_r, frame_ids), args.steps, args.warmup,
-                             collect=results.append)
-    dev.SPOKE_EVENTS = None
+        if world == 1 and args.streams > 1:
+            # throughput path: `streams` host threads, each with its own CUDA stream and library context, run whole
+            # blocks concurrently; timed from an event recorded before the first block is submitted to an event the
+            # current stream records after waiting for every block
+            from radar_point_cloud_tracking_b200.pipeline import OverlappedPipeline
+            overlapped = OverlappedPipeline(cfg, device.index, workers=args.streams)
+            block = ((echo, d_c, d_s, d_r, frame_ids), {})
+            overlapped.map([block] * max(args.warmup, args.streams))
+            barrier()
+            l0 = overlapped.launch_count()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            results = overlapped.map([block] * args.steps, start_event=ev0)
+            ev1.record()
+            barrier()
+            ms, launches = ev0.elapsed_time(ev1), overlapped.launch_count() - l0
+        else:
+            ms, launches = timed(lambda: pipe.run_device(echo, d_c, d_s, d_r, frame_ids), args.steps, args.warmup,
+                                 collect=results.append)
     res = results[-1]
     n_raw, n_pts = res.raw.n, res.points.n
-    spoke_ms = [a.elapsed_time(b) for a, b in spoke_events[-args.steps:]]
-    spoke_ms_mean = sum(spoke_ms) / max(len(spoke_ms), 1)
     echo_bytes = B * G * args.spokes * args.bins * 4
     spoke_bytes = echo_bytes + B * G * args.spokes * 12 + 16 * n_raw          # SURVEY.md 8(d), whole stage
-    stage_gbs = spoke_bytes / (spoke_ms_mean * 1e-3) / 1e9 if spoke_ms_mean > 0 else 0.0
     # per-kernel split of the stage: a few extra (untimed) steps with events recorded inside the library,
     # on the launch stream, around each of the three kernels
     ctx.set_option("spoke_profile", 1)
@@ -263,6 +276,8 @@ def run_ours(args):
     ctx.set_option("spoke_profile", 0)
     mask_ms, offs_ms, emit_ms = (sum(r[i] for r in split) / len(split) for i in range(3))
     achieved = echo_bytes / (mask_ms * 1e-3) / 1e9 if mask_ms > 0 else 0.0
+    spoke_ms_mean = mask_ms + offs_ms + emit_ms                               # first event to last event of the stage
+    stage_gbs = spoke_bytes / (spoke_ms_mean * 1e-3) / 1e9 if spoke_ms_mean > 0 else 0.0
     frames_total = B * world * args.steps
     value = frames_total / (ms * 1e-3)
     pts_t = torch.tensor([n_raw, n_pts, res.n_clusters], device=device, dtype=torch.int64)
@@ -302,11 +317,11 @@ def run_ours(args):
         "dtype": "f32 (points) / f64 (neighbour test) / i32 (labels)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "spokes": args.spokes, "bins": args.bins,
                    "gains": [40, 50, 75], "seed": args.seed, "clutter_p": args.clutter_p,
-                   "parallelism": f"time-sharded x{world}" if world > 1 else "single GPU",
+                   "parallelism": f"time-sharded x{world}" if world > 1 else f"single GPU, {args.streams if overlapped else 1} block(s) in flight",
                    "l2_policy": "inputs larger than L2 (echo block %.2f GB per step)" % (echo.numel() * 4 / 1e9)},
         "points_per_s": n_raw_all * args.steps / (ms * 1e-3),
         "points_per_step": {"after_stride": n_raw_all, "after_land_filter": n_pts_all, "clusters": int(pts_t[2])},
-        "roofline": {"bound": "hbm", "kernel": "spoke_mask_kernel", "achieved": achieved, "peak": hbm_peak,
+        "roofline": {"bound": "hbm", "kernel": "spoke_mask_tma_kernel", "achieved": achieved, "peak": hbm_peak,
                      "unit": "GB/s", "frac": achieved / hbm_peak, "frac_of_nominal_8TBs": achieved / 8000.0,
                      "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_launch": echo_bytes,
                      "kernel_ms": mask_ms, "share_of_step": mask_ms / (ms / args.steps),
@@ -316,8 +331,8 @@ def run_ours(args):
                                               "spoke_emit_kernel": emit_ms},
                                "stage_ms": spoke_ms_mean, "algorithmic_bytes": spoke_bytes,
                                "achieved": stage_gbs, "frac": stage_gbs / hbm_peak,
-                               "note": "whole rb_spoke_to_points call (3 launches) timed with CUDA events inside the "
-                                       "timed region; bytes = echo + spoke tables + 16 B per kept point"}},
+                               "note": "whole rb_spoke_to_points call (3 launches), first to last CUDA event recorded inside the "
+                                       "library on the launch stream; bytes = echo + spoke tables + 16 B per kept point"}},
         "stdbscan": {"pair_tests_per_step": st["pair_tests_count"] + st["pair_tests_union"] + st["pair_tests_border"],
                      "pair_tests": [st["pair_tests_count"], st["pair_tests_union"], st["pair_tests_border"]], "tight": st["tight"],
                      "cells": st["n_cells"], "dims": st["dims"], "time_radius": st["time_radius"]},

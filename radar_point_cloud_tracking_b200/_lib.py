@@ -165,9 +165,10 @@ def context(device: Optional[int] = None) -> Context:
         raise RadarB200Error("no CUDA device: the radar-b200 detection path is GPU only (no CPU fallback)")
     if device is None:
         device = torch.cuda.current_device()
-    ctx = _contexts.get(device)
+    key = (device, threading.get_ident())          # a ctx is not thread safe: one per device AND host thread
+    ctx = _contexts.get(key)
     if ctx is None:
-        ctx = _contexts[device] = Context(device)
+        ctx = _contexts[key] = Context(device)
     return ctx
 
 

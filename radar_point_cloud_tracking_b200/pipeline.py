@@ -227,3 +227,59 @@ class DetectionPipeline:
         out["h2d_bytes"] = t_echo.numel() * 4 + 3 * c.nbytes
         out["d2h_bytes"] = out["points"].nbytes + out["gains"].nbytes + out["labels"].nbytes + out["frame_off"].nbytes
         return out
+
+
+class OverlappedPipeline:
+    """Throughput driver: ``workers`` host threads, each with its own CUDA stream and its own library context
+    (scratch), run whole blocks concurrently, so the host-side gaps of one block (its read-backs, launch
+    latency of the many small ST-DBSCAN kernels) are filled by another block's kernels - the HBM-bound mask
+    kernel of block k+1 runs next to the latency-bound clustering of block k. Results are exactly those of
+    :meth:`DetectionPipeline.run_device` per block."""
+
+    def __init__(self, config: Optional[DetectionConfig] = None, device: Optional[int] = None, workers: int = 2):
+        from concurrent.futures import ThreadPoolExecutor
+
+        self.base = DetectionPipeline(config, device)
+        self.device = self.base.device
+        self.workers = max(1, int(workers))
+        self._pool = ThreadPoolExecutor(max_workers=self.workers, thread_name_prefix="radarb200")
+        import threading
+        self._tls = threading.local()
+        self._ctxs = []
+
+    def _worker_state(self):
+        st = getattr(self._tls, "state", None)
+        if st is None:
+            torch.cuda.set_device(self.device)
+            st = self._tls.state = (DetectionPipeline(self.base.cfg, self.device.index), torch.cuda.Stream(self.device))
+            self._ctxs.append(st[0].ctx)
+        return st
+
+    def _run(self, start_event, args, kwargs):
+        pipe, stream = self._worker_state()
+        with torch.cuda.stream(stream):
+            if start_event is not None:
+                stream.wait_event(start_event)
+            res = pipe.run_device(*args, **kwargs)          # ends with the block's final read-back (stream sync)
+            done = torch.cuda.Event()
+            done.record(stream)
+        return res, done, pipe.ctx.launch_count()
+
+    def map(self, blocks, start_event=None) -> List[DetectionResult]:
+        """``blocks``: iterable of ``(args, kwargs)`` for :meth:`DetectionPipeline.run_device`. Returns the results
+        in order; the current stream waits for all of them."""
+        futs = [self._pool.submit(self._run, start_event, a, k) for a, k in blocks]
+        out = []
+        cur = torch.cuda.current_stream(self.device)
+        for f in futs:
+            res, done, _ = f.result()
+            cur.wait_event(done)
+            out.append(res)
+        return out
+
+    def launch_count(self) -> int:
+        """Kernels launched so far by all worker contexts (each worker registers its ctx on first use)."""
+        return sum(c.launch_count() for c in self._ctxs)
+
+    def close(self):
+        self._pool.shutdown(wait=True)

@@ -560,3 +560,31 @@ def test_native_block_driver_equals_staged_path(gpu, kw):
         assert a.land is None and a.points.n == a.raw.n
     empty = pipe.run_device(torch.zeros_like(echo), *tabs)              # nothing above the threshold
     assert empty.raw.n == 0 and empty.points.n == 0 and empty.n_clusters == 0 and empty.labels.numel() == 0
+
+
+def test_overlapped_pipeline_equals_sequential(gpu):
+    """Two host threads / CUDA streams / library contexts running blocks concurrently give the per-block results
+    of the sequential driver."""
+    from radar_point_cloud_tracking_b200.pipeline import DetectionConfig, DetectionPipeline, OverlappedPipeline
+    cfg = DetectionConfig()
+    specs = [syn.SweepSpec(seed=40 + k, frames=12, spokes=256, bins=1024, clutter_p=0.006, land_blobs=2, buoys=2, boats=2) for k in range(5)]
+    pipe = DetectionPipeline(cfg, 0)
+    blocks, want = [], []
+    for sp in specs:
+        echo = gpu.synth_echo(sp)
+        c, s, r = pipe.spoke_tables(sp.angle_units(), sp.scale(), sp.frames, sp.bins)
+        tabs = [torch.from_numpy(t).to(echo.device) for t in (c, s, r)]
+        blocks.append(((echo, *tabs), {}))
+        want.append(pipe.run_device(echo, *tabs))
+    torch.cuda.synchronize()
+    op = OverlappedPipeline(cfg, 0, workers=2)
+    try:
+        got = op.map(blocks * 2)
+        torch.cuda.synchronize()
+        assert op.launch_count() > 0
+    finally:
+        op.close()
+    for k, g in enumerate(got):
+        w = want[k % len(want)]
+        assert g.points.n == w.points.n and g.n_clusters == w.n_clusters
+        assert torch.equal(g.labels, w.labels) and torch.equal(g.points.x[:g.points.n], w.points.x[:w.points.n])
