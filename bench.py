@@ -37,7 +37,7 @@ WORKLOAD = "config3-shard: gain-fused 40/50/75, 2048x1024 sweeps, land filter, S
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames-per-step", type=int, default=128, help="frames per rank and step")
@@ -47,10 +47,21 @@ def parse_args():
     ap.add_argument("--clutter-p", type=float, default=0.003)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--streams", type=int, default=2, help="N=1: blocks in flight (host threads x CUDA streams) for `value`")
+    ap.add_argument("--streams", type=int, default=3, help="N=1: blocks in flight (host threads x CUDA streams) for `value`")
     ap.add_argument("--cpu-frames", type=int, default=64, help="frames per CPU worker in the reference/cpu_baseline sample")
     ap.add_argument("--shard-profile", action="store_true", help="N>1: print per-stage wall-clock of the sharded driver to stderr")
     return ap.parse_args()
+
+
+def load_traffic(frames_per_launch: int):
+    """DRAM bytes (read + write) of the mask kernel per launch, from the committed ncu --set full capture,
+    scaled from the captured launch size to this run's (the kernel's traffic is proportional to its input)."""
+    p = REPO / "profiles" / "r01_ncu_spoke_v4_traffic.json"
+    if not p.exists():
+        return None, None
+    d = json.loads(p.read_text())
+    per_frame = (d["dram_bytes_read"] + d["dram_bytes_write"]) / d["frames_per_launch"]
+    return int(per_frame * frames_per_launch), f"{d['capture']}: {d['dram_bytes_read']} B read + {d['dram_bytes_write']} B written per {d['frames_per_launch']}-frame launch, scaled to {frames_per_launch} frames"
 
 
 def load_peaks():
@@ -63,26 +74,62 @@ def load_peaks():
 
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock / throttle reasons sampled DURING the timed region: NVML through nvidia_ml_py (a query takes
+    well under a millisecond, so even a 10 ms timed region gets several samples); nvidia-smi as fallback."""
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, period_s: float = 0.002):
         self.index = index
-        self.rows = []
+        self.period = period_s
+        self.rows = []            # (sm_mhz, max_mhz, power_w, reason bits)
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
+        self.source = "nvml"
 
-    def _run(self):
+    def _run_nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = self.index
+        if visible:
+            try:
+                idx = int(visible.split(",")[self.index])
+            except (ValueError, IndexError):
+                pass
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            try:
+                pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+            except Exception:
+                pw = 0.0
+            self.rows.append((float(sm), float(mx), pw, int(get_reasons(h))))
+            self._stop.wait(self.period)
+
+    def _run_smi(self):
+        self.source = "nvidia-smi"
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
                                       "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
-                    self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
+                    c = [v.strip() for v in out.splitlines()[0].split(",")]
+                    bits = sum(bit for (name, bit), v in zip(self.REASONS.items(), c[3:7]) if v.lower().startswith("active"))
+                    self.rows.append((float(c[0]), float(c[1]), float(c[2]) if c[2].replace(".", "").isdigit() else 0.0, bits))
             except Exception:
                 pass
             self._stop.wait(0.2)
+
+    def _run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
 
     def __enter__(self):
         self._t.start()
@@ -92,15 +139,17 @@ class ClockSampler:
         self._stop.set()
         self._t.join(timeout=6)
 
-    def summary(self):
-        if not self.rows:
+    def mark(self):
+        """Index of the next sample: call at the start of the timed region."""
+        return len(self.rows)
+
+    def summary(self, first: int = 0, last=None):
+        rows = self.rows[first:last] or self.rows
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        reasons = [n for n, bit in self.REASONS.items() if any(r[3] & bit for r in rows)]
+        return {"sm_mhz": statistics.median(r[0] for r in rows), "sm_max_mhz": max(r[1] for r in rows),
+                "power_w_max": max(r[2] for r in rows), "reasons": reasons, "samples": len(rows), "source": self.source}
 
 
 # ------------------------------------------------------------------------------------ CPU (oracle port)
@@ -254,14 +303,19 @@ def run_ours(args):
             barrier()
             l0 = overlapped.launch_count()
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0 = clocks.mark()
             ev0.record()
             results = overlapped.map([block] * args.steps, start_event=ev0)
             ev1.record()
             barrier()
+            c1 = clocks.mark()
             ms, launches = ev0.elapsed_time(ev1), overlapped.launch_count() - l0
         else:
-            ms, launches = timed(lambda: pipe.run_device(echo, d_c, d_s, d_r, frame_ids), args.steps, args.warmup,
-                                 collect=results.append)
+            for _ in range(args.warmup):
+                pipe.run_device(echo, d_c, d_s, d_r, frame_ids)
+            c0 = clocks.mark()
+            ms, launches = timed(lambda: pipe.run_device(echo, d_c, d_s, d_r, frame_ids), args.steps, 0, collect=results.append)
+            c1 = clocks.mark()
     res = results[-1]
     n_raw, n_pts = res.raw.n, res.points.n
     echo_bytes = B * G * args.spokes * args.bins * 4
@@ -278,6 +332,7 @@ def run_ours(args):
     achieved = echo_bytes / (mask_ms * 1e-3) / 1e9 if mask_ms > 0 else 0.0
     spoke_ms_mean = mask_ms + offs_ms + emit_ms                               # first event to last event of the stage
     stage_gbs = spoke_bytes / (spoke_ms_mean * 1e-3) / 1e9 if spoke_ms_mean > 0 else 0.0
+    traffic, traffic_src = load_traffic(B)
     frames_total = B * world * args.steps
     value = frames_total / (ms * 1e-3)
     pts_t = torch.tensor([n_raw, n_pts, res.n_clusters], device=device, dtype=torch.int64)
@@ -323,7 +378,8 @@ def run_ours(args):
         "points_per_step": {"after_stride": n_raw_all, "after_land_filter": n_pts_all, "clusters": int(pts_t[2])},
         "roofline": {"bound": "hbm", "kernel": "spoke_mask_tma_kernel", "achieved": achieved, "peak": hbm_peak,
                      "unit": "GB/s", "frac": achieved / hbm_peak, "frac_of_nominal_8TBs": achieved / 8000.0,
-                     "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_launch": echo_bytes,
+                     "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
+                     "algorithmic_bytes_per_launch": echo_bytes,
                      "kernel_ms": mask_ms, "share_of_step": mask_ms / (ms / args.steps),
                      "note": "dominant kernel of the spoke-to-point stage: reads every echo byte once (algorithmic "
                              "bytes = echo tensor only; its 1-bit/cell mask output is overhead, not counted)",
@@ -337,7 +393,7 @@ def run_ours(args):
                      "pair_tests": [st["pair_tests_count"], st["pair_tests_union"], st["pair_tests_border"]], "tight": st["tight"],
                      "cells": st["n_cells"], "dims": st["dims"], "time_radius": st["time_radius"]},
         "gpu_launches": launches,
-        "clocks": clocks.summary(),
+        "clocks": clocks.summary(c0, c1),
     }
     if e2e:
         line["e2e"] = e2e
