@@ -76,6 +76,16 @@ int rb_spoke_to_points(rb_ctx* ctx, const float* echo, const float* cos_tab, con
                        float* x, float* y, float* inten, int32_t* gain, int64_t cap,
                        int64_t* sweep_base, void* stream);
 
+/* The same with uint8 echoes (what the radar delivers: 0..255, a quarter of the bytes to move): survives when
+ * (float)echo > threshold, intensity = (float)echo. Results are identical to rb_spoke_to_points on the same values
+ * converted to float32. The TMA-staged kernel needs S*E % 16 == 0 and a 16-byte aligned pointer. */
+int rb_spoke_to_points_u8(rb_ctx* ctx, const uint8_t* echo, const float* cos_tab, const float* sin_tab,
+                          const float* range_res, const float* ranges, const int32_t* sweep_gain,
+                          int64_t n_sweeps, int n_spokes, int n_bins,
+                          float threshold, int stride,
+                          float* x, float* y, float* inten, int32_t* gain, int64_t cap,
+                          int64_t* sweep_base, void* stream);
+
 /* polar_to_cartesian on a full grid (PKG/core/transforms.py:13-34): x = ranges*cos[:,None],
  * y = ranges*sin[:,None]; ranges/x/y float32 [n_rows][n_cols], cos/sin float32 [n_rows] from the
  * host's numpy. No sync. */
@@ -232,6 +242,7 @@ typedef struct rb_detect_params {
     float eps_time;
     int32_t min_samples;
     int32_t cluster;                /* 0 = stop after the land filter */
+    int32_t echo_u8;                /* 1 = `echo` points at uint8 cells (rb_spoke_to_points_u8) */
 } rb_detect_params;
 
 typedef struct rb_detect_buffers {

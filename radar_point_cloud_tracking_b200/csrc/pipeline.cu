@@ -54,9 +54,14 @@ extern "C" int rb_detect_block(rb_ctx* ctx, const float* echo, const float* cos_
     RB_TRY(rb_scratch_get(ctx, RB_S_PIPE, sizeof(int64_t) * (size_t)(W + 1) + 64, &sb_v));
     int64_t* sweep_base = (int64_t*)sb_v;
     float* d_bounds = (float*)(sweep_base + W + 1);
-    RB_TRY(rb_spoke_to_points(ctx, echo, cos_tab, sin_tab, range_res, nullptr, sweep_gain, W, prm->n_spokes, prm->n_bins,
-                              prm->intensity_threshold, prm->point_stride, buf->x, buf->y, buf->inten, buf->gain, buf->cap,
-                              sweep_base, stream_));
+    if (prm->echo_u8)
+        RB_TRY(rb_spoke_to_points_u8(ctx, reinterpret_cast<const uint8_t*>(echo), cos_tab, sin_tab, range_res, nullptr, sweep_gain, W,
+                                     prm->n_spokes, prm->n_bins, prm->intensity_threshold, prm->point_stride, buf->x, buf->y,
+                                     buf->inten, buf->gain, buf->cap, sweep_base, stream_));
+    else
+        RB_TRY(rb_spoke_to_points(ctx, echo, cos_tab, sin_tab, range_res, nullptr, sweep_gain, W, prm->n_spokes, prm->n_bins,
+                                  prm->intensity_threshold, prm->point_stride, buf->x, buf->y, buf->inten, buf->gain, buf->cap,
+                                  sweep_base, stream_));
     RB_TRY(rb_frame_offsets(ctx, sweep_base, F, prm->gains_per_frame, buf->frame_off, stream_));
     if (buf->cap > 0) RB_TRY(rb_bounds_devn(ctx, buf->x, buf->y, sweep_base + W, buf->cap, d_bounds, stream));
     // read-back 1: frame offsets (point count, frames built) + bounds

@@ -83,6 +83,40 @@ __device__ __forceinline__ unsigned nibble(const float4& v, float thr, const Lan
     return (set_gt(v.x, thr) & lb.b0) | (set_gt(v.y, thr) & lb.b1) | (set_gt(v.z, thr) & lb.b2) | (set_gt(v.w, thr) & lb.b3);
 }
 
+// Echo element types: float32 (the reference's in-memory type, T4:206) and uint8 (what the radar delivers,
+// 0..255, PIPELINE_DOCUMENTATION.txt:47 - a quarter of the bytes to move). For uint8 the float comparison
+// (float)e > thr is the integer comparison e >= lb with lb = 0 for thr < 0, floor(thr) + 1 otherwise (lb > 255 or a
+// NaN threshold: nothing survives), evaluated four cells at a time with the SIMD byte compare.
+struct ThrArg {
+    float thr;              // float32 path
+    unsigned lb4;           // uint8 path: lower bound replicated into the four bytes
+    int none;               // uint8 path: nothing can survive
+};
+inline ThrArg make_thr(float thr) {
+    ThrArg a; a.thr = thr; a.lb4 = 0; a.none = 0;
+    if (!(thr == thr)) { a.none = 1; return a; }                      // NaN: every comparison is false
+    if (thr < 0.f) return a;                                          // every byte >= 0 passes
+    const double lb = floor((double)thr) + 1.0;
+    if (lb > 255.0) { a.none = 1; return a; }
+    a.lb4 = (unsigned)lb * 0x01010101u;
+    return a;
+}
+template <typename T> struct Elem;
+template <> struct Elem<float>   { static constexpr int STAGE_TILES = 4;  static constexpr int ALIGN_CELLS = 4; };   // 64 KiB stages,
+template <> struct Elem<uint8_t> { static constexpr int STAGE_TILES = 16; static constexpr int ALIGN_CELLS = 16; }; // 16-byte bulk copies
+
+__device__ __forceinline__ unsigned nibble_u8(unsigned word, const ThrArg& t, unsigned sh) {
+    const unsigned r = t.none ? 0u : __vcmpgeu4(word, t.lb4);          // 0xff in every byte that survives
+    return (((r & 0x01010101u) * 0x01020408u) >> 24) << sh;           // gather the four flags into bits 0..3
+}
+// survivor nibble of lane's 4 cells of chunk k of a 1024-cell batch held in shared memory
+template <typename T>
+__device__ __forceinline__ unsigned batch_nibble(const unsigned char* __restrict__ batch, int k, unsigned lane, const ThrArg& t,
+                                                 const LaneBits& lb) {
+    if (sizeof(T) == 4) return nibble(reinterpret_cast<const float4*>(batch)[k * 32 + lane], t.thr, lb);
+    return nibble_u8(reinterpret_cast<const unsigned*>(batch)[k * 32 + lane], t, 4u * (lane & 7u));
+}
+
 // transposing OR-butterfly over the 8 lanes of a group: 8 -> 4 -> 2 -> 1 registers
 __device__ __forceinline__ unsigned butterfly8(const unsigned (&nib)[8], unsigned lane) {
     unsigned a4[4], a2[2];
@@ -106,11 +140,13 @@ __device__ __forceinline__ unsigned butterfly8(const unsigned (&nib)[8], unsigne
     return keep | __shfl_xor_sync(0xffffffffu, give, 4);
 }
 
-struct TileRef { const float* src; int valid; };                          // first cell + cells inside the sweep
-__device__ __forceinline__ TileRef tile_ref(const float* echo, const SpokeGeom& g, long long tile) {
+template <typename T>
+struct TileRef { const T* src; int valid; };                              // first cell + cells inside the sweep
+template <typename T>
+__device__ __forceinline__ TileRef<T> tile_ref(const T* echo, const SpokeGeom& g, long long tile) {
     const int w = (int)(tile / g.tiles_per_sweep);
     const int cell0 = (int)(tile - (long long)w * g.tiles_per_sweep) * SK_TILE;
-    return TileRef{echo + (int64_t)w * g.sweep_cells + cell0, min(SK_TILE, g.sweep_cells - cell0)};
+    return TileRef<T>{echo + (int64_t)w * g.sweep_cells + cell0, min(SK_TILE, g.sweep_cells - cell0)};
 }
 
 // ---- 1a. TMA-staged variant (the default) --------------------------------------------------------------
@@ -124,24 +160,24 @@ __device__ __forceinline__ TileRef tile_ref(const float* echo, const SpokeGeom& 
 // 4.8 instead of 7.0 TB/s, tools/mask_bench.cu).
 constexpr int MT_WARPS = 8;                                                // consumer warps
 constexpr int MT_STAGES = 3;
-constexpr int MT_TILES = 4;                                                // tiles per stage
-constexpr int MT_STAGE_CELLS = MT_TILES * SK_TILE;                         // 16384 cells = 64 KiB
-constexpr int MT_STAGE_BATCHES = MT_STAGE_CELLS / SK_BATCH_CELLS;          // 16
+constexpr int MT_STAGE_BYTES = 64 * 1024;                                  // 4 float32 tiles or 16 uint8 tiles
 constexpr int MT_THREADS = MT_WARPS * 32 + 32;
 
+template <int TILES>
 struct MtMeta {
     long long first_tile;                 // global id of the stage's first tile; < 0: no more work
     int n_tiles;
-    int valid[MT_TILES];                  // cells of each tile inside its sweep
-    unsigned cnt[MT_TILES];               // survivors, accumulated by the consumers
+    int valid[TILES];                     // cells of each tile inside its sweep
+    unsigned cnt[TILES];                  // survivors, accumulated by the consumers
 };
+template <int TILES>
 struct __align__(128) MtSmem {
-    float ring[MT_STAGES][MT_STAGE_CELLS];
+    unsigned char ring[MT_STAGES][MT_STAGE_BYTES];
     unsigned long long full[MT_STAGES];
     unsigned long long empty[MT_STAGES];
-    MtMeta meta[MT_STAGES];
+    MtMeta<TILES> meta[MT_STAGES];
 };
-constexpr int MT_SMEM = (int)sizeof(MtSmem) + 128;
+template <typename T> constexpr int mt_smem_bytes() { return (int)sizeof(MtSmem<Elem<T>::STAGE_TILES>) + 128; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
@@ -170,11 +206,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+template <typename T>
 __global__ void __launch_bounds__(MT_THREADS, 1)
-spoke_mask_tma_kernel(const float* __restrict__ echo, const SpokeGeom g, const float threshold,
+spoke_mask_tma_kernel(const T* __restrict__ echo, const SpokeGeom g, const ThrArg threshold,
                       uint32_t* __restrict__ mask, uint32_t* __restrict__ tile_count, unsigned* __restrict__ ticket) {
+    constexpr int MT_TILES = Elem<T>::STAGE_TILES;
+    constexpr int MT_STAGE_BATCHES = MT_TILES * SK_BATCHES;
+    static_assert(MT_TILES * SK_TILE * sizeof(T) == MT_STAGE_BYTES, "a stage is 64 KiB");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    MtSmem& sm = *reinterpret_cast<MtSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    MtSmem<MT_TILES>& sm = *reinterpret_cast<MtSmem<MT_TILES>*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
     const unsigned lane = rb_lane();
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
@@ -195,7 +235,7 @@ spoke_mask_tma_kernel(const float* __restrict__ echo, const SpokeGeom g, const f
         // ================= producer (one thread) =================
         if (lane != 0) return;
         auto flush = [&](int s) {                                          // counts of the stage that just left slot s
-            MtMeta& m = sm.meta[s];
+            MtMeta<MT_TILES>& m = sm.meta[s];
             for (int t = 0; t < m.n_tiles; ++t) {
                 tile_count[m.first_tile + t] = m.cnt[t];
                 m.cnt[t] = 0;
@@ -209,7 +249,7 @@ spoke_mask_tma_kernel(const float* __restrict__ echo, const SpokeGeom g, const f
                 mbar_wait(&sm.empty[s], (uint32_t)(it / MT_STAGES - 1) & 1u);
                 flush(s);
             }
-            MtMeta& m = sm.meta[s];
+            MtMeta<MT_TILES>& m = sm.meta[s];
             if (st >= n_stages) {                                          // end marker for the consumers
                 m.first_tile = -1;
                 m.n_tiles = 0;
@@ -220,18 +260,18 @@ spoke_mask_tma_kernel(const float* __restrict__ echo, const SpokeGeom g, const f
             const int nt = (int)min((long long)MT_TILES, g.total_tiles - t0);
             m.first_tile = t0;
             m.n_tiles = nt;
-            TileRef tr[MT_TILES];
             uint32_t bytes = 0;
-#pragma unroll
             for (int t = 0; t < MT_TILES; ++t) {
-                tr[t] = t < nt ? tile_ref(echo, g, t0 + t) : TileRef{nullptr, 0};
-                m.valid[t] = tr[t].valid;
-                bytes += (uint32_t)tr[t].valid * 4u;
+                const int v = t < nt ? tile_ref<T>(echo, g, t0 + t).valid : 0;
+                m.valid[t] = v;
+                bytes += (uint32_t)v * (uint32_t)sizeof(T);
             }
             mbar_expect_tx(&sm.full[s], bytes);
-#pragma unroll
-            for (int t = 0; t < MT_TILES; ++t)
-                if (tr[t].valid > 0) bulk_g2s(&sm.ring[s][t * SK_TILE], tr[t].src, (uint32_t)tr[t].valid * 4u, &sm.full[s]);
+            for (int t = 0; t < nt; ++t) {
+                const TileRef<T> tr = tile_ref<T>(echo, g, t0 + t);
+                if (tr.valid > 0)
+                    bulk_g2s(&sm.ring[s][(size_t)t * SK_TILE * sizeof(T)], tr.src, (uint32_t)tr.valid * (uint32_t)sizeof(T), &sm.full[s]);
+            }
             st = (long long)gridDim.x + atomicAdd(ticket, 1u);
             ++it;
         }
@@ -250,28 +290,25 @@ spoke_mask_tma_kernel(const float* __restrict__ echo, const SpokeGeom g, const f
     for (int it = 0;; ++it) {
         const int s = it % MT_STAGES;
         mbar_wait(&sm.full[s], (uint32_t)(it / MT_STAGES) & 1u);
-        MtMeta& m = sm.meta[s];
+        MtMeta<MT_TILES>& m = sm.meta[s];
         const long long t0 = m.first_tile;
         if (t0 < 0) break;
         const int nt = m.n_tiles;
-        const float4* __restrict__ b4 = reinterpret_cast<const float4*>(sm.ring[s]);
-#pragma unroll
+#pragma unroll 2
         for (int b = warp; b < MT_STAGE_BATCHES; b += MT_WARPS) {
             const int t = b / SK_BATCHES;                                  // tile of the batch inside the stage
             if (t >= nt) break;
             const int valid = m.valid[t] - (b % SK_BATCHES) * SK_BATCH_CELLS;   // cells of this batch inside the sweep
+            const unsigned char* __restrict__ batch = sm.ring[s] + (size_t)b * SK_BATCH_CELLS * sizeof(T);
             unsigned nib[SK_BATCH];
             if (valid >= SK_BATCH_CELLS) {
-                float4 v[SK_BATCH];
 #pragma unroll
-                for (int k = 0; k < SK_BATCH; ++k) v[k] = b4[b * (SK_BATCH_CELLS / 4) + k * 32 + lane];
-#pragma unroll
-                for (int k = 0; k < SK_BATCH; ++k) nib[k] = nibble(v[k], threshold, lb);
+                for (int k = 0; k < SK_BATCH; ++k) nib[k] = batch_nibble<T>(batch, k, lane, threshold, lb);
             } else {
 #pragma unroll
                 for (int k = 0; k < SK_BATCH; ++k) {
                     const int c = k * 128 + (int)lane * 4;                  // valid is a multiple of 4 here
-                    nib[k] = c < valid ? nibble(b4[b * (SK_BATCH_CELLS / 4) + k * 32 + lane], threshold, lb) : 0u;
+                    nib[k] = c < valid ? batch_nibble<T>(batch, k, lane, threshold, lb) : 0u;
                 }
             }
             const unsigned word = butterfly8(nib, lane);
@@ -285,10 +322,11 @@ spoke_mask_tma_kernel(const float* __restrict__ echo, const SpokeGeom g, const f
 }
 
 // ---- 1b. register-staged variant (any shape; 128-bit loads when VEC) -------------------------------------
-template <bool VEC>
+template <typename T, bool VEC>
 __global__ void __launch_bounds__(SK_THREADS, SK_CTAS_PER_SM)
-spoke_mask_kernel(const float* __restrict__ echo, const SpokeGeom g, const float threshold,
+spoke_mask_kernel(const T* __restrict__ echo, const SpokeGeom g, const float threshold,
                   uint32_t* __restrict__ mask, uint32_t* __restrict__ tile_count) {
+    static_assert(!VEC || sizeof(T) == 4, "128-bit path is float32 only");
     const unsigned lane = rb_lane();
     const LaneBits lb = lane_bits(lane);
     const unsigned sh = 4u * (lane & 7u);
@@ -296,9 +334,9 @@ spoke_mask_kernel(const float* __restrict__ echo, const SpokeGeom g, const float
     // static round-robin over the tiles: a per-warp ticket would serialise on the atomic unit (see above)
     const long long n_warps = (long long)gridDim.x * SK_WARPS;
     for (long long tile = (long long)blockIdx.x * SK_WARPS + (threadIdx.x >> 5); tile < g.total_tiles; tile += n_warps) {
-        const TileRef tr = tile_ref(echo, g, tile);
+        const TileRef<T> tr = tile_ref<T>(echo, g, tile);
         const int valid = tr.valid;
-        const float* __restrict__ src = tr.src;
+        const T* __restrict__ src = tr.src;
         uint32_t* __restrict__ mw = mask + tile * SK_WORDS;
         unsigned cnt = 0;
 #pragma unroll 1
@@ -306,17 +344,18 @@ spoke_mask_kernel(const float* __restrict__ echo, const SpokeGeom g, const float
             const int c0 = b * SK_BATCH_CELLS + (int)lane * 4;
             unsigned nib[SK_BATCH];
             if (VEC) {
+                const float* __restrict__ fsrc = reinterpret_cast<const float*>(src);
                 if (valid == SK_TILE) {
                     float4 v[SK_BATCH];
 #pragma unroll
-                    for (int k = 0; k < SK_BATCH; ++k) v[k] = rb_ld_stream4(src + c0 + k * 128);
+                    for (int k = 0; k < SK_BATCH; ++k) v[k] = rb_ld_stream4(fsrc + c0 + k * 128);
 #pragma unroll
                     for (int k = 0; k < SK_BATCH; ++k) nib[k] = nibble(v[k], threshold, lb);
                 } else {
 #pragma unroll
                     for (int k = 0; k < SK_BATCH; ++k) {
                         const int c = c0 + k * 128;
-                        nib[k] = c < valid ? nibble(rb_ld_stream4(src + c), threshold, lb) : 0u;
+                        nib[k] = c < valid ? nibble(rb_ld_stream4(fsrc + c), threshold, lb) : 0u;
                     }
                 }
             } else {
@@ -326,7 +365,7 @@ spoke_mask_kernel(const float* __restrict__ echo, const SpokeGeom g, const float
                     unsigned m = 0;
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        if (c + i < valid) m |= (unsigned)(__ldg(src + c + i) > threshold) << i;
+                        if (c + i < valid) m |= (unsigned)((float)__ldg(src + c + i) > threshold) << i;
                     nib[k] = m << sh;
                 }
             }
@@ -409,8 +448,9 @@ spoke_offsets_kernel(const uint32_t* __restrict__ tile_count, uint32_t* __restri
 }
 
 // ---- 3. emit ------------------------------------------------------------------------------------------
+template <typename T>
 struct EmitArgs {
-    const float* echo;
+    const T* echo;
     const float* cos_tab;
     const float* sin_tab;
     const float* range_res;
@@ -443,7 +483,8 @@ __device__ __forceinline__ int select_bit(uint32_t word, uint32_t o) {   // posi
     return pos;
 }
 
-__global__ void __launch_bounds__(SK_THREADS) spoke_emit_kernel(const EmitArgs a) {
+template <typename T>
+__global__ void __launch_bounds__(SK_THREADS) spoke_emit_kernel(const EmitArgs<T> a) {
     __shared__ uint4 s_mask[SK_WARPS][SK_ENTRIES];
     __shared__ uint32_t s_rank[SK_WARPS][SK_ENTRIES];
     const unsigned lane = rb_lane();
@@ -510,7 +551,7 @@ __global__ void __launch_bounds__(SK_THREADS) spoke_emit_kernel(const EmitArgs a
         if (pos < a.cap) {
             const int sp = (int)fastdiv((uint32_t)cell, a.div_bins);
             const int j = cell - sp * a.g.n_bins;
-            const float val = __ldg(a.echo + cell_off + cell);
+            const float val = (float)__ldg(a.echo + cell_off + cell);
             const float cs = __ldg(a.cos_tab + tab_off + sp), sn = __ldg(a.sin_tab + tab_off + sp);
             const float rng = a.ranges ? __ldg(a.ranges + cell_off + cell)
                                        : __fmul_rn(__ldg(a.range_res + tab_off + sp), (float)j);   // T4:214
@@ -567,11 +608,11 @@ extern "C" int rb_polar_to_cartesian(rb_ctx* ctx, const float* ranges, const flo
     return RB_OK;
 }
 
-extern "C" int rb_spoke_to_points(rb_ctx* ctx, const float* echo, const float* cos_tab, const float* sin_tab,
-                                  const float* range_res, const float* ranges, const int32_t* sweep_gain,
-                                  int64_t n_sweeps,
-                                  int n_spokes, int n_bins, float threshold, int stride, float* x, float* y,
-                                  float* inten, int32_t* gain, int64_t cap, int64_t* sweep_base, void* stream_) {
+template <typename T>
+int spoke_to_points_impl(rb_ctx* ctx, const T* echo, const float* cos_tab, const float* sin_tab,
+                         const float* range_res, const float* ranges, const int32_t* sweep_gain, int64_t n_sweeps,
+                         int n_spokes, int n_bins, float threshold, int stride, float* x, float* y,
+                         float* inten, int32_t* gain, int64_t cap, int64_t* sweep_base, void* stream_) {
     RB_REQUIRE(ctx, "ctx is NULL");
     RB_REQUIRE(n_sweeps >= 0 && n_spokes >= 0 && n_bins >= 0, "negative size");
     RB_REQUIRE(sweep_base, "sweep_base is NULL");
@@ -618,26 +659,28 @@ extern "C" int rb_spoke_to_points(rb_ctx* ctx, const float* echo, const float* c
         for (int i = 0; i < 4; ++i) RB_CUDA(cudaEventCreate(&ctx->spoke_ev[i]));
     if (prof) RB_CUDA(cudaEventRecord(ctx->spoke_ev[0], stream));
 
-    const bool vec = (cells % 4 == 0) && (((uintptr_t)echo & 15u) == 0);
+    // the TMA-staged kernel moves whole tiles with 16-byte bulk copies: the sweeps must be a multiple of 16 bytes
+    const bool vec = (cells % Elem<T>::ALIGN_CELLS == 0) && (((uintptr_t)echo & 15u) == 0);
     // 0 = auto (TMA-staged when the shape allows 16-byte bulk copies), 1 = register-staged, 2 = require TMA
     const int variant = ctx->opt_spoke_mask_variant;
-    RB_REQUIRE(variant != 2 || vec, "TMA-staged mask kernel needs S*E % 4 == 0 and a 16-byte aligned echo pointer");
+    RB_REQUIRE(variant != 2 || vec, "TMA-staged mask kernel needs sweeps of a multiple of 16 bytes and a 16-byte aligned echo pointer");
     if (vec && variant != 1) {
-        static bool attr_set = false;
+        static bool attr_set = false;                   // one flag per element type (template instance)
+        constexpr int smem = mt_smem_bytes<T>();
         if (!attr_set) {
-            RB_CUDA(cudaFuncSetAttribute(spoke_mask_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM));
+            RB_CUDA(cudaFuncSetAttribute(spoke_mask_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             attr_set = true;
         }
-        const int64_t want_blocks = rb_div_up(g.total_tiles, MT_TILES);
+        const int64_t want_blocks = rb_div_up(g.total_tiles, Elem<T>::STAGE_TILES);
         const unsigned blocks = (unsigned)(want_blocks < ctx->sm_count ? want_blocks : ctx->sm_count);
-        spoke_mask_tma_kernel<<<blocks, MT_THREADS, MT_SMEM, stream>>>(echo, g, threshold, mask, tile_count, ticket);
+        spoke_mask_tma_kernel<T><<<blocks, MT_THREADS, smem, stream>>>(echo, g, make_thr(threshold), mask, tile_count, ticket);
         ctx->spoke_last_variant = 2;
     } else {
         const int64_t want_blocks = rb_div_up(g.total_tiles, SK_WARPS);
         const int64_t max_blocks = (int64_t)ctx->sm_count * SK_CTAS_PER_SM;
         const unsigned blocks = (unsigned)(want_blocks < max_blocks ? want_blocks : max_blocks);
-        if (vec) spoke_mask_kernel<true><<<blocks, SK_THREADS, 0, stream>>>(echo, g, threshold, mask, tile_count);
-        else spoke_mask_kernel<false><<<blocks, SK_THREADS, 0, stream>>>(echo, g, threshold, mask, tile_count);
+        if (vec && sizeof(T) == 4) spoke_mask_kernel<T, sizeof(T) == 4><<<blocks, SK_THREADS, 0, stream>>>(echo, g, threshold, mask, tile_count);
+        else spoke_mask_kernel<T, false><<<blocks, SK_THREADS, 0, stream>>>(echo, g, threshold, mask, tile_count);
         ctx->spoke_last_variant = 1;
     }
     RB_LAUNCH_CHECK(ctx);
@@ -649,7 +692,7 @@ extern "C" int rb_spoke_to_points(rb_ctx* ctx, const float* echo, const float* c
     if (prof) RB_CUDA(cudaEventRecord(ctx->spoke_ev[2], stream));
 
     if (cap > 0) {
-        EmitArgs a;
+        EmitArgs<T> a;
         a.echo = echo; a.cos_tab = cos_tab; a.sin_tab = sin_tab; a.range_res = range_res; a.ranges = ranges;
         a.sweep_gain = sweep_gain;
         a.mask = mask; a.tile_count = tile_count; a.tile_prefix = tile_prefix; a.sweep_base = sweep_base;
@@ -663,11 +706,27 @@ extern "C" int rb_spoke_to_points(rb_ctx* ctx, const float* echo, const float* c
         a.div_bins = make_fastdiv((uint32_t)n_bins);
         const int64_t eblocks = rb_div_up(a.total_groups, SK_WARPS);
         RB_REQUIRE(eblocks < (int64_t)1 << 31, "too many tiles in one batch; split the batch");
-        spoke_emit_kernel<<<(unsigned)eblocks, SK_THREADS, 0, stream>>>(a);
+        spoke_emit_kernel<T><<<(unsigned)eblocks, SK_THREADS, 0, stream>>>(a);
         RB_LAUNCH_CHECK(ctx);
     }
     if (prof) RB_CUDA(cudaEventRecord(ctx->spoke_ev[3], stream));
     return RB_OK;
+}
+
+extern "C" int rb_spoke_to_points(rb_ctx* ctx, const float* echo, const float* cos_tab, const float* sin_tab,
+                                  const float* range_res, const float* ranges, const int32_t* sweep_gain,
+                                  int64_t n_sweeps, int n_spokes, int n_bins, float threshold, int stride, float* x, float* y,
+                                  float* inten, int32_t* gain, int64_t cap, int64_t* sweep_base, void* stream_) {
+    return spoke_to_points_impl<float>(ctx, echo, cos_tab, sin_tab, range_res, ranges, sweep_gain, n_sweeps, n_spokes, n_bins,
+                                       threshold, stride, x, y, inten, gain, cap, sweep_base, stream_);
+}
+
+extern "C" int rb_spoke_to_points_u8(rb_ctx* ctx, const uint8_t* echo, const float* cos_tab, const float* sin_tab,
+                                     const float* range_res, const float* ranges, const int32_t* sweep_gain,
+                                     int64_t n_sweeps, int n_spokes, int n_bins, float threshold, int stride, float* x, float* y,
+                                     float* inten, int32_t* gain, int64_t cap, int64_t* sweep_base, void* stream_) {
+    return spoke_to_points_impl<uint8_t>(ctx, echo, cos_tab, sin_tab, range_res, ranges, sweep_gain, n_sweeps, n_spokes, n_bins,
+                                         threshold, stride, x, y, inten, gain, cap, sweep_base, stream_);
 }
 
 extern "C" int rb_frame_offsets(rb_ctx* ctx, const int64_t* sweep_base, int64_t n_frames, int gains_per_frame,

@@ -55,7 +55,9 @@ def spoke_to_points_raw(echo: torch.Tensor, cos_tab: torch.Tensor, sin_tab: torc
     """One launch over ``echo[W,S,E]``; returns ``(x, y, inten, gain, sweep_base)`` without syncing.
     ``sweep_base[W]`` (device) is the true total, which may exceed ``cap`` (then points were dropped)."""
     ctx = context(echo.device.index)
-    echo = _dev(echo, torch.float32, "echo")
+    if echo.dtype not in (torch.float32, torch.uint8):
+        raise RadarB200Error(f"echo must be float32 or uint8, got {echo.dtype}")
+    echo = _dev(echo, echo.dtype, "echo")
     if echo.dim() != 3:
         raise RadarB200Error("echo must be [sweeps, spokes, bins]")
     W, S, E = echo.shape
@@ -88,9 +90,10 @@ def spoke_to_points_raw(echo: torch.Tensor, cos_tab: torch.Tensor, sin_tab: torc
     if events is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    check(ctx.lib.rb_spoke_to_points(ctx.handle, ptr(echo), ptr(cos_tab), ptr(sin_tab), ptr(range_res),
-                                     ptr(ranges), ptr(sweep_gain), W, S, E, float(threshold), int(stride),
-                                     ptr(x), ptr(y), ptr(inten), ptr(gain), cap, ptr(sweep_base), stream_ptr()),
+    entry = ctx.lib.rb_spoke_to_points_u8 if echo.dtype == torch.uint8 else ctx.lib.rb_spoke_to_points
+    check(entry(ctx.handle, ptr(echo), ptr(cos_tab), ptr(sin_tab), ptr(range_res),
+                ptr(ranges), ptr(sweep_gain), W, S, E, float(threshold), int(stride),
+                ptr(x), ptr(y), ptr(inten), ptr(gain), cap, ptr(sweep_base), stream_ptr()),
           "rb_spoke_to_points")
     if events is not None:
         e1.record()
@@ -370,7 +373,10 @@ def detect_block(echo: torch.Tensor, cos_tab: torch.Tensor, sin_tab: torch.Tenso
                              x_edges=xe.ctypes.data, y_edges=ye.ctypes.data, max_edges=int(max_edges))
     res = _lib.DetectResult()
     ids = np.ascontiguousarray(frame_ids, dtype=np.float32)
-    rc = ctx.lib.rb_detect_block(ctx.handle, ptr(_dev(echo, torch.float32, "echo")), ptr(_dev(cos_tab, torch.float32, "cos_tab")),
+    if echo.dtype not in (torch.float32, torch.uint8):
+        raise RadarB200Error(f"echo must be float32 or uint8, got {echo.dtype}")
+    params.echo_u8 = int(echo.dtype == torch.uint8)
+    rc = ctx.lib.rb_detect_block(ctx.handle, ptr(_dev(echo, echo.dtype, "echo")), ptr(_dev(cos_tab, torch.float32, "cos_tab")),
                                  ptr(_dev(sin_tab, torch.float32, "sin_tab")), ptr(_dev(range_res, torch.float32, "range_res")),
                                  ptr(_dev(sweep_gain, torch.int32, "sweep_gain")), ids.ctypes.data, C.byref(params), C.byref(buf),
                                  C.byref(res), stream_ptr())

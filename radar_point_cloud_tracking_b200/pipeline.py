@@ -129,7 +129,8 @@ class DetectionPipeline:
     # ---- device path ----------------------------------------------------------------------------
     def run_device(self, echo: torch.Tensor, cos_tab: torch.Tensor, sin_tab: torch.Tensor, range_res: torch.Tensor,
                    frame_ids: Optional[Sequence[int]] = None, cluster: bool = True) -> DetectionResult:
-        """``echo[F,G,S,E]`` float32 already on the device; tables ``[F*G,S]`` on the device.
+        """``echo[F,G,S,E]`` float32 (or uint8: the radar's native 0..255 echoes, identical results, a quarter of
+        the bytes) already on the device; tables ``[F*G,S]`` on the device.
         One library call (``rb_detect_block``): every launch and the small read-backs in between happen in the
         native driver, not in Python."""
         from . import _lib
@@ -215,7 +216,11 @@ class DetectionPipeline:
                  frame_ids: Optional[Sequence[int]] = None, pinned: Optional[torch.Tensor] = None) -> dict:
         """Host buffers in, host buffers out: uploads ``echo[F,G,S,E]`` (numpy or pinned torch tensor),
         computes the spoke tables with numpy, runs the device path and reads the result back."""
-        t_echo = pinned if pinned is not None else torch.from_numpy(np.ascontiguousarray(echo, dtype=np.float32))
+        if pinned is not None:
+            t_echo = pinned
+        else:
+            a = np.asarray(echo)
+            t_echo = torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint8 if a.dtype == np.uint8 else np.float32))
         F, G, S, E = t_echo.shape
         c, s, r = self.spoke_tables(angle_units, scale, F, E)
         d = self.device
@@ -224,7 +229,7 @@ class DetectionPipeline:
                               torch.from_numpy(r).to(d), frame_ids)
         out = res.to_host()
         out["n_clusters"] = res.n_clusters
-        out["h2d_bytes"] = t_echo.numel() * 4 + 3 * c.nbytes
+        out["h2d_bytes"] = t_echo.numel() * t_echo.element_size() + 3 * c.nbytes
         out["d2h_bytes"] = out["points"].nbytes + out["gains"].nbytes + out["labels"].nbytes + out["frame_off"].nbytes
         return out
 

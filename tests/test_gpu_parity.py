@@ -588,3 +588,43 @@ def test_overlapped_pipeline_equals_sequential(gpu):
         w = want[k % len(want)]
         assert g.points.n == w.points.n and g.n_clusters == w.n_clusters
         assert torch.equal(g.labels, w.labels) and torch.equal(g.points.x[:g.points.n], w.points.x[:w.points.n])
+
+
+@pytest.mark.parametrize("S,E,thr,stride", [(2048, 1024, 10.0, 4), (64, 1024, 9.5, 3), (33, 130, 8.0, 1), (17, 1000, 2.0, 2),
+                                            (5, 1023, -1.0, 5), (40, 512, 254.0, 1), (40, 512, 255.0, 1), (40, 512, 0.0, 7)])
+def test_spoke_to_points_uint8_equals_float32(gpu, S, E, thr, stride):
+    """uint8 echoes (integer compare on four cells at a time, 16-byte bulk copies when S*E % 16 == 0, scalar
+    fallback otherwise) give exactly the float32 result: fractional, negative and saturating thresholds."""
+    from radar_point_cloud_tracking_b200 import _lib
+    spec = syn.SweepSpec(seed=13, frames=2, spokes=S, bins=E, clutter_p=0.02, land_blobs=1, buoys=1, boats=1)
+    echo = syn.synth_echo(spec).reshape(-1, S, E)
+    echo[0, 0, :min(E, 8)] = [0, 255, 254, 1, 10, 9, 11, 255][:min(E, 8)]
+    assert np.array_equal(echo, echo.astype(np.uint8).astype(np.float32))       # the generator emits 0..255 integers
+    d = torch.device("cuda:0")
+    c, s, r = _tables(gpu, spec, 6, d)
+    gains = torch.tensor([40, 50, 75] * 2, dtype=torch.int32, device=d)
+    outs = []
+    for t in (torch.from_numpy(echo).to(d), torch.from_numpy(echo.astype(np.uint8)).to(d)):
+        outs.append(gpu.spoke_to_points(t, c, s, r, gains, thr, stride, gains_per_frame=3))
+        want_variant = 2 if (S * E) % (16 if t.dtype == torch.uint8 else 4) == 0 else 1
+        assert _lib.context(0).info("spoke_last_variant") == want_variant
+    a, b = outs
+    assert a.n == b.n and torch.equal(a.frame_off, b.frame_off)
+    for f in ("x", "y", "inten", "gain"):
+        assert torch.equal(getattr(a, f)[:a.n], getattr(b, f)[:b.n])
+    assert (a.n > 0) == (thr < 255.0)
+
+
+def test_pipeline_uint8_block_equals_float32(gpu):
+    from radar_point_cloud_tracking_b200.pipeline import DetectionConfig, DetectionPipeline
+    spec = syn.SweepSpec(seed=23, frames=12, spokes=512, bins=1024, clutter_p=0.005)
+    pipe = DetectionPipeline(DetectionConfig(), 0)
+    echo = gpu.synth_echo(spec)
+    c, s, r = pipe.spoke_tables(spec.angle_units(), spec.scale(), spec.frames, spec.bins)
+    tabs = [torch.from_numpy(t).to(echo.device) for t in (c, s, r)]
+    a = pipe.run_device(echo, *tabs)
+    b = pipe.run_device(echo.to(torch.uint8), *tabs)
+    assert a.points.n == b.points.n > 0 and a.n_clusters == b.n_clusters > 0
+    assert torch.equal(a.labels, b.labels) and torch.equal(a.points.inten[:a.points.n], b.points.inten[:b.points.n])
+    h = pipe.run_host(echo.to(torch.uint8).cpu().numpy(), spec.angle_units(), spec.scale())
+    assert np.array_equal(h["labels"], a.labels.cpu().numpy()) and h["h2d_bytes"] < echo.numel() * 1.1
