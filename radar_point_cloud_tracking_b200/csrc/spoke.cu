@@ -260,18 +260,30 @@ spoke_mask_tma_kernel(const T* __restrict__ echo, const SpokeGeom g, const ThrAr
             const int nt = (int)min((long long)MT_TILES, g.total_tiles - t0);
             m.first_tile = t0;
             m.n_tiles = nt;
+            // (sweep, tile in sweep) of the stage's first tile by ONE division, then stepped: this thread feeds the
+            // whole SM and must not spend its time in 64-bit divisions
+            int sw = (int)(t0 / g.tiles_per_sweep);
+            int ts = (int)(t0 - (long long)sw * g.tiles_per_sweep);
+            const T* srcs[MT_TILES];
             uint32_t bytes = 0;
+#pragma unroll
             for (int t = 0; t < MT_TILES; ++t) {
-                const int v = t < nt ? tile_ref<T>(echo, g, t0 + t).valid : 0;
+                int v = 0;
+                srcs[t] = nullptr;
+                if (t < nt) {
+                    const int cell0 = ts * SK_TILE;
+                    v = min(SK_TILE, g.sweep_cells - cell0);
+                    srcs[t] = echo + (int64_t)sw * g.sweep_cells + cell0;
+                    if (++ts == g.tiles_per_sweep) { ts = 0; ++sw; }
+                }
                 m.valid[t] = v;
                 bytes += (uint32_t)v * (uint32_t)sizeof(T);
             }
             mbar_expect_tx(&sm.full[s], bytes);
-            for (int t = 0; t < nt; ++t) {
-                const TileRef<T> tr = tile_ref<T>(echo, g, t0 + t);
-                if (tr.valid > 0)
-                    bulk_g2s(&sm.ring[s][(size_t)t * SK_TILE * sizeof(T)], tr.src, (uint32_t)tr.valid * (uint32_t)sizeof(T), &sm.full[s]);
-            }
+#pragma unroll
+            for (int t = 0; t < MT_TILES; ++t)
+                if (m.valid[t] > 0)
+                    bulk_g2s(&sm.ring[s][(size_t)t * SK_TILE * sizeof(T)], srcs[t], (uint32_t)m.valid[t] * (uint32_t)sizeof(T), &sm.full[s]);
             st = (long long)gridDim.x + atomicAdd(ticket, 1u);
             ++it;
         }
@@ -294,7 +306,7 @@ spoke_mask_tma_kernel(const T* __restrict__ echo, const SpokeGeom g, const ThrAr
         const long long t0 = m.first_tile;
         if (t0 < 0) break;
         const int nt = m.n_tiles;
-#pragma unroll 2
+#pragma unroll
         for (int b = warp; b < MT_STAGE_BATCHES; b += MT_WARPS) {
             const int t = b / SK_BATCHES;                                  // tile of the batch inside the stage
             if (t >= nt) break;

@@ -397,7 +397,11 @@ class ShardedDetection:
         pinned torch tensor), runs the sharded device path and reads this rank's result back."""
         if self.base is None:
             raise RadarB200Error("run_host needs the CUDA engine")
-        t_echo = pinned if pinned is not None else torch.from_numpy(np.ascontiguousarray(echo, dtype=np.float32))
+        if pinned is not None:
+            t_echo = pinned
+        else:
+            a = np.asarray(echo)
+            t_echo = torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint8 if a.dtype == np.uint8 else np.float32))
         F, G, S, E = t_echo.shape
         c, s, r = self.base.spoke_tables(angle_units, scale, F, E)
         d = self.device
@@ -405,6 +409,6 @@ class ShardedDetection:
         res = self.run_device(d_echo, torch.from_numpy(c).to(d), torch.from_numpy(s).to(d), torch.from_numpy(r).to(d), frame_ids)
         out = res.to_host()
         out["n_clusters"] = res.n_clusters
-        out["h2d_bytes"] = t_echo.numel() * 4 + 3 * c.nbytes
+        out["h2d_bytes"] = t_echo.numel() * t_echo.element_size() + 3 * c.nbytes
         out["d2h_bytes"] = out["points"].nbytes + out["gains"].nbytes + out["labels"].nbytes + out["frame_off"].nbytes
         return out

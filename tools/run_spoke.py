@@ -2,6 +2,7 @@
 
     python tools/run_spoke.py [frames] [reps] [thr] [stride]
 """
+import os
 import sys
 from pathlib import Path
 
@@ -20,6 +21,8 @@ spec = syn.SweepSpec(seed=2025, frames=frames)
 d = torch.device("cuda:0")
 W = frames * 3
 echo = dev.synth_echo(spec, device=d).view(W, spec.spokes, spec.bins)
+if os.environ.get('RB_U8'):
+    echo = echo.to(torch.uint8)
 c, s, r = sweep_tables(spec.angle_units(), spec.scale(), spec.bins)
 rep = lambda t: torch.from_numpy(np.ascontiguousarray(np.broadcast_to(t, (W, len(t)))).copy()).to(d)
 c, s, r = rep(c), rep(s), rep(r)
@@ -37,7 +40,7 @@ for i in range(reps):
     rows.append([ctx.info(k) * 1e-3 for k in ("spoke_mask_ns", "spoke_offsets_ns", "spoke_emit_ns")])
 torch.cuda.synchronize()
 n = int(base[-1].item())
-gb = echo.numel() * 4 / 1e9
+gb = echo.numel() * echo.element_size() / 1e9
 for i, (a, b, e) in enumerate(rows):
     print(f"rep {i}: mask {a:8.1f} us ({gb / a * 1e6:7.1f} GB/s)  offsets {b:6.1f} us  emit {e:8.1f} us  "
           f"stage {(gb + 16e-9 * n) / (a + b + e) * 1e6:7.1f} GB/s")
