@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <vector>
+
 #include "radarb200.h"
 
 #define RB_WARP 32
@@ -52,6 +54,7 @@ struct rb_ctx {
     int64_t l2_bytes = 0;
     int64_t launches = 0;
     rb_scratch slots[RB_S_COUNT];
+    std::vector<void*> retired;      // outgrown scratch buffers, freed in rb_destroy (never while work may be in flight)
     void* pinned = nullptr;          // small pinned staging buffer (host)
     size_t pinned_cap = 0;
     rb_dbscan_stats last_stats;

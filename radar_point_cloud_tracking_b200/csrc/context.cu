@@ -40,7 +40,7 @@ extern "C" int rb_create(int device, rb_ctx** out) {
     ctx->cc_minor = prop.minor;
     ctx->l2_bytes = prop.l2CacheSize;
     memset(&ctx->last_stats, 0, sizeof ctx->last_stats);
-    ctx->pinned_cap = 1 << 16;
+    ctx->pinned_cap = 1 << 20;                     // 1 MiB: frame offsets of 130k frames fit without a re-allocation
     e = cudaMallocHost(&ctx->pinned, ctx->pinned_cap);
     if (e != cudaSuccess) {
         rb_set_error("rb_create: cudaMallocHost -> %s", cudaGetErrorString(e));
@@ -56,6 +56,7 @@ extern "C" void rb_destroy(rb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     for (int i = 0; i < RB_S_COUNT; ++i)
         if (ctx->slots[i].ptr) cudaFree(ctx->slots[i].ptr);
+    for (void* p : ctx->retired) cudaFree(p);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (int i = 0; i < 4; ++i)
         if (ctx->spoke_ev[i]) cudaEventDestroy(ctx->spoke_ev[i]);
@@ -115,13 +116,15 @@ int rb_scratch_get(rb_ctx* ctx, rb_slot slot, size_t bytes, void** out) {
     if (bytes == 0) bytes = 16;
     if (s.cap < bytes) {
         if (s.ptr) {
-            // buffers may still be in use by work queued on the caller's stream
-            RB_CUDA(cudaDeviceSynchronize());
-            RB_CUDA(cudaFree(s.ptr));
+            // The old buffer may still be in use by work queued on the caller's stream, and neither a device-wide
+            // sync nor cudaFree (which syncs implicitly) is safe here: with several contexts per device (blocks in
+            // flight, one NCCL communicator per worker) another thread's collective may be waiting for a peer that
+            // is itself blocked in such a sync. Retire the buffer; it is freed with the context.
+            ctx->retired.push_back(s.ptr);
             s.ptr = nullptr;
             s.cap = 0;
         }
-        size_t want = bytes + bytes / 4;           // headroom: avoid a realloc for every small growth
+        size_t want = bytes + bytes / 2;           // headroom: retired buffers stay allocated until rb_destroy
         want = (want + 255) & ~size_t(255);
         cudaError_t e = cudaMalloc(&s.ptr, want);
         if (e != cudaSuccess) {
