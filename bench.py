@@ -47,8 +47,8 @@ def parse_args():
     ap.add_argument("--clutter-p", type=float, default=0.003)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--streams", type=int, default=0, help="blocks in flight per GPU (host threads x CUDA streams, and one NCCL "
-                    "communicator each when N>1) for `value`; 0 = 3 on one GPU, 2 per rank when time-sharded")
+    ap.add_argument("--streams", type=int, default=3, help="N=1: blocks in flight (host threads x CUDA streams x library contexts) "
+                    "for `value`; the time-sharded path (N>1) always has one block in flight per rank")
     ap.add_argument("--cpu-frames", type=int, default=64, help="frames per CPU worker in the reference/cpu_baseline sample")
     ap.add_argument("--shard-profile", action="store_true", help="N>1: print per-stage wall-clock of the sharded driver to stderr")
     return ap.parse_args()
@@ -233,10 +233,6 @@ def run_ours(args):
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
-    if world > 1:
-        # several NCCL communicators + worker streams per process: give every stream its own hardware queue, so a
-        # collective that waits for its peer can never hold up another stream's work through a shared queue
-        os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
@@ -297,16 +293,12 @@ def run_ours(args):
     results = []
     overlapped = None
     with ClockSampler(device.index) as clocks:
-        if args.streams > 1:
+        if world == 1 and args.streams > 1:
             # throughput path: `streams` host threads, each with its own CUDA stream and library context, run whole
             # blocks concurrently; timed from an event recorded before the first block is submitted to an event the
             # current stream records after waiting for every block
             from radar_point_cloud_tracking_b200.pipeline import OverlappedPipeline
-            if world > 1:
-                from radar_point_cloud_tracking_b200.sharded import OverlappedSharded
-                overlapped = OverlappedSharded(cfg, rank, world, device.index, workers=args.streams)
-            else:
-                overlapped = OverlappedPipeline(cfg, device.index, workers=args.streams)
+            overlapped = OverlappedPipeline(cfg, device.index, workers=args.streams)
             block = ((echo, d_c, d_s, d_r, frame_ids), {})
             overlapped.map([block] * max(args.warmup, 2 * args.streams))
             barrier()
@@ -393,7 +385,7 @@ def run_ours(args):
         "dtype": "f32 (points) / f64 (neighbour test) / i32 (labels)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "spokes": args.spokes, "bins": args.bins,
                    "gains": [40, 50, 75], "seed": args.seed, "clutter_p": args.clutter_p,
-                   "parallelism": f"time-sharded x{world}, {args.streams if overlapped else 1} block(s) in flight per rank" if world > 1 else f"single GPU, {args.streams if overlapped else 1} block(s) in flight",
+                   "parallelism": f"time-sharded x{world}, 1 block in flight per rank" if world > 1 else f"single GPU, {args.streams if overlapped else 1} block(s) in flight",
                    "l2_policy": "inputs larger than L2 (echo block %.2f GB per step)" % (echo.numel() * 4 / 1e9)},
         "points_per_s": n_raw_all * args.steps / (ms * 1e-3),
         "points_per_step": {"after_stride": n_raw_all, "after_land_filter": n_pts_all, "clusters": int(pts_t[2])},
@@ -452,8 +444,6 @@ def run_reference(args):
 
 def main():
     args = parse_args()
-    if args.streams <= 0:
-        args.streams = 3 if int(os.environ.get("WORLD_SIZE", "1")) == 1 else 2
     # exactly ONE line on stdout: libraries under us (NCCL's version banner, for one) write to fd 1, so fd 1
     # points at stderr while the benchmark runs and is restored for the JSON line
     sys.stdout.flush()

@@ -413,52 +413,3 @@ class ShardedDetection:
         out["d2h_bytes"] = out["points"].nbytes + out["gains"].nbytes + out["labels"].nbytes + out["frame_off"].nbytes
         return out
 
-
-class OverlappedSharded:
-    """Several sharded blocks in flight per rank: ``workers`` host threads, each with its own CUDA stream, library
-    context and process group (its own NCCL communicator), take the blocks round-robin - worker w of EVERY rank
-    handles blocks w, w + workers, ... in the same order, so the collectives of one communicator are issued
-    consistently on all ranks while the exchanges and host gaps of one block are hidden behind the kernels of
-    the others. Per-block results are exactly those of :class:`ShardedDetection`."""
-
-    def __init__(self, config=None, rank: Optional[int] = None, world: Optional[int] = None, device: Optional[int] = None,
-                 workers: int = 2):
-        from concurrent.futures import ThreadPoolExecutor
-
-        self.workers = max(1, int(workers))
-        self.cfg, self.rank, self.world, self.device_index = config, rank, world, device
-        # process groups must be created by all ranks, in the same order, before any of them is used
-        self.groups = [dist.new_group() if dist.is_initialized() and dist.get_world_size() > 1 else None for _ in range(self.workers)]
-        self._pools = [ThreadPoolExecutor(max_workers=1, thread_name_prefix=f"radarb200-shard{w}") for w in range(self.workers)]
-        self._state = [None] * self.workers
-
-    def _run(self, w: int, start_event, args, kwargs):
-        if self._state[w] is None:
-            sd = ShardedDetection(self.cfg, self.rank, self.world, self.device_index, group=self.groups[w])
-            torch.cuda.set_device(sd.device)
-            self._state[w] = (sd, torch.cuda.Stream(sd.device))
-        sd, stream = self._state[w]
-        with torch.cuda.stream(stream):
-            if start_event is not None:
-                stream.wait_event(start_event)
-            res = sd.run_device(*args, **kwargs)
-            done = torch.cuda.Event()
-            done.record(stream)
-        return res, done
-
-    def map(self, blocks, start_event=None) -> List[ShardResult]:
-        futs = [self._pools[i % self.workers].submit(self._run, i % self.workers, start_event, a, k) for i, (a, k) in enumerate(blocks)]
-        out = []
-        cur = torch.cuda.current_stream()
-        for f in futs:
-            res, done = f.result()
-            cur.wait_event(done)
-            out.append(res)
-        return out
-
-    def launch_count(self) -> int:
-        return sum(st[0].base.ctx.launch_count() for st in self._state if st is not None)
-
-    def close(self):
-        for p in self._pools:
-            p.shutdown(wait=True)

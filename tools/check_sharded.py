@@ -45,19 +45,6 @@ if rank == 0:
         all(g["ncl"] == ref.n_clusters for g in gathered)
     print(f"sharded x{world}: {len(got_l)} points, {ref.n_clusters} clusters, halo points per rank "
           f"{[g['halo'] for g in gathered]} -> {'IDENTICAL to single GPU' if ok else 'MISMATCH'}")
-# several blocks in flight per rank (own NCCL communicator per worker thread): same labels
-from radar_point_cloud_tracking_b200.sharded import OverlappedSharded
-ov = OverlappedSharded(cfg, rank, world, local, workers=2)
-tabs = tuple(torch.from_numpy(t).to(device) for t in sd.base.spoke_tables(spec.angle_units(), spec.scale(), B, spec.bins))
-many = ov.map([((echo, *tabs, np.arange(first, first + B)), {})] * 6)
-torch.cuda.synchronize()
-same = all(torch.equal(m.labels, res.labels) and m.n_clusters == res.n_clusters for m in many)
-ov.close()
-if rank == 0:
-    print(f"6 blocks, 2 in flight per rank: {'IDENTICAL' if same else 'MISMATCH'}")
-t_same = torch.tensor([1 if same else 0], device=device)
-dist.all_reduce(t_same, op=dist.ReduceOp.MIN)
-ok = ok and bool(int(t_same.item()))
 flag = torch.tensor([1 if ok else 0], device=device)
 dist.broadcast(flag, src=0)
 dist.destroy_process_group()
