@@ -25,10 +25,6 @@ def _dev(t: torch.Tensor, dtype: torch.dtype, name: str) -> torch.Tensor:
     return t.contiguous()
 
 
-#: bench hook: when a list, (start, end) CUDA events around every spoke-to-point launch are appended
-SPOKE_EVENTS = None
-
-
 @dataclass
 class PointBatch:
     """Points of a batch of frames, SoA on the device, frames concatenated in order.
@@ -86,18 +82,11 @@ def spoke_to_points_raw(echo: torch.Tensor, cos_tab: torch.Tensor, sin_tab: torc
     else:
         x, y, inten, gain, sweep_base = out
         cap = min(x.numel(), y.numel(), inten.numel(), gain.numel())
-    events = SPOKE_EVENTS
-    if events is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
     entry = ctx.lib.rb_spoke_to_points_u8 if echo.dtype == torch.uint8 else ctx.lib.rb_spoke_to_points
     check(entry(ctx.handle, ptr(echo), ptr(cos_tab), ptr(sin_tab), ptr(range_res),
                 ptr(ranges), ptr(sweep_gain), W, S, E, float(threshold), int(stride),
                 ptr(x), ptr(y), ptr(inten), ptr(gain), cap, ptr(sweep_base), stream_ptr()),
           "rb_spoke_to_points")
-    if events is not None:
-        e1.record()
-        events.append((e0, e1))
     return x, y, inten, gain, sweep_base
 
 
