@@ -270,16 +270,21 @@ class OverlappedPipeline:
             done.record(stream)
         return res, done, pipe.ctx.launch_count()
 
-    def map(self, blocks, start_event=None) -> List[DetectionResult]:
+    def map(self, blocks, start_event=None, keep: bool = True) -> List[DetectionResult]:
         """``blocks``: iterable of ``(args, kwargs)`` for :meth:`DetectionPipeline.run_device`. Returns the results
-        in order; the current stream waits for all of them."""
+        in order (``keep=False``: only the last one - earlier results are released as soon as they are complete,
+        so their buffers are recycled by the following blocks instead of growing the pool); the current stream
+        waits for all of them."""
         futs = [self._pool.submit(self._run, start_event, a, k) for a, k in blocks]
         out = []
         cur = torch.cuda.current_stream(self.device)
-        for f in futs:
-            res, done, _ = f.result()
+        for i in range(len(futs)):
+            res, done, _ = futs[i].result()
+            futs[i] = None
             cur.wait_event(done)
-            out.append(res)
+            if keep or i == len(futs) - 1:
+                out.append(res)
+            del res
         return out
 
     def launch_count(self) -> int:
