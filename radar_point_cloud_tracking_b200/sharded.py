@@ -92,6 +92,35 @@ class CudaEngine:
     def spoke_to_points(self, echo, cos_tab, sin_tab, range_res, sweep_gain, thr, stride, gpf, cap=None) -> PointBatch:
         return self.dev.spoke_to_points(echo, cos_tab, sin_tab, range_res, sweep_gain, thr, stride, gains_per_frame=gpf, cap=cap)
 
+    # -- the spoke stage of the NEXT block, launched on a side stream while the current block is in its exchange and
+    #    clustering phases (it needs no exchange and no host knowledge): software pipelining inside one rank
+    def spoke_launch(self, echo, cos_tab, sin_tab, range_res, sweep_gain, thr, stride, gpf, cap):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(self.device)
+        main = torch.cuda.current_stream(self.device)
+        # outputs are allocated on the MAIN stream (they are consumed and freed there; the caching allocator can then
+        # recycle them block after block), only the launches go to the side stream
+        W = echo.shape[0]
+        out = (torch.empty(cap, dtype=torch.float32, device=self.device), torch.empty(cap, dtype=torch.float32, device=self.device),
+               torch.empty(cap, dtype=torch.float32, device=self.device), torch.empty(cap, dtype=torch.int32, device=self.device),
+               torch.empty(W + 1, dtype=torch.int64, device=self.device))
+        self._side.wait_stream(main)                      # inputs (and the fresh buffers) are ready on the main stream
+        with torch.cuda.stream(self._side):
+            self.dev.spoke_to_points_raw(echo, cos_tab, sin_tab, range_res, sweep_gain, thr, stride, cap, out=out)
+            done = torch.cuda.Event()
+            done.record(self._side)
+        return dict(outs=out, done=done, cap=cap, args=(echo, cos_tab, sin_tab, range_res, sweep_gain, thr, stride, gpf))
+
+    def spoke_finish(self, h) -> PointBatch:
+        torch.cuda.current_stream(self.device).wait_event(h["done"])
+        x, y, inten, gain, sweep_base = h["outs"]
+        n = int(sweep_base[-1].item())
+        if n > h["cap"]:                                   # capacity guess too small: redo synchronously
+            echo, cos_tab, sin_tab, range_res, sweep_gain, thr, stride, gpf = h["args"]
+            return self.spoke_to_points(echo, cos_tab, sin_tab, range_res, sweep_gain, thr, stride, gpf, cap=n)
+        gpf = h["args"][7]
+        return PointBatch(x, y, inten, gain, self.dev.frame_offsets(sweep_base, (sweep_base.numel() - 1) // gpf, gpf), n)
+
     def bounds(self, x, y) -> torch.Tensor:
         return self.dev.bounds(x, y)
 
@@ -168,6 +197,7 @@ class ShardedDetection:
             self.base = DetectionPipeline(self.cfg, self.device.index)       # spoke tables + ctx for the bench
         self._cap_hint = 0
         self._gain_cache = None
+        self._prefetched = None
         self.profile = False               # True: synchronise and record wall-clock per stage in self.timings
         self.timings = {}
         self._t_last = None
@@ -219,6 +249,46 @@ class ShardedDetection:
         return left, right
 
     # ---- the path -------------------------------------------------------------------------------------
+    def _gains(self, n_sweeps: int) -> torch.Tensor:
+        if self._gain_cache is None or self._gain_cache.numel() != n_sweeps:
+            self._gain_cache = self._t(list(self.cfg.gains) * (n_sweeps // len(self.cfg.gains)), torch.int32)
+        return self._gain_cache
+
+    def prefetch(self, echo, cos_tab, sin_tab, range_res) -> None:
+        """Launch the spoke-to-point stage of the block that :meth:`run_device` will be called with NEXT, on a side
+        stream, without waiting for it: it overlaps the exchange and clustering phases of the current block.
+        Optional; engines without ``spoke_launch`` ignore it."""
+        if not hasattr(self.engine, "spoke_launch"):
+            return
+        F, G, S, E = echo.shape
+        cap = self._cap_hint or max(1, F * G * ((S * E + self.cfg.point_stride - 1) // max(self.cfg.point_stride, 1)) // 8)
+        h = self.engine.spoke_launch(echo.reshape(F * G, S, E), cos_tab, sin_tab, range_res, self._gains(F * G),
+                                     self.cfg.intensity_threshold, self.cfg.point_stride, G, cap)
+        self._prefetched = (echo.data_ptr(), tuple(echo.shape), h)
+
+    def run_blocks(self, blocks, keep: bool = True):
+        """Run a sequence of blocks ``(echo, cos_tab, sin_tab, range_res, frame_ids)`` of this rank, software
+        pipelined: while block k goes through its exchange and clustering phases, the spoke stage of block k+1
+        is already running on the side stream. Same results as calling :meth:`run_device` per block.
+        Returns the results (``keep=False``: only the last one, earlier ones are released for buffer reuse)."""
+        blocks = list(blocks)
+        out, nxt = [], None
+        for i, blk in enumerate(blocks):
+            if nxt is None:
+                self.prefetch(*blk[:4])
+                nxt = self._prefetched
+            cur, self._prefetched = nxt, None
+            nxt = None
+            if i + 1 < len(blocks):
+                self.prefetch(*blocks[i + 1][:4])              # goes out BEFORE block i's phases are enqueued
+                nxt = self._prefetched
+            self._prefetched = cur
+            res = self.run_device(*blk)
+            if keep or i == len(blocks) - 1:
+                out.append(res)
+            del res
+        return out
+
     def run_device(self, echo, cos_tab, sin_tab, range_res, frame_ids: Sequence[int], cluster: bool = True) -> ShardResult:
         """``echo[F,G,S,E]`` = this rank's frames (device tensor of the engine); ``frame_ids`` their ids,
         increasing across ranks (rank r's ids are all smaller than rank r+1's)."""
@@ -226,10 +296,12 @@ class ShardedDetection:
         F, G, S, E = echo.shape
         ids = np.asarray(frame_ids, dtype=np.int64)
         self._tick(None)
-        if self._gain_cache is None or self._gain_cache.numel() != F * G:
-            self._gain_cache = self._t(list(cfg.gains) * F, torch.int32)
-        raw = eng.spoke_to_points(echo.reshape(F * G, S, E), cos_tab, sin_tab, range_res, self._gain_cache,
-                                  cfg.intensity_threshold, cfg.point_stride, G, cap=self._cap_hint or None)
+        pf, self._prefetched = self._prefetched, None
+        if pf is not None and pf[0] == echo.data_ptr() and pf[1] == tuple(echo.shape):
+            raw = eng.spoke_finish(pf[2])
+        else:
+            raw = eng.spoke_to_points(echo.reshape(F * G, S, E), cos_tab, sin_tab, range_res, self._gains(F * G),
+                                      cfg.intensity_threshold, cfg.point_stride, G, cap=self._cap_hint or None)
         self._cap_hint = max(self._cap_hint, int(raw.n * 1.25) + 1024)
         self._tick("spoke")
 

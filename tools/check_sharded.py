@@ -45,6 +45,16 @@ if rank == 0:
         all(g["ncl"] == ref.n_clusters for g in gathered)
     print(f"sharded x{world}: {len(got_l)} points, {ref.n_clusters} clusters, halo points per rank "
           f"{[g['halo'] for g in gathered]} -> {'IDENTICAL to single GPU' if ok else 'MISMATCH'}")
+# software-pipelined blocks (next block's spoke stage prefetched on a side stream): same labels per block
+tabs = tuple(torch.from_numpy(t).to(device) for t in sd.base.spoke_tables(spec.angle_units(), spec.scale(), B, spec.bins))
+many = sd.run_blocks([(echo, *tabs, np.arange(first, first + B))] * 4)
+torch.cuda.synchronize()
+same = all(torch.equal(m.labels, res.labels) and m.n_clusters == res.n_clusters and m.points.n == res.points.n for m in many)
+t_same = torch.tensor([1 if same else 0], device=device)
+dist.all_reduce(t_same, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(f"4 pipelined blocks per rank: {'IDENTICAL' if int(t_same.item()) else 'MISMATCH'}")
+ok = ok and bool(int(t_same.item()))
 flag = torch.tensor([1 if ok else 0], device=device)
 dist.broadcast(flag, src=0)
 dist.destroy_process_group()
