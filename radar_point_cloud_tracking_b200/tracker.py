@@ -135,7 +135,11 @@ def _points_from_sweeps(sweeps: Sequence[Tuple[np.ndarray, np.ndarray, np.ndarra
             for i in idxs:
                 out[i] = (np.array([], np.float32), np.array([], np.float32), np.array([], np.float32))
             continue
-        echo = torch.from_numpy(np.stack([sweeps[i][2] for i in idxs])).to(d)
+        stacked = np.stack([sweeps[i][2] for i in idxs])
+        # real echoes are 8-bit (PIPELINE_DOCUMENTATION.txt:47): when the parsed values are exactly 0..255 integers
+        # they travel as uint8 - a quarter of the PCIe bytes, identical points (rb_spoke_to_points_u8)
+        as_u8 = stacked.astype(np.uint8)
+        echo = torch.from_numpy(as_u8 if np.array_equal(as_u8, stacked) else stacked).to(d)
         cs, sn, rs = sweep_tables(np.stack([sweeps[i][0] for i in idxs]), np.stack([sweeps[i][1] for i in idxs]), E)
         gains = torch.tensor([sweeps[i][3] for i in idxs], dtype=torch.int32, device=d)
         batch = dev.spoke_to_points(echo, torch.from_numpy(cs).to(d), torch.from_numpy(sn).to(d),
