@@ -102,9 +102,13 @@ inline ThrArg make_thr(float thr) {
     return a;
 }
 template <typename T> struct Elem;
-template <> struct Elem<float>   { static constexpr int STAGE_TILES = 4;  static constexpr int ALIGN_CELLS = 4; };   // 64 KiB stages,
-template <> struct Elem<uint8_t> { static constexpr int STAGE_TILES = 16; static constexpr int ALIGN_CELLS = 16; }; // 16-byte bulk copies
+template <> struct Elem<float>   { static constexpr int STAGE_TILES = 4;  static constexpr int ALIGN_CELLS = 4;  static constexpr int WARPS = 8; };    // 64 KiB stages,
+template <> struct Elem<uint8_t> { static constexpr int STAGE_TILES = 16; static constexpr int ALIGN_CELLS = 16; static constexpr int WARPS = 16; };   // 16-byte bulk copies; 4x the cells per stage: twice the consumer warps
 
+__device__ __forceinline__ unsigned u8_bits4(unsigned word, const ThrArg& t) {              // survivor flags of 4 cells in bits 0..3
+    const unsigned r = t.none ? 0u : __vcmpgeu4(word, t.lb4);
+    return ((r & 0x01010101u) * 0x01020408u) >> 24;
+}
 __device__ __forceinline__ unsigned nibble_u8(unsigned word, const ThrArg& t, unsigned sh) {
     const unsigned r = t.none ? 0u : __vcmpgeu4(word, t.lb4);          // 0xff in every byte that survives
     return (((r & 0x01010101u) * 0x01020408u) >> 24) << sh;           // gather the four flags into bits 0..3
@@ -152,16 +156,15 @@ __device__ __forceinline__ TileRef<T> tile_ref(const T* echo, const SpokeGeom& g
 // ---- 1a. TMA-staged variant (the default) --------------------------------------------------------------
 // One persistent CTA per SM: a producer thread streams stages of MT_TILES tiles (64 KiB) into a ring of
 // MT_STAGES shared-memory buffers with 1-D bulk async copies (cp.async.bulk ... mbarrier::complete_tx, one
-// per tile), so the bytes in flight per SM (up to 192 KiB) are held by the TMA engine and shared memory,
+// per stage when its tiles are full), so the bytes in flight per SM (up to 192 KiB) are held by the TMA engine and shared memory,
 // not by registers. MT_WARPS consumer warps turn each stage into mask words, one 1024-cell batch (= one
 // 128-byte line of mask) per warp at a time, and add their survivor counts to per-tile shared counters
 // that the producer flushes to global memory when it recycles the slot. Stages are handed out by one
 // atomic ticket per CTA and stage (a ticket per WARP and tile serialises on the atomic unit: measured
 // 4.8 instead of 7.0 TB/s, tools/mask_bench.cu).
-constexpr int MT_WARPS = 8;                                                // consumer warps
 constexpr int MT_STAGES = 3;
 constexpr int MT_STAGE_BYTES = 64 * 1024;                                  // 4 float32 tiles or 16 uint8 tiles
-constexpr int MT_THREADS = MT_WARPS * 32 + 32;
+template <typename T> constexpr int mt_threads() { return Elem<T>::WARPS * 32 + 32; }    // consumer warps + the producer warp
 
 template <int TILES>
 struct MtMeta {
@@ -207,10 +210,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 template <typename T>
-__global__ void __launch_bounds__(MT_THREADS, 1)
+__global__ void __launch_bounds__(mt_threads<T>(), 1)
 spoke_mask_tma_kernel(const T* __restrict__ echo, const SpokeGeom g, const ThrArg threshold,
                       uint32_t* __restrict__ mask, uint32_t* __restrict__ tile_count, unsigned* __restrict__ ticket) {
     constexpr int MT_TILES = Elem<T>::STAGE_TILES;
+    constexpr int MT_WARPS = Elem<T>::WARPS;
     constexpr int MT_STAGE_BATCHES = MT_TILES * SK_BATCHES;
     static_assert(MT_TILES * SK_TILE * sizeof(T) == MT_STAGE_BYTES, "a stage is 64 KiB");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -232,18 +236,22 @@ spoke_mask_tma_kernel(const T* __restrict__ echo, const SpokeGeom g, const ThrAr
     const long long n_stages = (g.total_tiles + MT_TILES - 1) / MT_TILES;
 
     if (warp == MT_WARPS) {
-        // ================= producer (one thread) =================
-        if (lane != 0) return;
+        // ================= producer warp: lane t looks after tile t of the stage =================
+        static_assert(MT_TILES <= 32, "one lane per tile");
         auto flush = [&](int s) {                                          // counts of the stage that just left slot s
             MtMeta<MT_TILES>& m = sm.meta[s];
-            for (int t = 0; t < m.n_tiles; ++t) {
-                tile_count[m.first_tile + t] = m.cnt[t];
-                m.cnt[t] = 0;
+            if ((int)lane < m.n_tiles) {
+                tile_count[m.first_tile + lane] = m.cnt[lane];
+                m.cnt[lane] = 0;
             }
+            __syncwarp();
         };
         long long st = blockIdx.x;
         int it = 0;
         while (true) {
+            // the ticket of the NEXT stage goes out first: its round trip hides behind this stage's work
+            unsigned tk = 0;
+            if (lane == 0) tk = atomicAdd(ticket, 1u);
             const int s = it % MT_STAGES;
             if (it >= MT_STAGES) {
                 mbar_wait(&sm.empty[s], (uint32_t)(it / MT_STAGES - 1) & 1u);
@@ -251,40 +259,35 @@ spoke_mask_tma_kernel(const T* __restrict__ echo, const SpokeGeom g, const ThrAr
             }
             MtMeta<MT_TILES>& m = sm.meta[s];
             if (st >= n_stages) {                                          // end marker for the consumers
-                m.first_tile = -1;
-                m.n_tiles = 0;
-                mbar_arrive(&sm.full[s]);
+                if (lane == 0) {
+                    m.first_tile = -1;
+                    m.n_tiles = 0;
+                    mbar_arrive(&sm.full[s]);
+                }
                 break;
             }
             const long long t0 = st * MT_TILES;
             const int nt = (int)min((long long)MT_TILES, g.total_tiles - t0);
-            m.first_tile = t0;
-            m.n_tiles = nt;
-            // (sweep, tile in sweep) of the stage's first tile by ONE division, then stepped: this thread feeds the
-            // whole SM and must not spend its time in 64-bit divisions
-            int sw = (int)(t0 / g.tiles_per_sweep);
-            int ts = (int)(t0 - (long long)sw * g.tiles_per_sweep);
-            const T* srcs[MT_TILES];
-            uint32_t bytes = 0;
-#pragma unroll
-            for (int t = 0; t < MT_TILES; ++t) {
-                int v = 0;
-                srcs[t] = nullptr;
-                if (t < nt) {
-                    const int cell0 = ts * SK_TILE;
-                    v = min(SK_TILE, g.sweep_cells - cell0);
-                    srcs[t] = echo + (int64_t)sw * g.sweep_cells + cell0;
-                    if (++ts == g.tiles_per_sweep) { ts = 0; ++sw; }
-                }
-                m.valid[t] = v;
-                bytes += (uint32_t)v * (uint32_t)sizeof(T);
+            int v = 0;
+            const T* src = nullptr;
+            if ((int)lane < nt) {
+                const TileRef<T> tr = tile_ref<T>(echo, g, t0 + lane);
+                v = tr.valid;
+                src = tr.src;
             }
-            mbar_expect_tx(&sm.full[s], bytes);
-#pragma unroll
-            for (int t = 0; t < MT_TILES; ++t)
-                if (m.valid[t] > 0)
-                    bulk_g2s(&sm.ring[s][(size_t)t * SK_TILE * sizeof(T)], srcs[t], (uint32_t)m.valid[t] * (uint32_t)sizeof(T), &sm.full[s]);
-            st = (long long)gridDim.x + atomicAdd(ticket, 1u);
+            if ((int)lane < MT_TILES) m.valid[lane] = v;
+            if (lane == 0) { m.first_tile = t0; m.n_tiles = nt; }
+            const uint32_t bytes = __reduce_add_sync(0xffffffffu, (uint32_t)v * (uint32_t)sizeof(T));
+            // full tiles are contiguous in memory (also across a sweep boundary) and in the ring
+            const bool all_full = __all_sync(0xffffffffu, (int)lane >= nt || v == SK_TILE);
+            if (lane == 0) mbar_expect_tx(&sm.full[s], bytes);             // releases the meta data to the consumers
+            __syncwarp();
+            if (all_full) {                                                // the common case: ONE 64 KiB copy per stage
+                if (lane == 0) bulk_g2s(&sm.ring[s][0], src, bytes, &sm.full[s]);
+            } else if (v > 0) {                                            // ragged stage: every lane copies its own tile
+                bulk_g2s(&sm.ring[s][(size_t)lane * SK_TILE * sizeof(T)], src, (uint32_t)v * (uint32_t)sizeof(T), &sm.full[s]);
+            }
+            st = (long long)gridDim.x + (long long)__shfl_sync(0xffffffffu, tk, 0);
             ++it;
         }
         // stages still in flight: fills it-1 .. it-(MT_STAGES-1)
@@ -312,19 +315,39 @@ spoke_mask_tma_kernel(const T* __restrict__ echo, const SpokeGeom g, const ThrAr
             if (t >= nt) break;
             const int valid = m.valid[t] - (b % SK_BATCHES) * SK_BATCH_CELLS;   // cells of this batch inside the sweep
             const unsigned char* __restrict__ batch = sm.ring[s] + (size_t)b * SK_BATCH_CELLS * sizeof(T);
-            unsigned nib[SK_BATCH];
-            if (valid >= SK_BATCH_CELLS) {
-#pragma unroll
-                for (int k = 0; k < SK_BATCH; ++k) nib[k] = batch_nibble<T>(batch, k, lane, threshold, lb);
+            uint32_t* __restrict__ mw = mask + (t0 + t) * SK_WORDS + (b % SK_BATCHES) * 32;
+            unsigned word;
+            if (sizeof(T) == 1 && valid >= SK_BATCH_CELLS) {
+                // uint8, full batch (1 KiB): two 128-bit loads per lane - 16 cells of each 512-cell half - give 16 survivor
+                // bits per half; lanes 2w and 2w+1 together hold mask word w of a half, so ONE shuffle per half finishes
+                // the words: even lanes keep the first half's, odd lanes the second half's, one 128-byte store.
+                const uint4* __restrict__ q = reinterpret_cast<const uint4*>(batch);
+                const uint4 h0 = q[lane], h1 = q[32 + lane];
+                unsigned b0 = u8_bits4(h0.x, threshold) | (u8_bits4(h0.y, threshold) << 4) | (u8_bits4(h0.z, threshold) << 8) |
+                              (u8_bits4(h0.w, threshold) << 12);
+                unsigned b1 = u8_bits4(h1.x, threshold) | (u8_bits4(h1.y, threshold) << 4) | (u8_bits4(h1.z, threshold) << 8) |
+                              (u8_bits4(h1.w, threshold) << 12);
+                const unsigned sh16 = (lane & 1u) * 16u;
+                b0 <<= sh16; b1 <<= sh16;
+                b0 |= __shfl_xor_sync(0xffffffffu, b0, 1);
+                b1 |= __shfl_xor_sync(0xffffffffu, b1, 1);
+                word = (lane & 1u) ? b1 : b0;
+                mw[(lane & 1u) * 16u + (lane >> 1)] = word;
             } else {
+                unsigned nib[SK_BATCH];
+                if (valid >= SK_BATCH_CELLS) {
 #pragma unroll
-                for (int k = 0; k < SK_BATCH; ++k) {
-                    const int c = k * 128 + (int)lane * 4;                  // valid is a multiple of 4 here
-                    nib[k] = c < valid ? batch_nibble<T>(batch, k, lane, threshold, lb) : 0u;
+                    for (int k = 0; k < SK_BATCH; ++k) nib[k] = batch_nibble<T>(batch, k, lane, threshold, lb);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < SK_BATCH; ++k) {
+                        const int c = k * 128 + (int)lane * 4;              // valid is a multiple of 4 here
+                        nib[k] = c < valid ? batch_nibble<T>(batch, k, lane, threshold, lb) : 0u;
+                    }
                 }
+                word = butterfly8(nib, lane);
+                mw[word_slot] = word;
             }
-            const unsigned word = butterfly8(nib, lane);
-            mask[(t0 + t) * SK_WORDS + (b % SK_BATCHES) * 32 + word_slot] = word;
             const unsigned c = __reduce_add_sync(0xffffffffu, __popc(word));
             if (lane == 0 && c) atomicAdd(&m.cnt[t], c);
         }
@@ -685,7 +708,7 @@ int spoke_to_points_impl(rb_ctx* ctx, const T* echo, const float* cos_tab, const
         }
         const int64_t want_blocks = rb_div_up(g.total_tiles, Elem<T>::STAGE_TILES);
         const unsigned blocks = (unsigned)(want_blocks < ctx->sm_count ? want_blocks : ctx->sm_count);
-        spoke_mask_tma_kernel<T><<<blocks, MT_THREADS, smem, stream>>>(echo, g, make_thr(threshold), mask, tile_count, ticket);
+        spoke_mask_tma_kernel<T><<<blocks, mt_threads<T>(), smem, stream>>>(echo, g, make_thr(threshold), mask, tile_count, ticket);
         ctx->spoke_last_variant = 2;
     } else {
         const int64_t want_blocks = rb_div_up(g.total_tiles, SK_WARPS);
