@@ -161,6 +161,16 @@ int rb_stdbscan(rb_ctx* ctx, const float* x, const float* y, const float* z, int
                 const float* times, int64_t n, double eps_space, float eps_time, int min_samples,
                 int32_t* labels, uint8_t* core, int64_t* n_clusters, void* stream);
 
+/* The "paper" variant of the same clustering (PointCloudWorkF/stdbscan_denoising_pipeline.py:264-369, SURVEY.md
+ * section 8 f rank 3): a point is core only if its neighbours ALSO span at least min_frames distinct int32(times)
+ * (WF:308-315), and border points follow the rule of its FIFO expansion (WF:337-366): a border point joins the
+ * smallest-id cluster among those of its core neighbours that either started (smallest core index) before the
+ * border point's own index or whose start point itself is the neighbour. Labels are identical to the reference
+ * function's. eps_time <= 30. Syncs. */
+int rb_stdbscan_wf(rb_ctx* ctx, const float* x, const float* y, const float* z, int64_t stride,
+                   const float* times, int64_t n, double eps_space, float eps_time, int min_samples, int min_frames,
+                   int32_t* labels, uint8_t* core, int64_t* n_clusters, void* stream);
+
 /* Work counters of the last rb_stdbscan on this ctx (host): pair tests per neighbour sweep, grid
  * cells, cell size. For bench/roofline reporting only. */
 typedef struct rb_dbscan_stats {

@@ -110,10 +110,47 @@ static void visit_border(int64_t p, int64_t q, void* v) {
     if (b->core[q] && (b->best < 0 || b->labels[q] < b->best)) b->best = b->labels[q];
 }
 
+/* the "paper" variant (PointCloudWorkF/stdbscan_denoising_pipeline.py:264-369): distinct int32(times) among the
+ * neighbours, and the border rule of its FIFO expansion (see numpy_oracle.st_dbscan_wf_canonical) */
+typedef struct { const float* t; int32_t* vals; int n; int64_t count; } frames_ctx;
+static void visit_frames(int64_t p, int64_t q, void* v) {
+    (void)p;
+    frames_ctx* f = (frames_ctx*)v;
+    f->count++;
+    int32_t ti = (int32_t)f->t[q];                       /* numpy astype(int32): truncation toward zero */
+    for (int i = 0; i < f->n; ++i) if (f->vals[i] == ti) return;
+    if (f->n < 4096) f->vals[f->n++] = ti;
+}
+typedef struct { const int* labels; const unsigned char* core; int64_t* parent; int64_t self; int best; } border_wf_ctx;
+static void visit_border_wf(int64_t p, int64_t q, void* v) {
+    (void)p;
+    border_wf_ctx* b = (border_wf_ctx*)v;
+    if (!b->core[q]) return;
+    int64_t start = uf_find(b->parent, q);               /* min-root union: the root is the cluster's start point */
+    if (!(start < b->self || q == start)) return;
+    if (b->best < 0 || b->labels[q] < b->best) b->best = b->labels[q];
+}
+
+static int64_t oracle_stdbscan_impl(const float* xyz, int dim, const float* times, int64_t n,
+                                    double eps_space, float eps_time, int min_samples, int min_frames, int wf_border,
+                                    int* labels, unsigned char* core_out);
+
 /* Returns number of clusters, or -1 on allocation failure / bad arguments. */
 int64_t oracle_stdbscan(const float* xyz, int dim, const float* times, int64_t n,
                         double eps_space, float eps_time, int min_samples,
                         int* labels, unsigned char* core_out) {
+    return oracle_stdbscan_impl(xyz, dim, times, n, eps_space, eps_time, min_samples, 0, 0, labels, core_out);
+}
+
+int64_t oracle_stdbscan_wf(const float* xyz, int dim, const float* times, int64_t n,
+                           double eps_space, float eps_time, int min_samples, int min_frames,
+                           int* labels, unsigned char* core_out) {
+    return oracle_stdbscan_impl(xyz, dim, times, n, eps_space, eps_time, min_samples, min_frames, 1, labels, core_out);
+}
+
+static int64_t oracle_stdbscan_impl(const float* xyz, int dim, const float* times, int64_t n,
+                                    double eps_space, float eps_time, int min_samples, int min_frames, int wf_border,
+                                    int* labels, unsigned char* core_out) {
     if (dim < 1 || dim > 3 || n < 0) return -1;
     for (int64_t i = 0; i < n; ++i) labels[i] = -1;
     if (core_out) memset(core_out, 0, (size_t)n);
@@ -167,9 +204,21 @@ int64_t oracle_stdbscan(const float* xyz, int dim, const float* times, int64_t n
     }
     g.ustart[g.nu] = n;
 
-    count_ctx cc = {count};
-    for (int64_t p = 0; p < n; ++p) for_each_neighbour(&g, p, visit_count, &cc);
-    for (int64_t p = 0; p < n; ++p) { core[p] = count[p] >= min_samples; parent[p] = p; }
+    if (wf_border) {
+        int32_t* vals = (int32_t*)malloc(sizeof(int32_t) * 4096);
+        if (!vals) return -1;
+        for (int64_t p = 0; p < n; ++p) {
+            frames_ctx fc = {times, vals, 0, 0};
+            for_each_neighbour(&g, p, visit_frames, &fc);
+            core[p] = fc.count >= min_samples && fc.n >= min_frames;
+            parent[p] = p;
+        }
+        free(vals);
+    } else {
+        count_ctx cc = {count};
+        for (int64_t p = 0; p < n; ++p) for_each_neighbour(&g, p, visit_count, &cc);
+        for (int64_t p = 0; p < n; ++p) { core[p] = count[p] >= min_samples; parent[p] = p; }
+    }
 
     union_ctx uc = {parent, core};
     for (int64_t p = 0; p < n; ++p) if (core[p]) for_each_neighbour(&g, p, visit_union, &uc);
@@ -182,9 +231,15 @@ int64_t oracle_stdbscan(const float* xyz, int dim, const float* times, int64_t n
     for (int64_t p = 0; p < n; ++p) if (core[p]) labels[p] = root_id[uf_find(parent, p)];
     for (int64_t p = 0; p < n; ++p) {
         if (core[p]) continue;
-        border_ctx bc = {labels, core, -1};
-        for_each_neighbour(&g, p, visit_border, &bc);
-        labels[p] = bc.best;
+        if (wf_border) {
+            border_wf_ctx bw = {labels, core, parent, p, -1};
+            for_each_neighbour(&g, p, visit_border_wf, &bw);
+            labels[p] = bw.best;
+        } else {
+            border_ctx bc = {labels, core, -1};
+            for_each_neighbour(&g, p, visit_border, &bc);
+            labels[p] = bc.best;
+        }
     }
     if (core_out) memcpy(core_out, core, (size_t)n);
 

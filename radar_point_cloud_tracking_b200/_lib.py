@@ -71,6 +71,7 @@ SIGNATURES = {
                                c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "rb_stdbscan": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_f64, c_f32, c_i32,
                             c_vp, c_vp, C.POINTER(c_i64), c_vp]),
+    "rb_stdbscan_wf": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_f64, c_f32, c_i32, c_i32, c_vp, c_vp, C.POINTER(c_i64), c_vp]),
     "rb_stdbscan_last_stats": (c_i32, [c_vp, C.POINTER(DbscanStats)]),
     "rb_stdbscan_plan": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_f64, c_f32, c_i32, c_vp]),
     "rb_stdbscan_plan_hinted": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_f64, c_f32, c_i32, C.POINTER(StdbscanHint), c_vp]),

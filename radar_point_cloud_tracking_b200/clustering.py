@@ -24,10 +24,14 @@ def _as_float32_exact(a: np.ndarray, what: str) -> np.ndarray:
     return b
 
 
-def st_dbscan(coords: np.ndarray, times: np.ndarray, eps_space: float, eps_time: float, min_samples: int
-              ) -> np.ndarray:
+def st_dbscan(coords: np.ndarray, times: np.ndarray, eps_space: float, eps_time: float, min_samples: int,
+              min_frames: int = None) -> np.ndarray:
     """Spatio-temporal DBSCAN: neighbours are within ``eps_space`` (Euclidean, float64 test on the
-    float32 coordinates, inclusive) AND within ``eps_time``. ``coords`` is ``[N, D]`` with D in 1..3."""
+    float32 coordinates, inclusive) AND within ``eps_time``. ``coords`` is ``[N, D]`` with D in 1..3.
+
+    ``min_frames=None``: the function of ``3_stdbscan_point_clouds.py:101`` / ``radar_pipeline.processors.clustering``.
+    ``min_frames=k``: the ``PointCloudWorkF/stdbscan_denoising_pipeline.py:264`` variant (core points must also have
+    neighbours in at least k distinct frames; its FIFO border rule), labels identical to that function's."""
     coords = np.asarray(coords)
     if coords.ndim == 1:
         coords = coords.reshape(-1, 1)
@@ -50,5 +54,5 @@ def st_dbscan(coords: np.ndarray, times: np.ndarray, eps_space: float, eps_time:
     flat = torch.from_numpy(coords).to(d).view(-1)
     t = torch.from_numpy(np.ascontiguousarray(times)).to(d)
     labels, _ = dev.stdbscan(flat, flat[1:] if dim > 1 else None, flat[2:] if dim > 2 else None, t,
-                             eps_space, eps_time, min_samples, stride=dim, n=n)
+                             eps_space, eps_time, min_samples, stride=dim, n=n, min_frames=min_frames)
     return labels.cpu().numpy()

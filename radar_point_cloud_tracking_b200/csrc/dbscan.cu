@@ -273,21 +273,30 @@ __device__ __forceinline__ void for_each_candidate(const DbGrid& g, const int* _
 }
 
 // core[p]: 1 = core, 0 = not core, 2 = not core and alone (no neighbour but itself)
-template <int DIM>
+// WF = the PointCloudWorkF variant (stdbscan_denoising_pipeline.py:308-315): the neighbours must also span at least
+// min_frames distinct int32(times). |t_q - t_p| <= eps_t <= 30 keeps int(t_q) - int(t_p) + 31 inside a 64-bit mask.
+template <int DIM, bool WF>
 __global__ void __launch_bounds__(DB_THREADS) dbg_count_kernel(Sorted s, DbGrid g, int n, double eps2, float eps_t,
-                                                              int min_samples, uint8_t* __restrict__ core,
+                                                              int min_samples, int min_frames, uint8_t* __restrict__ core,
                                                               unsigned long long* __restrict__ ctr) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long tests = 0;
     if (p < n) {
         Pt<DIM> a = load_pt<DIM>(s, p);
         int cnt = 0;
+        unsigned long long frames = 0;
+        const int ta = (int)a.t;
         for_each_candidate<DIM>(g, s.cell_start, s.cell[p], [&](int q) {
             ++tests;
-            cnt += is_neighbour<DIM>(a, load_pt<DIM>(s, q), eps2, eps_t);
-            return cnt < min_samples || cnt < 2;          // keep going until core is certain
+            const Pt<DIM> b = load_pt<DIM>(s, q);
+            if (is_neighbour<DIM>(a, b, eps2, eps_t)) {
+                ++cnt;
+                if (WF) frames |= 1ull << ((int)b.t - ta + 31);
+            }
+            return cnt < min_samples || cnt < 2 || (WF && __popcll(frames) < min_frames);   // until core is certain
         });
-        core[p] = cnt >= min_samples ? 1 : (cnt <= 1 ? 2 : 0);
+        const bool is_core = cnt >= min_samples && (!WF || __popcll(frames) >= min_frames);
+        core[p] = is_core ? 1 : (cnt <= 1 ? 2 : 0);
     }
     add_counter(ctr, tests);
 }
@@ -340,10 +349,14 @@ __global__ void __launch_bounds__(DB_THREADS) dbg_keyout_kernel(int n, const uin
     comp_key[sidx[p]] = core[p] == 1 ? minkey[parent[p]] : -1;
 }
 
-template <int DIM>
+// WF border rule (FIFO expansion of stdbscan_denoising_pipeline.py:337-366, see oracle st_dbscan_wf_canonical): the
+// cluster of a core neighbour q may be joined only if it started before the border point was looked at (its start
+// point = smallest core index = comp_key < the border point's index) or q IS the start point.
+template <int DIM, bool WF>
 __global__ void __launch_bounds__(DB_THREADS) dbg_border_kernel(Sorted s, DbGrid g, int n, double eps2, float eps_t,
                                                                const uint8_t* __restrict__ core, const int* __restrict__ slabel,
-                                                               const int* __restrict__ sidx, int32_t* __restrict__ labels,
+                                                               const int* __restrict__ sidx, const long long* __restrict__ comp_key,
+                                                               int32_t* __restrict__ labels,
                                                                unsigned long long* __restrict__ ctr) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long tests = 0;
@@ -356,6 +369,11 @@ __global__ void __launch_bounds__(DB_THREADS) dbg_border_kernel(Sorted s, DbGrid
                 if (core[q] == 1) {
                     int lq = slabel[q];
                     if (lq < best) {                          // only a smaller id can change the answer
+                        if (WF) {
+                            const int oq = sidx[q];
+                            const long long start = comp_key[oq];
+                            if (!(start < (long long)sidx[p] || start == (long long)oq)) return true;
+                        }
                         ++tests;
                         if (is_neighbour<DIM>(a, load_pt<DIM>(s, q), eps2, eps_t)) best = lq;
                     }
@@ -385,8 +403,8 @@ __device__ __forceinline__ Window window_of(const DbGrid& g, const CellPos& c) {
     return w;
 }
 
-template <int DIM>
-__global__ void __launch_bounds__(DB_THREADS) dbt_count_kernel(Sorted s, DbGrid g, int n, double eps2, int min_samples,
+template <int DIM, bool WF>
+__global__ void __launch_bounds__(DB_THREADS) dbt_count_kernel(Sorted s, DbGrid g, int n, double eps2, int min_samples, int min_frames,
                                                               uint8_t* __restrict__ core, unsigned long long* __restrict__ ctr) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long tests = 0;
@@ -397,30 +415,36 @@ __global__ void __launch_bounds__(DB_THREADS) dbt_count_kernel(Sorted s, DbGrid 
         const int per_t = g.n[0] * g.n[1] * g.n[2];
         const int sp = cell - c.tb * per_t;
         int cnt = 0;
+        unsigned long long frames = 0;                    // WF: time bins (= integer times) seen among the neighbours
         // own spatial cell over the time window: neighbours by construction
-        for (int tt = w.t0; tt <= w.t1; ++tt) cnt += s.cell_start[tt * per_t + sp + 1] - s.cell_start[tt * per_t + sp];
-        if (cnt < min_samples) {
+        for (int tt = w.t0; tt <= w.t1; ++tt) {
+            const int k = s.cell_start[tt * per_t + sp + 1] - s.cell_start[tt * per_t + sp];
+            cnt += k;
+            if (WF && k > 0) frames |= 1ull << (tt - w.t0);
+        }
+        auto open = [&]() { return cnt < min_samples || (WF && __popcll(frames) < min_frames); };
+        if (open()) {
             const Pt<DIM> a = load_pt<DIM>(s, p);
-            for (int tt = w.t0; tt <= w.t1 && cnt < min_samples; ++tt)
-                for (int zz = w.z0; zz <= w.z1 && cnt < min_samples; ++zz)
-                    for (int yy = w.y0; yy <= w.y1 && cnt < min_samples; ++yy) {
+            for (int tt = w.t0; tt <= w.t1 && open(); ++tt)
+                for (int zz = w.z0; zz <= w.z1 && open(); ++zz)
+                    for (int yy = w.y0; yy <= w.y1 && open(); ++yy) {
                         const int row = ((tt * g.n[2] + zz) * g.n[1] + yy) * g.n[0];
                         const bool own_row = zz == c.cz && yy == c.cy;
                         // the row's cells x0..x1 are one contiguous range of sorted points; skip the own cell
                         const int b = s.cell_start[row + w.x0], e = s.cell_start[row + w.x1 + 1];
                         int hb = e, he = e;                                   // hole = the own cell's points (already counted)
                         if (own_row) { hb = s.cell_start[row + c.cx]; he = s.cell_start[row + c.cx + 1]; }
-                        for (int q = b; q < hb && cnt < min_samples; ++q) {
+                        for (int q = b; q < hb && open(); ++q) {
                             ++tests;
-                            cnt += near_enough<DIM>(a, load_pt<DIM>(s, q), eps2);
+                            if (near_enough<DIM>(a, load_pt<DIM>(s, q), eps2)) { ++cnt; if (WF) frames |= 1ull << (tt - w.t0); }
                         }
-                        for (int q = he; q < e && cnt < min_samples; ++q) {
+                        for (int q = he; q < e && open(); ++q) {
                             ++tests;
-                            cnt += near_enough<DIM>(a, load_pt<DIM>(s, q), eps2);
+                            if (near_enough<DIM>(a, load_pt<DIM>(s, q), eps2)) { ++cnt; if (WF) frames |= 1ull << (tt - w.t0); }
                         }
                     }
         }
-        core[p] = cnt >= min_samples ? 1 : (cnt <= 1 ? 2 : 0);
+        core[p] = !open() ? 1 : (cnt <= 1 ? 2 : 0);
     }
     add_counter(ctr, tests);
 }
@@ -711,11 +735,12 @@ __global__ void __launch_bounds__(DB_THREADS) db_gather_labels_kernel(int n, con
     slabel[p] = lab;
 }
 
-template <int DIM>
+template <int DIM, bool WF>
 __global__ void __launch_bounds__(DB_THREADS) dbt_border_kernel(Sorted s, DbGrid g, int n, double eps2, const uint8_t* __restrict__ core,
                                                                const int* __restrict__ slabel, const int* __restrict__ sidx,
                                                                const int* __restrict__ b_ncore, const int* __restrict__ core_start,
-                                                               const int* __restrict__ b_label, int32_t* __restrict__ labels,
+                                                               const int* __restrict__ b_label, const int* __restrict__ b_parent,
+                                                               const long long* __restrict__ b_minkey, int32_t* __restrict__ labels,
                                                                unsigned long long* __restrict__ ctr) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long tests = 0;
@@ -729,9 +754,19 @@ __global__ void __launch_bounds__(DB_THREADS) dbt_border_kernel(Sorted s, DbGrid
             const int sp = cell - c.tb * per_t;
             int best = INT_MAX;
             // cores of the own spatial cell inside the time window are neighbours
+            const long long me = sidx[p];
             for (int tt = w.t0; tt <= w.t1; ++tt) {
                 const int b = tt * per_t + sp;
-                if (b_ncore[b] > 0) best = min(best, b_label[b]);
+                if (b_ncore[b] <= 0) continue;
+                if (WF) {
+                    // WF border rule: the bucket's cluster must have started before this point was looked at, or its
+                    // start point itself (the core whose index is the component key) must be among the neighbours
+                    const long long start = b_minkey[b_parent[b]];
+                    bool ok = start < me;
+                    for (int q = s.cell_start[b]; !ok && q < s.cell_start[b + 1]; ++q) ok = core[q] == 1 && (long long)sidx[q] == start;
+                    if (!ok) continue;
+                }
+                best = min(best, b_label[b]);
             }
             if (best != 0) {
                 const Pt<DIM> a = load_pt<DIM>(s, p);
@@ -745,8 +780,10 @@ __global__ void __launch_bounds__(DB_THREADS) dbt_border_kernel(Sorted s, DbGrid
                                 if (b_ncore[b] == 0 || (xx == c.cx && yy == c.cy && zz == c.cz)) continue;
                                 const int lb = b_label[b];
                                 if (lb >= best) continue;                 // only a smaller id can change the answer
+                                const long long start = WF ? b_minkey[b_parent[b]] : 0;
+                                const bool any_core = !WF || start < me;   // WF: else only the start point itself counts
                                 for (int q = s.cell_start[b]; q < s.cell_start[b + 1]; ++q) {
-                                    if (core[q] != 1) continue;
+                                    if (core[q] != 1 || (!any_core && (long long)sidx[q] != start)) continue;
                                     ++tests;
                                     if (near_enough<DIM>(a, load_pt<DIM>(s, q), eps2)) { best = lb; break; }
                                 }
@@ -908,6 +945,7 @@ struct rb_db_plan {
     double eps2 = 0, cell = 0, wt = 0;
     float eps_t = 0;
     int min_samples = 0;
+    int min_frames = 0;                          // > 0: PointCloudWorkF variant (extra core test + FIFO border rule)
     bool have_cores = false, have_components = false;
     // device arrays (scratch slots of the ctx)
     int *cell_start = nullptr, *sidx = nullptr, *scell = nullptr, *parent = nullptr, *flags = nullptr, *rank = nullptr, *slabel = nullptr;
@@ -938,6 +976,7 @@ int plan_build(rb_ctx* ctx, rb_db_plan& P, const DbPoints& pts, int64_t n64, dou
     P.valid = false;
     P.dim = DIM; P.n = n; P.eps2 = eps_space * eps_space; P.eps_t = eps_time; P.min_samples = min_samples;
     P.have_cores = P.have_components = false;
+    P.min_frames = 0;
 
     // 1. bounds -> host
     RB_TRY(scratch(ctx, RB_S_MISC, 64, &P.d_misc));
@@ -1013,8 +1052,11 @@ template <int DIM>
 int phase_cores(rb_ctx* ctx, rb_db_plan& P, cudaStream_t stream) {
     const unsigned blocks = (unsigned)rb_div_up(P.n, DB_THREADS);
     const Sorted s = sorted_view(P);
-    if (P.g.tight) dbt_count_kernel<DIM><<<blocks, DB_THREADS, 0, stream>>>(s, P.g, P.n, P.eps2, P.min_samples, P.core, P.d_ctr + 0);
-    else dbg_count_kernel<DIM><<<blocks, DB_THREADS, 0, stream>>>(s, P.g, P.n, P.eps2, P.eps_t, P.min_samples, P.core, P.d_ctr + 0);
+    const bool wf = P.min_frames > 0;
+    if (P.g.tight && wf) dbt_count_kernel<DIM, true><<<blocks, DB_THREADS, 0, stream>>>(s, P.g, P.n, P.eps2, P.min_samples, P.min_frames, P.core, P.d_ctr + 0);
+    else if (P.g.tight) dbt_count_kernel<DIM, false><<<blocks, DB_THREADS, 0, stream>>>(s, P.g, P.n, P.eps2, P.min_samples, 0, P.core, P.d_ctr + 0);
+    else if (wf) dbg_count_kernel<DIM, true><<<blocks, DB_THREADS, 0, stream>>>(s, P.g, P.n, P.eps2, P.eps_t, P.min_samples, P.min_frames, P.core, P.d_ctr + 0);
+    else dbg_count_kernel<DIM, false><<<blocks, DB_THREADS, 0, stream>>>(s, P.g, P.n, P.eps2, P.eps_t, P.min_samples, 0, P.core, P.d_ctr + 0);
     RB_LAUNCH_CHECK(ctx);
     P.have_cores = true;
     P.have_components = false;
@@ -1075,12 +1117,19 @@ int phase_assign(rb_ctx* ctx, rb_db_plan& P, const int32_t* core_label, int32_t*
     db_gather_labels_kernel<<<blocks, DB_THREADS, 0, stream>>>(n, P.core, P.sidx, P.scell, core_label, P.slabel,
                                                               P.g.tight ? P.b_label : nullptr);
     RB_LAUNCH_CHECK(ctx);
-    if (P.g.tight)
-        dbt_border_kernel<DIM><<<blocks, DB_THREADS, 0, stream>>>(s, P.g, n, P.eps2, P.core, P.slabel, P.sidx, P.b_ncore, P.core_start,
-                                                                  P.b_label, labels, P.d_ctr + 2);
+    const bool wf = P.min_frames > 0;
+    if (P.g.tight && wf)
+        dbt_border_kernel<DIM, true><<<blocks, DB_THREADS, 0, stream>>>(s, P.g, n, P.eps2, P.core, P.slabel, P.sidx, P.b_ncore, P.core_start,
+                                                                        P.b_label, P.b_parent, P.b_minkey, labels, P.d_ctr + 2);
+    else if (P.g.tight)
+        dbt_border_kernel<DIM, false><<<blocks, DB_THREADS, 0, stream>>>(s, P.g, n, P.eps2, P.core, P.slabel, P.sidx, P.b_ncore, P.core_start,
+                                                                         P.b_label, P.b_parent, P.b_minkey, labels, P.d_ctr + 2);
+    else if (wf)
+        dbg_border_kernel<DIM, true><<<blocks, DB_THREADS, 0, stream>>>(s, P.g, n, P.eps2, P.eps_t, P.core, P.slabel, P.sidx, P.comp_key, labels,
+                                                                        P.d_ctr + 2);
     else
-        dbg_border_kernel<DIM><<<blocks, DB_THREADS, 0, stream>>>(s, P.g, n, P.eps2, P.eps_t, P.core, P.slabel, P.sidx, labels,
-                                                                  P.d_ctr + 2);
+        dbg_border_kernel<DIM, false><<<blocks, DB_THREADS, 0, stream>>>(s, P.g, n, P.eps2, P.eps_t, P.core, P.slabel, P.sidx, P.comp_key, labels,
+                                                                         P.d_ctr + 2);
     RB_LAUNCH_CHECK(ctx);
     return RB_OK;
 }
@@ -1227,6 +1276,33 @@ extern "C" int rb_stdbscan(rb_ctx* ctx, const float* x, const float* y, const fl
     if (n == 0) return RB_OK;
     RB_REQUIRE(labels, "labels is NULL");
     RB_TRY(rb_stdbscan_enqueue(ctx, x, y, z, stride, times, n, eps_space, eps_time, min_samples, labels, core, nullptr, stream_));
+    return rb_stdbscan_fetch_stats(ctx, n_clusters, stream_);
+}
+
+extern "C" int rb_stdbscan_wf(rb_ctx* ctx, const float* x, const float* y, const float* z, int64_t stride,
+                              const float* times, int64_t n, double eps_space, float eps_time, int min_samples, int min_frames,
+                              int32_t* labels, uint8_t* core, int64_t* n_clusters, void* stream_) {
+    RB_REQUIRE(ctx, "ctx is NULL");
+    RB_REQUIRE(n >= 0 && n < ((int64_t)1 << 31) - 1, "point count out of range");
+    RB_REQUIRE(min_frames >= 1, "min_frames must be >= 1");
+    RB_REQUIRE(!(eps_time > 30.f), "rb_stdbscan_wf supports eps_time <= 30 (the frame set of a neighbourhood is a 64-bit mask)");
+    if (n_clusters) *n_clusters = 0;
+    if (n == 0) return RB_OK;
+    RB_REQUIRE(labels, "labels is NULL");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    RB_TRY(rb_stdbscan_plan(ctx, x, y, z, stride, times, n, eps_space, eps_time, min_samples, stream_));
+    rb_db_plan& P = *ctx->db_plan;
+    P.min_frames = min_frames;                                  // switches the core test and the border rule
+    RB_TRY(rb_stdbscan_cores(ctx, core, stream_));
+    RB_TRY(rb_stdbscan_components(ctx, nullptr, nullptr, stream_));
+    const unsigned blocks = (unsigned)rb_div_up(P.n, DB_THREADS);
+    db_rootflag_kernel<<<blocks, DB_THREADS, 0, stream>>>(P.n, P.comp_key, P.flags);
+    RB_LAUNCH_CHECK(ctx);
+    int* d_total = (int*)(P.d_ctr + 3);
+    RB_TRY(rb_exclusive_scan_i32(ctx, P.flags, P.rank, P.n, d_total, stream));
+    db_rank_labels_kernel<<<blocks, DB_THREADS, 0, stream>>>(P.n, P.comp_key, P.rank, labels);
+    RB_LAUNCH_CHECK(ctx);
+    RB_TRY(rb_stdbscan_assign(ctx, labels, labels, stream_));
     return rb_stdbscan_fetch_stats(ctx, n_clusters, stream_);
 }
 

@@ -239,7 +239,7 @@ def land_filter(batch: PointBatch, x_edges: torch.Tensor, y_edges: torch.Tensor,
 # --------------------------------------------------------------------------------------- a7
 def stdbscan(x: torch.Tensor, y: Optional[torch.Tensor], z: Optional[torch.Tensor], times: torch.Tensor,
              eps_space: float, eps_time: float, min_samples: int, stride: int = 1, n: Optional[int] = None,
-             want_core: bool = False):
+             want_core: bool = False, min_frames: Optional[int] = None):
     """ST-DBSCAN labels (int32, the reference's own numbering). ``x/y/z`` may be SoA tensors
     (stride 1) or views into one row-major ``[N,D]`` tensor (stride D)."""
     ctx = context(x.device.index)
@@ -252,9 +252,14 @@ def stdbscan(x: torch.Tensor, y: Optional[torch.Tensor], z: Optional[torch.Tenso
     for name, t in (("x", x), ("y", y), ("z", z), ("times", times)):
         if t is not None and (not t.is_cuda or t.dtype != torch.float32):
             raise RadarB200Error(f"{name} must be a float32 CUDA tensor")
-    check(ctx.lib.rb_stdbscan(ctx.handle, ptr(x), ptr(y), ptr(z), int(stride), ptr(times), int(n),
-                              float(eps_space), float(np.float32(eps_time)), int(min_samples), ptr(labels), ptr(core),
-                              C.byref(ncl), stream_ptr()), "rb_stdbscan")
+    if min_frames is None:
+        check(ctx.lib.rb_stdbscan(ctx.handle, ptr(x), ptr(y), ptr(z), int(stride), ptr(times), int(n),
+                                  float(eps_space), float(np.float32(eps_time)), int(min_samples), ptr(labels), ptr(core),
+                                  C.byref(ncl), stream_ptr()), "rb_stdbscan")
+    else:                                                         # PointCloudWorkF variant (WF:264-369)
+        check(ctx.lib.rb_stdbscan_wf(ctx.handle, ptr(x), ptr(y), ptr(z), int(stride), ptr(times), int(n),
+                                     float(eps_space), float(np.float32(eps_time)), int(min_samples), int(min_frames),
+                                     ptr(labels), ptr(core), C.byref(ncl), stream_ptr()), "rb_stdbscan_wf")
     if want_core:
         return labels, core, ncl.value
     return labels, ncl.value

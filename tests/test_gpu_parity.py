@@ -628,3 +628,34 @@ def test_pipeline_uint8_block_equals_float32(gpu):
     assert torch.equal(a.labels, b.labels) and torch.equal(a.points.inten[:a.points.n], b.points.inten[:b.points.n])
     h = pipe.run_host(echo.to(torch.uint8).cpu().numpy(), spec.angle_units(), spec.scale())
     assert np.array_equal(h["labels"], a.labels.cpu().numpy()) and h["h2d_bytes"] < echo.numel() * 1.1
+
+
+# ------------------------------------------------------------------------------- f3: PointCloudWorkF variant
+def test_stdbscan_wf_variant_vs_reference_golden(gpu, db_mode):
+    """min_frames core test + FIFO border rule: labels identical to the unmodified reference function (golden)."""
+    from radar_point_cloud_tracking_b200.clustering import st_dbscan
+    g = golden("wf_stdbscan")
+    for k in range(int(g["n_cases"])):
+        eps_s, eps_t, ms, mf = g[f"c{k}_params"]
+        got = st_dbscan(g[f"c{k}_coords"], g[f"c{k}_times"], float(eps_s), float(eps_t), int(ms), min_frames=int(mf))
+        assert np.array_equal(got, g[f"c{k}_labels"]), k
+
+
+@pytest.mark.parametrize("n,frames,eps_s,eps_t,ms,mf", [(60000, 30, 8.0, 2.0, 15, 2), (40000, 12, 6.0, 1.0, 8, 3), (30000, 6, 5.0, 1.5, 6, 2)])
+def test_stdbscan_wf_variant_vs_c_oracle_medium(gpu, db_mode, n, frames, eps_s, eps_t, ms, mf):
+    from oracle.c_oracle import st_dbscan_wf_c
+    rng = np.random.default_rng(n + mf)
+    coords = (rng.random((n, 2)) * 400).astype(np.float32)
+    centres = (rng.random((40, 2)) * 400).astype(np.float32)
+    coords[: n // 2] = (centres[rng.integers(0, 40, n // 2)] + rng.normal(0, 3.0, (n // 2, 2))).astype(np.float32)
+    coords = coords[rng.permutation(n)]
+    times = rng.integers(0, frames, n).astype(np.float32) if eps_t == int(eps_t) else (rng.random(n) * frames).astype(np.float32)
+    want, want_core = st_dbscan_wf_c(coords, times, eps_s, eps_t, ms, mf)
+    plain, _ = st_dbscan_c(coords, times, eps_s, eps_t, ms)
+    assert (want != plain).any()                                   # the variant really differs from T4 on this case
+    d = torch.device("cuda:0")
+    flat = torch.from_numpy(coords).to(d).view(-1)
+    lab, core, ncl = gpu.stdbscan(flat, flat[1:], None, torch.from_numpy(times).to(d), eps_s, eps_t, ms, stride=2, n=n,
+                                  want_core=True, min_frames=mf)
+    assert np.array_equal(core.cpu().numpy().astype(bool), want_core)
+    assert np.array_equal(lab.cpu().numpy(), want) and ncl == want.max() + 1

@@ -180,3 +180,19 @@ def test_rust_known_answer_clusters(fn):
     assert lab[0] >= 0 and lab[0] == lab[1] == lab[2] and lab[3] == -1
     assert len(fn(np.zeros((0, 3), np.float32), np.zeros(0, np.float32), 5.0, 1.0, 3)) == 0
     assert fn(np.zeros((1, 3), np.float32), np.zeros(1, np.float32), 5.0, 1.0, 2)[0] == -1
+
+
+def test_wf_variant_oracles_vs_reference_golden():
+    """PointCloudWorkF min_frames variant: the order-free numpy statement and the C oracle against labels of the
+    UNMODIFIED reference function (tests/golden/make_golden_wf.py), incl. 3-D and fractional-time cases."""
+    from oracle.c_oracle import st_dbscan_wf_c
+    g = golden("wf_stdbscan")
+    assert int(g["n_cases"]) >= 16
+    for k in range(int(g["n_cases"])):
+        eps_s, eps_t, ms, mf = g[f"c{k}_params"]
+        c, tm, want = g[f"c{k}_coords"], g[f"c{k}_times"], g[f"c{k}_labels"]
+        got_c, _ = st_dbscan_wf_c(c, tm, float(eps_s), float(eps_t), int(ms), int(mf))
+        assert np.array_equal(got_c, want), k
+        if k < 6:                                                 # the Python restatements are slow: a few cases
+            assert np.array_equal(O.st_dbscan_wf_canonical(c, tm, float(eps_s), float(eps_t), int(ms), int(mf))[0], want), k
+            assert np.array_equal(O.st_dbscan_wf_sequential(c, tm, float(eps_s), float(eps_t), int(ms), int(mf)), want), k
