@@ -1,7 +1,6 @@
 """Build ``libradarb200.so`` (hand-written CUDA for sm_100a + the C ABI) in-tree with nvcc."""
 from __future__ import annotations
 
-import os
 import shutil
 import subprocess
 import sys

@@ -7,10 +7,12 @@
 // measured first: its prefix latency of ~9 us per 64 KiB tile capped it at 1.4 TB/s, see
 // profiles/r01_spoke_v2_tma_lookback_trace.txt):
 //
-//   1. spoke_mask_kernel    streams echo[W][S][E] ONCE at HBM speed (128-bit loads, 8 in flight per
-//                           lane, tiles handed out by a warp-level ticket). Output: 1 bit per cell
-//                           (survivor mask, cell order) and one survivor count per 4096-cell tile.
-//                           This is the HBM-bound kernel: 4 B read + 1/8 B written per cell.
+//   1. spoke_mask_tma_kernel streams echo[W][S][E] ONCE at HBM speed: one persistent CTA per SM, a producer warp
+//                           fills a ring of 64 KiB shared-memory stages with 1-D bulk async copies (TMA), consumer
+//                           warps turn them into 1 bit per cell (survivor mask, cell order) and one survivor
+//                           count per 4096-cell tile. The HBM-bound kernel: 4 B (float32) or 1 B (uint8 echoes)
+//                           read + 1/8 B written per cell. spoke_mask_kernel is the register-staged fallback for
+//                           sweeps that are not a multiple of 16 bytes.
 //   2. spoke_offsets_kernel in-sweep exclusive prefix of the tile counts (one block per sweep) and,
 //                           by the last block to finish, the output base of every sweep:
 //                           base[w] = sum_{w'<w} ceil(M_w' / stride)   (x[mask][::stride], T4:222-230)

@@ -11,7 +11,7 @@ per-frame ``Cluster`` records, the Hungarian tracker and the CSV writers can con
 from __future__ import annotations
 
 from collections import defaultdict
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from datetime import datetime
 from typing import Dict, List, Optional, Sequence, Tuple
 

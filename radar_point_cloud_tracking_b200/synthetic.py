@@ -16,7 +16,7 @@ Data model (mirrors the radar CSV of the reference, ``PIPELINE_DOCUMENTATION.txt
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from pathlib import Path
 from typing import Dict, List, Sequence, Tuple
 

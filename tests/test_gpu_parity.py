@@ -659,3 +659,31 @@ def test_stdbscan_wf_variant_vs_c_oracle_medium(gpu, db_mode, n, frames, eps_s, 
                                   want_core=True, min_frames=mf)
     assert np.array_equal(core.cpu().numpy().astype(bool), want_core)
     assert np.array_equal(lab.cpu().numpy(), want) and ncl == want.max() + 1
+
+
+def test_stdbscan_partition_is_permutation_invariant_at_scale(gpu):
+    """Size-independent property on a full-size block (64 frames, ~150 k points after the land filter): shuffling
+    the points changes cluster NUMBERS (ranks of smallest core indices) and which cluster a shared border point
+    joins, but not the core set, the partition of the core points or the noise set."""
+    from radar_point_cloud_tracking_b200.pipeline import DetectionConfig, DetectionPipeline
+    spec = syn.SweepSpec(seed=77, frames=64)
+    pipe = DetectionPipeline(DetectionConfig(), 0)
+    echo = gpu.synth_echo(spec)
+    c, s, r = pipe.spoke_tables(spec.angle_units(), spec.scale(), spec.frames, spec.bins)
+    res = pipe.run_device(echo, *(torch.from_numpy(t).to(echo.device) for t in (c, s, r)))
+    n = res.points.n
+    assert n > 100_000 and res.n_clusters > 5
+    d = echo.device
+    x, y = res.points.x[:n], res.points.y[:n]
+    t = gpu.expand_frame_times(res.points.frame_off, torch.arange(spec.frames, dtype=torch.float32, device=d), n)
+    lab1, core1, ncl1 = gpu.stdbscan(x, y, None, t, 8.0, 2.0, 15, n=n, want_core=True)
+    assert torch.equal(lab1, res.labels)                         # the block driver's labels are rb_stdbscan's
+    perm = torch.randperm(n, device=d, generator=torch.Generator(device=d).manual_seed(3))
+    lab2, core2, ncl2 = gpu.stdbscan(x[perm].contiguous(), y[perm].contiguous(), None, t[perm].contiguous(), 8.0, 2.0, 15, n=n,
+                                     want_core=True)
+    assert ncl1 == ncl2 and torch.equal(core1[perm], core2)
+    a, b = lab1[perm].cpu().numpy(), lab2.cpu().numpy()
+    cm = core2.cpu().numpy().astype(bool)
+    assert np.array_equal(a < 0, b < 0)                          # same noise set
+    pairs = np.unique(np.stack([a[cm], b[cm]]), axis=1)          # label map between the two runs on core points
+    assert pairs.shape[1] == ncl1 and len(np.unique(pairs[0])) == ncl1 and len(np.unique(pairs[1])) == ncl1

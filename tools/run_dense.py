@@ -8,7 +8,6 @@ import time
 from pathlib import Path
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
-import numpy as np
 import torch
 
 from radar_point_cloud_tracking_b200 import device as dev, synthetic as syn
