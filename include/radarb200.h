@@ -116,6 +116,10 @@ int rb_fuse_max(rb_ctx* ctx, const float* x, const float* y, const float* inten,
 /* ---- a4-a6: land / stationary persistence filter --------------------------------------------- */
 /* Global bounds (T4:365-369): out4 = device float32 {x_min, x_max, y_min, y_max}. No sync. */
 int rb_bounds(rb_ctx* ctx, const float* x, const float* y, int64_t n, float* out4, void* stream);
+/* Same over the first min(*n_dev, n_max) points, the count still being on the device (e.g. sweep_base[W] of
+ * rb_spoke_to_points): lets a caller enqueue spoke-to-point + bounds and read count and bounds back with ONE sync. */
+int rb_bounds_counted(rb_ctx* ctx, const float* x, const float* y, const int64_t* n_dev, int64_t n_max, float* out4,
+                      void* stream);
 
 /* build_occupancy_grid accumulation (T4:378-389): for every point
  *   ix = clip(searchsorted_right(x_edges, (double)x) - 1, 0, n_x_edges - 2)      (T4:384)

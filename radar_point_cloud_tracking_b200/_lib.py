@@ -65,6 +65,7 @@ SIGNATURES = {
     "rb_fuse_max": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_i32, c_i32,
                             c_vp, c_vp, c_vp, c_i64, C.POINTER(c_i64), c_vp]),
     "rb_bounds": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "rb_bounds_counted": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "rb_land_accumulate": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp]),
     "rb_land_cells": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_f64, c_f64, c_vp, c_vp]),
     "rb_land_filter": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i32, c_vp, c_i32,
@@ -168,11 +169,32 @@ def context(device: Optional[int] = None) -> Context:
         raise RadarB200Error("no CUDA device: the radar-b200 detection path is GPU only (no CPU fallback)")
     if device is None:
         device = torch.cuda.current_device()
-    key = (device, threading.get_ident())          # a ctx is not thread safe: one per device AND host thread
+    # a ctx is not thread safe and holds per-call state (scratch, the ST-DBSCAN plan): one per device, host thread and
+    # block slot (several blocks interleaved by one thread, sharded.ShardedDetection.run_blocks)
+    key = (device, threading.get_ident(), getattr(_tls, "slot", 0))
     ctx = _contexts.get(key)
     if ctx is None:
         ctx = _contexts[key] = Context(device)
     return ctx
+
+
+_tls = threading.local()
+
+
+def set_slot(slot: int) -> int:
+    """Select the block slot of the calling thread (see :func:`context`); returns the previous one."""
+    prev = getattr(_tls, "slot", 0)
+    _tls.slot = int(slot)
+    return prev
+
+
+def launch_count_all() -> int:
+    """Kernel launches of every context of this process (all devices, threads and block slots)."""
+    return sum(c.launch_count() for c in list(_contexts.values()))
+
+
+def get_slot() -> int:
+    return getattr(_tls, "slot", 0)
 
 
 def stream_ptr() -> int:

@@ -247,6 +247,21 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
     }
 }
 
+// Union of the sets of two nodes, given (possibly stale) roots of theirs: hook the larger index under the smaller with
+// ONE atomic when it is still a root. The smaller one need not be a root: parents only point to smaller indices, so a
+// node below a root cannot belong to that root's set, and any member of the other set will do as parent. When the CAS
+// loses, the value it returns is the parent somebody else gave that node - a member of the same set with a smaller
+// index - and the loop goes on from there: no separate find, one atomic per step, the larger index falls every step.
+// (Many neighbouring buckets try the same hook at once; with a find-based retry those losers cost half the kernel.)
+__device__ __forceinline__ void uf_union_roots(int* parent, int ra, int rb) {
+    while (ra != rb) {
+        const int hi = max(ra, rb), lo = min(ra, rb);
+        const int old = atomicCAS(parent + hi, hi, lo);
+        if (old == hi || old == lo) return;
+        ra = old; rb = lo;
+    }
+}
+
 __device__ __forceinline__ long long point_key(const long long* __restrict__ gidx, int orig) {
     return gidx ? gidx[orig] : (long long)orig;
 }
@@ -472,12 +487,15 @@ __global__ void __launch_bounds__(DB_THREADS) dbt_bucket_list_kernel(int64_t n_c
                                                                     int* __restrict__ cb_list, int* __restrict__ n_cb,
                                                                     int* __restrict__ cb_slot, int* __restrict__ cb_bbox) {
     int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < n_cells && b_ncore[b] > 0) {
+    if (b >= n_cells) return;
+    if (b_ncore[b] > 0) {
         const int slot = atomicAdd(n_cb, 1);
         cb_list[slot] = (int)b;
         cb_slot[b] = slot;
 #pragma unroll
         for (int k = 0; k < 3; ++k) { cb_bbox[slot * 6 + k] = INT_MAX; cb_bbox[slot * 6 + 3 + k] = INT_MIN; }
+    } else {
+        cb_slot[b] = -1;                                 // "no core points here" for the window walk of dbt_union_kernel
     }
 }
 
@@ -504,6 +522,15 @@ __device__ __forceinline__ BBox load_bbox(const int* __restrict__ cb_bbox, int s
         b.hi[k] = k < DIM ? ord2f(__ldg(cb_bbox + (size_t)slot * 6 + 3 + k)) : 0.f;
     }
     return b;
+}
+// all core points of the bucket share one position (always so with a single core point): box_gap2 against another such
+// box IS the exact squared distance of every core pair, in near_enough's own arithmetic (0 + d*d == d*d)
+template <int DIM>
+__device__ __forceinline__ bool box_is_point(const BBox& b) {
+    bool same = b.lo[0] == b.hi[0];
+    if (DIM > 1) same = same && b.lo[1] == b.hi[1];
+    if (DIM > 2) same = same && b.lo[2] == b.hi[2];
+    return same;
 }
 // squared gap between two boxes / a point and a box, in the arithmetic of near_enough (float64, no FMA): a lower
 // bound of every pair distance it covers, so "gap > eps^2" proves that no pair can pass the exact test
@@ -558,140 +585,197 @@ __global__ void __launch_bounds__(DB_THREADS) dbt_flatten_kernel(const int* __re
     }
 }
 
-// One warp per bucket A that holds core points: connect it to the earlier buckets (B < A) in the OTHER cells of
-// its window: every lane takes one bucket of the window, resolves its root and drops it when it already
-//    shares A's root (the common case, done for 32 buckets at once); the warp then searches the remaining
-//    ones for one core-core pair within eps - cells at Chebyshev distance 1 before the far ones, so that the
-//    far ones are usually connected through a near one by the time they are looked at.
 // root lookup through the L1-cached path, for FILTERING only: a cached parent may be stale, but sets only ever
-// merge, so "same root" read from stale data is still true; "different" is re-checked with uf_find.
-__device__ __forceinline__ int uf_find_cached(const int* __restrict__ parent, int a) {
-    int cur = a;
+// merge, so "same root" read from stale data is still true; "different" is re-checked by the union itself.
+// The walk ends by pointing its start at the root it found. (Compressing every node of the path was measured too: the
+// chains are short, the extra loads and stores made the kernel 30 % slower.) Why the store is safe: parents only ever
+// point to SMALLER indices of the SAME set, and only non-roots are written (roots change by CAS alone).
+__device__ __forceinline__ int uf_find_cached(int* __restrict__ parent, int a) {
+    const int p = __ldca(parent + a);
+    if (p == a) return a;
+    int root = p;
     while (true) {
-        int p = __ldca(parent + cur);
-        if (p == cur) return cur;
-        cur = p;
+        const int q = __ldca(parent + root);
+        if (q == root) break;
+        root = q;
     }
+    if (root != p) parent[a] = root;
+    return root;
 }
 
+// One LANE per bucket A that holds core points (a warp = 32 consecutive entries of the core-bucket list, i.e. mostly
+// neighbouring cells): connect A to the earlier buckets (B < A) in the OTHER cells of its window. The warp walks the
+// half window row by row (a row = the SIDE buckets with the same dt, dz, dy - consecutive bucket indices): every lane
+// loads the list slots and then the parents of its row together (independent loads in flight, and neighbouring lanes
+// read neighbouring words), drops the buckets that already share A's root - the common case once the big components
+// have formed - and only then looks for ONE core-core pair within eps in what is left: small pairs alone, 32 lanes at
+// a time; big pairs with the whole warp. Cells at Chebyshev distance 1 come in a first pass, the far ones in a
+// second, when they are usually connected through a near one already.
+// (Round-1 history: the first version gave every bucket a warp with one window cell per lane; 20 % of its instructions
+// were the per-bucket cell decode and its scattered window loads kept it latency bound - 953 us per 512-frame block.)
 template <int DIM>
-__global__ void __launch_bounds__(DB_THREADS) dbt_union_kernel(Sorted s, DbGrid g, const int* __restrict__ cb_list,
+__global__ void __launch_bounds__(DB_THREADS, DIM == 2 ? 3 : 2) dbt_union_kernel(Sorted s, DbGrid g, const int* __restrict__ cb_list,
                                                               const int* __restrict__ n_cb, const uint8_t* __restrict__ core,
                                                               const int* __restrict__ b_ncore, int* __restrict__ b_parent,
                                                               const int* __restrict__ cb_slot, const int* __restrict__ cb_bbox,
                                                               double eps2, unsigned long long* __restrict__ ctr) {
-    // tight grids search (2R+1)^DIM cells with R = 2 (R = 1 in 1-D): compile-time side length, so the offset
-    // of a lane needs no division by run-time values
-    constexpr int SIDE = DIM == 1 ? 3 : 5;
+    constexpr int SIDE = DIM == 1 ? 3 : 5;                          // tight grids search (2R+1)^DIM cells, R = 2 (1 in 1-D)
     constexpr int R = SIDE / 2;
-    constexpr int SPATIAL = DIM == 1 ? SIDE : (DIM == 2 ? SIDE * SIDE : SIDE * SIDE * SIDE);
+    constexpr int RY = DIM > 1 ? R : 0, RZ = DIM > 2 ? R : 0;
     constexpr int SMALL_PAIR = 96;                                  // |A| * |B| up to which ONE lane searches the pair
+    constexpr unsigned FULL = 0xffffffffu;
     const unsigned lane = rb_lane();
-    const int n_warps = (gridDim.x * blockDim.x) >> 5;
     const int total = *n_cb;
-    // offsets are numbered (dt, dz, dy, dx) with dx fastest - the order of the bucket index - so the first half
-    // of them are exactly the buckets that precede the centre: every unordered pair is looked at once
-    const int n_half = (SPATIAL * (2 * g.tr + 1)) / 2;
     const int nxy = g.n[0] * g.n[1];
+    const int per_t = nxy * g.n[2];
+    const int n_threads = gridDim.x * blockDim.x;
     unsigned long long tests = 0;
-    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += n_warps) {
-        const int A = cb_list[w];
-        const CellPos c = decode_cell(g, A);
-        const int a0 = s.cell_start[A], a1 = s.cell_start[A + 1];
-        const int root_a = uf_find_cached(b_parent, A);
-        const BBox box_a = load_bbox<DIM>(cb_bbox, w);
-        for (int base = 0; base < n_half; base += 32) {
-            // ---- one bucket of the half window per lane ----
-            int B = -1;
-            bool far = false;
-            const int o = base + (int)lane;
-            if (o < n_half) {
-                int r = o;
-                const int dx = r % SIDE - R; r /= SIDE;
-                int dy = 0, dz = 0;
-                if (DIM > 1) { dy = r % SIDE - R; r /= SIDE; }
-                if (DIM > 2) { dz = r % SIDE - R; r /= SIDE; }
-                const int dt = r - g.tr;
-                const int xx = c.cx + dx, yy = c.cy + dy, zz = c.cz + dz, tt = c.tb + dt;
-                if ((dx | dy | dz) != 0 && xx >= 0 && xx < g.n[0] && yy >= 0 && yy < g.n[1] && zz >= 0 && zz < g.n[2] && tt >= 0) {
-                    const int bkt = A + dt * (nxy * g.n[2]) + dz * nxy + dy * g.n[0] + dx;
-                    if (__ldg(b_ncore + bkt) > 0) { B = bkt; far = max(abs(dx), max(abs(dy), abs(dz))) > 1; }
-                }
-            }
-            // ---- already connected? (cached roots: a stale "same" is still true) ----
-            if (B >= 0 && uf_find_cached(b_parent, B) == root_a) B = -1;
-            if (!__any_sync(0xffffffffu, B >= 0)) continue;
-            // ---- boxes of the core points more than eps apart: no pair can exist ----
-            BBox box_b = {};
-            int b0 = 0, b1 = 0;
-            if (B >= 0) {
-                box_b = load_bbox<DIM>(cb_bbox, __ldg(cb_slot + B));
-                if (box_gap2<DIM>(box_a, box_b) > eps2) B = -1;
-                else { b0 = s.cell_start[B]; b1 = s.cell_start[B + 1]; }
-            }
-            // ---- small pairs: the lane searches its pair alone, 32 pairs in parallel ----
-            if (B >= 0 && (a1 - a0) * (b1 - b0) <= SMALL_PAIR) {
-                bool found = false;
-                for (int ia = a0; ia < a1 && !found; ++ia) {
-                    if (core[ia] != 1) continue;
-                    const Pt<DIM> pa = load_pt<DIM>(s, ia);
-                    if (point_gap2<DIM>(pa, box_b) > eps2) continue;
-                    for (int jb = b0; jb < b1; ++jb) {
-                        if (core[jb] != 1) continue;
-                        ++tests;
-                        if (near_enough<DIM>(pa, load_pt<DIM>(s, jb), eps2)) { found = true; break; }
-                    }
-                }
-                if (found) uf_union(b_parent, A, B);
-                B = -1;
-            }
-            // ---- big pairs: the whole warp, 32 x 32 points in registers at a time; near cells first ----
-            for (int pass = 0; pass < 2; ++pass) {
-                unsigned todo = __ballot_sync(0xffffffffu, B >= 0 && (int)far == pass);
-                while (todo) {
-                    const int src = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const int Bw = __shfl_sync(0xffffffffu, B, src);
-                    int same = 0;
-                    if (lane == 0) same = uf_find(b_parent, A) == uf_find(b_parent, Bw);
-                    if (__shfl_sync(0xffffffffu, same, 0)) continue;
-                    const int w0 = __shfl_sync(0xffffffffu, b0, src), w1 = __shfl_sync(0xffffffffu, b1, src);
-                    BBox bb;
+    for (int wbase = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; wbase < total; wbase += n_threads) {
+        const int i = wbase + (int)lane;
+        const bool live = i < total;
+        int A = -1, a0 = 0, a1 = 0, root_a = -1;
+        CellPos c = {0, 0, 0, 0};
+        BBox box_a = {};
+        if (live) {
+            A = cb_list[i];
+            c = decode_cell(g, A);
+            a0 = s.cell_start[A]; a1 = s.cell_start[A + 1];
+            root_a = uf_find_cached(b_parent, A);
+            box_a = load_bbox<DIM>(cb_bbox, i);
+        }
+        const bool a_point = box_is_point<DIM>(box_a);
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int dt = -g.tr; dt <= 0; ++dt) {
+                const bool t_ok = live && c.tb + dt >= 0;
+                if (live) root_a = __ldca(b_parent + root_a);                        // one hop keeps a merged-away root fresh
+                for (int dz = -RZ; dz <= RZ; ++dz) {
+                    for (int dy = -RY; dy <= RY; ++dy) {
+                        // rows after the centre belong to the other half of the window (their buckets look back at A)
+                        if (dt == 0 && (dz > 0 || (dz == 0 && dy > 0))) continue;
+                        const bool row_far = max(abs(dy), abs(dz)) > 1;
+                        if (pass == 0 && row_far) continue;
+                        const bool centre_row = dt == 0 && dz == 0 && dy == 0;       // only dx < 0 there
+                        const bool same_cell_row = dz == 0 && dy == 0;               // dx = 0 is A's own cell: the time chain
+                        const int yy = c.cy + dy, zz = c.cz + dz;
+                        const bool row_ok = t_ok && yy >= 0 && yy < g.n[1] && zz >= 0 && zz < g.n[2];
+                        const int row = A + dt * per_t + dz * nxy + dy * g.n[0];     // the bucket at dx = 0
+                        // ---- list slots of the row (-1 = no core points), then the parents of the occupied buckets ----
+                        unsigned m = 0;
+                        int sl[SIDE];
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        bb.lo[k] = __shfl_sync(0xffffffffu, box_b.lo[k], src);
-                        bb.hi[k] = __shfl_sync(0xffffffffu, box_b.hi[k], src);
-                    }
-                    bool found = false;
-                    for (int ia0 = a0; ia0 < a1 && !found; ia0 += 32) {
-                        const int ia_l = ia0 + (int)lane;
-                        Pt<DIM> mine_a = {};
-                        bool use_a = false;
-                        if (ia_l < a1 && core[ia_l] == 1) { mine_a = load_pt<DIM>(s, ia_l); use_a = point_gap2<DIM>(mine_a, bb) <= eps2; }
-                        const unsigned act_a = __ballot_sync(0xffffffffu, use_a);
-                        if (!act_a) continue;
-                        for (int jb0 = w0; jb0 < w1 && !found; jb0 += 32) {
-                            const int jb_l = jb0 + (int)lane;
-                            Pt<DIM> mine_b = {};
-                            bool use_b = false;
-                            if (jb_l < w1 && core[jb_l] == 1) { mine_b = load_pt<DIM>(s, jb_l); use_b = point_gap2<DIM>(mine_b, box_a) <= eps2; }
-                            if (!__any_sync(0xffffffffu, use_b)) continue;
-                            unsigned act = act_a;
-                            while (act) {
-                                const int la = __ffs(act) - 1;
-                                act &= act - 1;
-                                Pt<DIM> pa;
-                                pa.x = __shfl_sync(0xffffffffu, mine_a.x, la);
-                                pa.y = DIM > 1 ? __shfl_sync(0xffffffffu, mine_a.y, la) : 0.f;
-                                pa.z = DIM > 2 ? __shfl_sync(0xffffffffu, mine_a.z, la) : 0.f;
-                                pa.t = 0.f;
-                                bool ok = false;
-                                if (use_b) { ++tests; ok = near_enough<DIM>(pa, mine_b, eps2); }
-                                if (__any_sync(0xffffffffu, ok)) { found = true; break; }
+                        for (int k = 0; k < SIDE; ++k) {
+                            const int dx = k - R;
+                            const bool far = row_far || abs(dx) > 1;
+                            const bool use = row_ok && (int)far == pass && !(centre_row && dx >= 0) && !(same_cell_row && dx == 0) &&
+                                             c.cx + dx >= 0 && c.cx + dx < g.n[0];
+                            sl[k] = use ? __ldg(cb_slot + row + dx) : -1;
+                            if (sl[k] >= 0) m |= 1u << k;
+                        }
+                        if (!__any_sync(FULL, m != 0)) continue;
+                        int par[SIDE];
+#pragma unroll
+                        for (int k = 0; k < SIDE; ++k) par[k] = (m >> k & 1) ? __ldca(b_parent + row + (k - R)) : root_a;
+#pragma unroll
+                        for (int k = 0; k < SIDE; ++k) {
+                            if (!(m >> k & 1)) continue;
+                            // parent == A's root: same set. Otherwise finish the walk (and compress); par[k] = B's root.
+                            if (par[k] != root_a) par[k] = uf_find_cached(b_parent, row + (k - R));
+                            if (par[k] == root_a) m &= ~(1u << k);
+                        }
+                        if (!__any_sync(FULL, m != 0)) continue;
+                        // ---- what is left: one bucket of the row at a time ----
+                        for (int k = 0; k < SIDE; ++k) {
+                            int B = (m >> k & 1) ? row + (k - R) : -1;
+                            if (!__any_sync(FULL, B >= 0)) continue;
+                            BBox box_b = {};
+                            int b0 = 0, b1 = 0, rb = root_a;
+                            if (B >= 0) {
+                                int slot = -1;
+#pragma unroll
+                                for (int q = 0; q < SIDE; ++q) { slot = q == k ? sl[q] : slot; rb = q == k ? par[q] : rb; }   // no register indexing
+                                box_b = load_bbox<DIM>(cb_bbox, slot);
+                                const double gap2 = box_gap2<DIM>(box_a, box_b);
+                                ++tests;
+                                if (gap2 > eps2) {
+                                    B = -1;                        // boxes of the core points more than eps apart: no pair can exist
+                                } else if (a_point && box_is_point<DIM>(box_b)) {
+                                    uf_union_roots(b_parent, root_a, rb);          // the gap is the exact distance of every core pair
+                                    root_a = min(root_a, rb);                      // a member of the merged set, most likely its root
+                                    B = -1;
+                                } else {
+                                    b0 = s.cell_start[B]; b1 = s.cell_start[B + 1];
+                                }
+                            }
+                            // small pairs: the lane searches its pair alone
+                            if (B >= 0 && (a1 - a0) * (b1 - b0) <= SMALL_PAIR) {
+                                bool found = false;
+                                for (int ia = a0; ia < a1 && !found; ++ia) {
+                                    if (core[ia] != 1) continue;
+                                    const Pt<DIM> pa = load_pt<DIM>(s, ia);
+                                    if (point_gap2<DIM>(pa, box_b) > eps2) continue;
+                                    for (int jb = b0; jb < b1; ++jb) {
+                                        if (core[jb] != 1) continue;
+                                        ++tests;
+                                        if (near_enough<DIM>(pa, load_pt<DIM>(s, jb), eps2)) { found = true; break; }
+                                    }
+                                }
+                                if (found) {
+                                    uf_union_roots(b_parent, root_a, rb);
+                                    root_a = min(root_a, rb);
+                                }
+                                B = -1;
+                            }
+                            // big pairs: the whole warp, 32 x 32 points in registers at a time
+                            unsigned todo = __ballot_sync(FULL, B >= 0);
+                            while (todo) {
+                                const int src = __ffs(todo) - 1;
+                                todo &= todo - 1;
+                                const int Aw = __shfl_sync(FULL, A, src), Bw = __shfl_sync(FULL, B, src);
+                                int same = 0;
+                                if (lane == 0) same = uf_find(b_parent, Aw) == uf_find(b_parent, Bw);
+                                if (__shfl_sync(FULL, same, 0)) continue;
+                                const int u0 = __shfl_sync(FULL, a0, src), u1 = __shfl_sync(FULL, a1, src);
+                                const int w0 = __shfl_sync(FULL, b0, src), w1 = __shfl_sync(FULL, b1, src);
+                                BBox ba, bb;
+#pragma unroll
+                                for (int q = 0; q < 3; ++q) {
+                                    ba.lo[q] = __shfl_sync(FULL, box_a.lo[q], src); ba.hi[q] = __shfl_sync(FULL, box_a.hi[q], src);
+                                    bb.lo[q] = __shfl_sync(FULL, box_b.lo[q], src); bb.hi[q] = __shfl_sync(FULL, box_b.hi[q], src);
+                                }
+                                bool found = false;
+                                for (int ia0 = u0; ia0 < u1 && !found; ia0 += 32) {
+                                    const int ia_l = ia0 + (int)lane;
+                                    Pt<DIM> mine_a = {};
+                                    bool use_a = false;
+                                    if (ia_l < u1 && core[ia_l] == 1) { mine_a = load_pt<DIM>(s, ia_l); use_a = point_gap2<DIM>(mine_a, bb) <= eps2; }
+                                    const unsigned act_a = __ballot_sync(FULL, use_a);
+                                    if (!act_a) continue;
+                                    for (int jb0 = w0; jb0 < w1 && !found; jb0 += 32) {
+                                        const int jb_l = jb0 + (int)lane;
+                                        Pt<DIM> mine_b = {};
+                                        bool use_b = false;
+                                        if (jb_l < w1 && core[jb_l] == 1) { mine_b = load_pt<DIM>(s, jb_l); use_b = point_gap2<DIM>(mine_b, ba) <= eps2; }
+                                        if (!__any_sync(FULL, use_b)) continue;
+                                        unsigned act = act_a;
+                                        while (act) {
+                                            const int la = __ffs(act) - 1;
+                                            act &= act - 1;
+                                            Pt<DIM> pa;
+                                            pa.x = __shfl_sync(FULL, mine_a.x, la);
+                                            pa.y = DIM > 1 ? __shfl_sync(FULL, mine_a.y, la) : 0.f;
+                                            pa.z = DIM > 2 ? __shfl_sync(FULL, mine_a.z, la) : 0.f;
+                                            pa.t = 0.f;
+                                            bool ok = false;
+                                            if (use_b) { ++tests; ok = near_enough<DIM>(pa, mine_b, eps2); }
+                                            if (__any_sync(FULL, ok)) { found = true; break; }
+                                        }
+                                    }
+                                }
+                                if (found && lane == 0) uf_union(b_parent, Aw, Bw);
+                                if (found && (int)lane == src) root_a = uf_find_cached(b_parent, A);
                             }
                         }
                     }
-                    if (found && lane == 0) uf_union(b_parent, A, Bw);
                 }
             }
         }
@@ -1080,8 +1164,8 @@ int phase_components(rb_ctx* ctx, rb_db_plan& P, const long long* gidx, cudaStre
         RB_LAUNCH_CHECK(ctx);
         RB_TRY(rb_exclusive_scan_i32(ctx, P.b_ncore, P.core_start, P.n_cells + 1, nullptr, stream));
         const int64_t max_buckets = P.n_cells < n ? P.n_cells : n;
-        const int64_t want = rb_div_up(max_buckets * 32, DB_THREADS);
-        const unsigned ublocks = (unsigned)(want < (int64_t)ctx->sm_count * 8 ? (want > 0 ? want : 1) : (int64_t)ctx->sm_count * 8);
+        const int64_t want = rb_div_up(max_buckets, DB_THREADS);         // one lane per core bucket
+        const unsigned ublocks = (unsigned)(want < (int64_t)ctx->sm_count * 16 ? (want > 0 ? want : 1) : (int64_t)ctx->sm_count * 16);
         const int64_t want2 = rb_div_up(max_buckets, DB_THREADS);
         const unsigned mblocks = (unsigned)(want2 < (int64_t)ctx->sm_count * 8 ? (want2 > 0 ? want2 : 1) : (int64_t)ctx->sm_count * 8);
         dbt_link_time_kernel<<<mblocks, DB_THREADS, 0, stream>>>(P.g, P.cb_list, P.d_ncb, P.b_ncore, P.b_parent);

@@ -286,6 +286,12 @@ int rb_bounds_devn(rb_ctx* ctx, const float* x, const float* y, const int64_t* n
     return RB_OK;
 }
 
+extern "C" int rb_bounds_counted(rb_ctx* ctx, const float* x, const float* y, const int64_t* n_dev, int64_t n_max, float* out4,
+                                 void* stream) {
+    RB_REQUIRE(ctx && n_dev && out4 && n_max >= 0 && (n_max == 0 || (x && y)), "bad arguments");
+    return rb_bounds_devn(ctx, x, y, n_dev, n_max, out4, (cudaStream_t)stream);
+}
+
 extern "C" int rb_land_accumulate(rb_ctx* ctx, const float* x, const float* y, const float* inten, int64_t n,
                                   const double* x_edges, int n_x_edges, const double* y_edges, int n_y_edges,
                                   int32_t* count, double* isum, void* stream_) {

@@ -184,6 +184,15 @@ def bounds(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def bounds_counted(x: torch.Tensor, y: torch.Tensor, n_dev: torch.Tensor) -> torch.Tensor:
+    """:func:`bounds` over the first ``min(n_dev[0], len(x))`` points, the count being a device int64 (no sync)."""
+    ctx = context(x.device.index)
+    out = torch.empty(4, dtype=torch.float32, device=x.device)
+    check(ctx.lib.rb_bounds_counted(ctx.handle, ptr(_dev(x, torch.float32, "x")), ptr(_dev(y, torch.float32, "y")),
+                                    ptr(_dev(n_dev, torch.int64, "n_dev")), x.numel(), ptr(out), stream_ptr()), "rb_bounds_counted")
+    return out
+
+
 def land_accumulate(x, y, inten, x_edges: torch.Tensor, y_edges: torch.Tensor,
                     count: Optional[torch.Tensor] = None, isum: Optional[torch.Tensor] = None):
     """Accumulate per-cell point counts (int32) and intensity sums (float64) — T4:378-389."""
@@ -271,7 +280,10 @@ class StDbscanPhases:
     Points are SoA tensors (stride 1) or views into one row-major ``[N,D]`` tensor (stride D)."""
 
     def __init__(self, x: torch.Tensor, y: Optional[torch.Tensor], z: Optional[torch.Tensor], times: torch.Tensor,
-                 eps_space: float, eps_time: float, min_samples: int, stride: int = 1, n: Optional[int] = None):
+                 eps_space: float, eps_time: float, min_samples: int, stride: int = 1, n: Optional[int] = None,
+                 hint: Optional[Tuple[float, ...]] = None):
+        """``hint`` = ``(x_min, x_max, y_min, y_max, t_min, t_max)`` of a box that contains every point, with integer
+        times: the plan then needs no bounds pass and does not sync (``rb_stdbscan_plan_hinted``)."""
         self.ctx = context(x.device.index)
         self.n = times.numel() if n is None else int(n)
         self.device = x.device
@@ -279,9 +291,15 @@ class StDbscanPhases:
             if t is not None and (not t.is_cuda or t.dtype != torch.float32):
                 raise RadarB200Error(f"{name} must be a float32 CUDA tensor")
         if self.n > 0:
-            check(self.ctx.lib.rb_stdbscan_plan(self.ctx.handle, ptr(x), ptr(y), ptr(z), int(stride), ptr(times), self.n,
-                                                float(eps_space), float(np.float32(eps_time)), int(min_samples),
-                                                stream_ptr()), "rb_stdbscan_plan")
+            h = None
+            if hint is not None and z is None and y is not None:
+                h = _lib.StdbscanHint()
+                h.lo[0], h.hi[0], h.lo[1], h.hi[1], h.lo[3], h.hi[3] = (float(v) for v in hint)
+                h.lo[2] = h.hi[2] = 0.0
+                h.times_integer = 1
+            check(self.ctx.lib.rb_stdbscan_plan_hinted(self.ctx.handle, ptr(x), ptr(y), ptr(z), int(stride), ptr(times), self.n,
+                                                       float(eps_space), float(np.float32(eps_time)), int(min_samples),
+                                                       C.byref(h) if h is not None else None, stream_ptr()), "rb_stdbscan_plan")
 
     def cores(self) -> torch.Tensor:
         core = torch.empty(max(self.n, 1), dtype=torch.uint8, device=self.device)[:self.n]

@@ -92,44 +92,31 @@ class CudaEngine:
     def spoke_to_points(self, echo, cos_tab, sin_tab, range_res, sweep_gain, thr, stride, gpf, cap=None) -> PointBatch:
         return self.dev.spoke_to_points(echo, cos_tab, sin_tab, range_res, sweep_gain, thr, stride, gains_per_frame=gpf, cap=cap)
 
-    # -- the spoke stage of the NEXT block, launched on a side stream while the current block is in its exchange and
-    #    clustering phases (it needs no exchange and no host knowledge): software pipelining inside one rank
+    # -- the spoke stage, frame offsets and bounds enqueued together WITHOUT a sync: the caller reads the count, the
+    #    offsets and the bounds back later (with its first collective), and repeats the launch if ``cap`` was too small
     def spoke_launch(self, echo, cos_tab, sin_tab, range_res, sweep_gain, thr, stride, gpf, cap):
-        if getattr(self, "_side", None) is None:
-            self._side = torch.cuda.Stream(self.device)
-        main = torch.cuda.current_stream(self.device)
-        # outputs are allocated on the MAIN stream (they are consumed and freed there; the caching allocator can then
-        # recycle them block after block), only the launches go to the side stream
         W = echo.shape[0]
         out = (torch.empty(cap, dtype=torch.float32, device=self.device), torch.empty(cap, dtype=torch.float32, device=self.device),
                torch.empty(cap, dtype=torch.float32, device=self.device), torch.empty(cap, dtype=torch.int32, device=self.device),
                torch.empty(W + 1, dtype=torch.int64, device=self.device))
-        self._side.wait_stream(main)                      # inputs (and the fresh buffers) are ready on the main stream
-        with torch.cuda.stream(self._side):
-            self.dev.spoke_to_points_raw(echo, cos_tab, sin_tab, range_res, sweep_gain, thr, stride, cap, out=out)
-            done = torch.cuda.Event()
-            done.record(self._side)
-        return dict(outs=out, done=done, cap=cap, args=(echo, cos_tab, sin_tab, range_res, sweep_gain, thr, stride, gpf))
-
-    def spoke_finish(self, h) -> PointBatch:
-        torch.cuda.current_stream(self.device).wait_event(h["done"])
-        x, y, inten, gain, sweep_base = h["outs"]
-        n = int(sweep_base[-1].item())
-        if n > h["cap"]:                                   # capacity guess too small: redo synchronously
-            echo, cos_tab, sin_tab, range_res, sweep_gain, thr, stride, gpf = h["args"]
-            return self.spoke_to_points(echo, cos_tab, sin_tab, range_res, sweep_gain, thr, stride, gpf, cap=n)
-        gpf = h["args"][7]
-        return PointBatch(x, y, inten, gain, self.dev.frame_offsets(sweep_base, (sweep_base.numel() - 1) // gpf, gpf), n)
+        self.dev.spoke_to_points_raw(echo, cos_tab, sin_tab, range_res, sweep_gain, thr, stride, cap, out=out)
+        off = self.dev.frame_offsets(out[4], W // gpf, gpf)
+        b4 = self.dev.bounds_counted(out[0], out[1], out[4][W:])
+        return dict(outs=out, off=off, b4=b4)
 
     def bounds(self, x, y) -> torch.Tensor:
         return self.dev.bounds(x, y)
 
     def _edges(self, xe: np.ndarray, ye: np.ndarray):
+        from . import _lib
+
         key = (xe.tobytes(), ye.tobytes())
-        if getattr(self, "_edge_key", None) != key:              # one upload per distinct grid
+        cache = self.__dict__.setdefault("_edge_cache", {})       # one upload per distinct grid and block slot (stream)
+        hit = cache.get(_lib.get_slot())
+        if hit is None or hit[0] != key:
             both = torch.from_numpy(np.concatenate([xe, ye])).to(self.device)
-            self._edge_key, self._edge_dev = key, (both[:len(xe)], both[len(xe):])
-        return self._edge_dev
+            hit = cache[_lib.get_slot()] = (key, (both[:len(xe)], both[len(xe):]))
+        return hit[1]
 
     def land_accumulate(self, batch: PointBatch, xe: np.ndarray, ye: np.ndarray):
         d_xe, d_ye = self._edges(xe, ye)
@@ -143,17 +130,23 @@ class CudaEngine:
         return self.dev.land_cells(count, isum, built, persistence, min_intensity)
 
     def land_filter(self, batch: PointBatch, xe, ye, land) -> PointBatch:
+        """Enqueues the filter; the point count of the result is read later (``n`` = -1 until then)."""
         d_xe, d_ye = self._edges(xe, ye)
-        return self.dev.land_filter(batch, d_xe, d_ye, land)
+        return self.dev.land_filter(batch, d_xe, d_ye, land, sync=False)
 
     def expand_frame_times(self, frame_off, frame_ids, n):
         return self.dev.expand_frame_times(frame_off, frame_ids, n)
 
-    def phases(self, x, y, times, eps_space, eps_time, min_samples):
-        return self.dev.StDbscanPhases(x, y, None, times, eps_space, eps_time, min_samples, stride=1, n=times.numel())
+    def phases(self, x, y, times, eps_space, eps_time, min_samples, hint=None):
+        return self.dev.StDbscanPhases(x, y, None, times, eps_space, eps_time, min_samples, stride=1, n=times.numel(), hint=hint)
 
     def relabel(self, keys, table_keys, table_ids):
         return self.dev.relabel(keys, table_keys, table_ids)
+
+
+# a block that has just enqueued its spoke stage (~2 ms of GPU time for 512 frames) sits out this many scheduler
+# rounds: a constant, so the schedule stays identical on every rank
+SPOKE_SKIP = 5
 
 
 # ------------------------------------------------------------------------------------------ result
@@ -197,7 +190,8 @@ class ShardedDetection:
             self.base = DetectionPipeline(self.cfg, self.device.index)       # spoke tables + ctx for the bench
         self._cap_hint = 0
         self._gain_cache = None
-        self._prefetched = None
+        self._streams = []                 # one CUDA stream per block slot (run_blocks)
+        self._key_cap = 8192               # capacity of the component-key vector (grows on demand)
         self.profile = False               # True: synchronise and record wall-clock per stage in self.timings
         self.timings = {}
         self._t_last = None
@@ -218,14 +212,27 @@ class ShardedDetection:
     def _t(self, values, dtype) -> torch.Tensor:
         return torch.tensor(values, dtype=dtype, device=self.device)
 
-    def _all_gather_vec(self, vec: np.ndarray, dtype=torch.float64) -> np.ndarray:
-        """All-gather one small fixed-length vector per rank -> ``[world, len]`` on the host (ONE collective)."""
-        mine = torch.from_numpy(np.ascontiguousarray(vec)).to(dtype).to(self.device)
+    def _up(self, arr, dtype=None) -> torch.Tensor:
+        """Host array -> device tensor WITHOUT a stream sync: staged in pinned memory (torch's caching host
+        allocator recycles the block only after the copy has run) and copied asynchronously. A plain ``.to(device)``
+        from pageable memory waits for everything queued on the stream - a hidden sync per call."""
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+        if dtype is not None and t.dtype != dtype:
+            t = t.to(dtype)
+        if self.device.type != "cuda":
+            return t
+        pinned = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        pinned.copy_(t)
+        return pinned.to(self.device, non_blocking=True)
+
+    def _all_gather_dev(self, mine: torch.Tensor) -> torch.Tensor:
+        """All-gather one fixed-length device vector per rank -> ``[world, len]``, still on the device (ONE
+        collective, no sync); the caller yields before reading it."""
         if self.world == 1:
-            return mine.cpu().numpy()[None]
-        out = torch.empty((self.world, mine.numel()), dtype=dtype, device=self.device)
-        dist.all_gather_into_tensor(out, mine[None], group=self.group)
-        return out.cpu().numpy()
+            return mine[None]
+        out = torch.empty((self.world, mine.numel()), dtype=mine.dtype, device=self.device)
+        dist.all_gather_into_tensor(out, mine.contiguous()[None], group=self.group)
+        return out
 
     def _exchange(self, to_left: Optional[torch.Tensor], to_right: Optional[torch.Tensor],
                   n_from_left: int, n_from_right: int, dtype, width: int = 1):
@@ -249,110 +256,170 @@ class ShardedDetection:
         return left, right
 
     # ---- the path -------------------------------------------------------------------------------------
+    # The path of one block is a GENERATOR that yields right before every host read-back. Driven alone
+    # (run_device) it is a plain sequential pass. run_blocks drives several of them round-robin in ONE host
+    # thread over ONE communicator: while a block waits for the GPU, the other blocks' next phases are enqueued,
+    # so kernels, collectives and host work of different blocks overlap. Every rank follows the same
+    # deterministic schedule (the yields and the collectives of a block do not depend on local data), so the
+    # collectives are issued in the same order everywhere - unlike several communicators used concurrently,
+    # which deadlocked.
     def _gains(self, n_sweeps: int) -> torch.Tensor:
         if self._gain_cache is None or self._gain_cache.numel() != n_sweeps:
             self._gain_cache = self._t(list(self.cfg.gains) * (n_sweeps // len(self.cfg.gains)), torch.int32)
         return self._gain_cache
 
-    def prefetch(self, echo, cos_tab, sin_tab, range_res) -> None:
-        """Launch the spoke-to-point stage of the block that :meth:`run_device` will be called with NEXT, on a side
-        stream, without waiting for it: it overlaps the exchange and clustering phases of the current block.
-        Optional; engines without ``spoke_launch`` ignore it."""
-        if not hasattr(self.engine, "spoke_launch"):
-            return
-        F, G, S, E = echo.shape
-        cap = self._cap_hint or max(1, F * G * ((S * E + self.cfg.point_stride - 1) // max(self.cfg.point_stride, 1)) // 8)
-        h = self.engine.spoke_launch(echo.reshape(F * G, S, E), cos_tab, sin_tab, range_res, self._gains(F * G),
-                                     self.cfg.intensity_threshold, self.cfg.point_stride, G, cap)
-        self._prefetched = (echo.data_ptr(), tuple(echo.shape), h)
+    def _slot(self, k: int):
+        """Context of block slot ``k``: its own CUDA stream and library context (scratch, ST-DBSCAN plan)."""
+        import contextlib
+        from . import _lib
 
-    def run_blocks(self, blocks, keep: bool = True):
-        """Run a sequence of blocks ``(echo, cos_tab, sin_tab, range_res, frame_ids)`` of this rank, software
-        pipelined: while block k goes through its exchange and clustering phases, the spoke stage of block k+1
-        is already running on the side stream. Same results as calling :meth:`run_device` per block.
-        Returns the results (``keep=False``: only the last one, earlier ones are released for buffer reuse)."""
+        if self.device.type != "cuda":
+            return contextlib.nullcontext()
+        while len(self._streams) <= k:
+            self._streams.append(torch.cuda.Stream(self.device))
+
+        @contextlib.contextmanager
+        def ctx():
+            prev = _lib.set_slot(k)
+            try:
+                with torch.cuda.stream(self._streams[k]):
+                    yield
+            finally:
+                _lib.set_slot(prev)
+        return ctx()
+
+    def run_blocks(self, blocks, keep: bool = True, in_flight: int = 2):
+        """Run a sequence of blocks ``(echo, cos_tab, sin_tab, range_res, frame_ids)`` of this rank with up to
+        ``in_flight`` of them interleaved (see above). Same results as :meth:`run_device` per block. Returns the
+        results in order (``keep=False``: only the last one; earlier ones are released for buffer reuse)."""
         blocks = list(blocks)
-        out, nxt = [], None
-        for i, blk in enumerate(blocks):
-            if nxt is None:
-                self.prefetch(*blk[:4])
-                nxt = self._prefetched
-            cur, self._prefetched = nxt, None
-            nxt = None
-            if i + 1 < len(blocks):
-                self.prefetch(*blocks[i + 1][:4])              # goes out BEFORE block i's phases are enqueued
-                nxt = self._prefetched
-            self._prefetched = cur
-            res = self.run_device(*blk)
-            if keep or i == len(blocks) - 1:
-                out.append(res)
-            del res
-        return out
+        results = [None] * len(blocks)
+        active = []                                           # [index, generator, slot, rounds to skip]
+        free = list(range(max(1, in_flight)))[::-1]
+        nxt = 0
+        main = torch.cuda.current_stream(self.device) if self.device.type == "cuda" else None
+        while active or nxt < len(blocks):
+            while free and nxt < len(blocks):                 # start blocks while there is a free slot
+                k = free.pop()
+                if main is not None:
+                    with self._slot(k):
+                        torch.cuda.current_stream(self.device).wait_stream(main)
+                active.append([nxt, self._run_gen(*blocks[nxt]), k, 0])
+                nxt += 1
+            for entry in list(active):                         # one step of every active block, in order
+                i, gen, k = entry[:3]
+                if entry[3] > 0 and len(active) > 1:           # it asked to be left alone for a few rounds (its GPU
+                    entry[3] -= 1                              # phase is long): the others' steps fill the time
+                    continue
+                with self._slot(k):
+                    try:
+                        entry[3] = next(gen) or 0
+                        continue
+                    except StopIteration as fin:
+                        res = fin.value
+                    if main is not None:
+                        ev = torch.cuda.Event()
+                        ev.record(torch.cuda.current_stream(self.device))
+                        main.wait_event(ev)
+                active.remove(entry)
+                free.append(k)
+                if keep or i == len(blocks) - 1:
+                    results[i] = res
+                del res
+        return [r for r in results if r is not None]
 
     def run_device(self, echo, cos_tab, sin_tab, range_res, frame_ids: Sequence[int], cluster: bool = True) -> ShardResult:
         """``echo[F,G,S,E]`` = this rank's frames (device tensor of the engine); ``frame_ids`` their ids,
         increasing across ranks (rank r's ids are all smaller than rank r+1's)."""
+        gen = self._run_gen(echo, cos_tab, sin_tab, range_res, frame_ids, cluster)
+        while True:
+            try:
+                next(gen)
+            except StopIteration as fin:
+                return fin.value
+
+    def _run_gen(self, echo, cos_tab, sin_tab, range_res, frame_ids: Sequence[int], cluster: bool = True):
+        """One block = three host read-backs (A: point count + every rank's statistics, B: filtered offsets + every
+        rank's halo layout, C: every rank's component keys), each preceded by a ``yield``. What the collectives carry
+        is assembled ON THE DEVICE, so nothing between two read-backs waits for the GPU."""
         cfg, eng = self.cfg, self.engine
         F, G, S, E = echo.shape
         ids = np.asarray(frame_ids, dtype=np.int64)
+        sweeps = echo.reshape(F * G, S, E)
+        launch = getattr(eng, "spoke_launch", None)
+        f64 = torch.float64
         self._tick(None)
-        pf, self._prefetched = self._prefetched, None
-        if pf is not None and pf[0] == echo.data_ptr() and pf[1] == tuple(echo.shape):
-            raw = eng.spoke_finish(pf[2])
-        else:
-            raw = eng.spoke_to_points(echo.reshape(F * G, S, E), cos_tab, sin_tab, range_res, self._gains(F * G),
-                                      cfg.intensity_threshold, cfg.point_stride, G, cap=self._cap_hint or None)
+        while True:
+            if launch is not None:
+                cap = self._cap_hint or max(1, F * G * ((S * E + cfg.point_stride - 1) // max(cfg.point_stride, 1)) // 8)
+                h = launch(sweeps, cos_tab, sin_tab, range_res, self._gains(F * G), cfg.intensity_threshold, cfg.point_stride, G, cap)
+                outs, raw_off_d, b4_d = h["outs"][:4], h["off"], h["b4"]
+            else:                                              # an engine without the split launch (CPU test engine)
+                r = eng.spoke_to_points(sweeps, cos_tab, sin_tab, range_res, self._gains(F * G), cfg.intensity_threshold,
+                                        cfg.point_stride, G, cap=None)
+                cap, outs, raw_off_d = r.n, (r.x, r.y, r.inten, r.gain), r.frame_off
+                b4_d = eng.bounds(r.x[:r.n], r.y[:r.n]) if r.n > 0 else torch.zeros(4, dtype=torch.float32, device=self.device)
+            # collective 1: [frames built, points, xmin, xmax, ymin, ymax, capacity] of every rank (exact in float64)
+            stats = torch.cat([torch.count_nonzero(torch.diff(raw_off_d))[None].to(f64), raw_off_d[-1:].to(f64), b4_d.to(f64),
+                               self._up(np.array([cap], dtype=np.float64))])
+            g_stats = self._all_gather_dev(stats)
+            yield SPOKE_SKIP if launch is not None else 0
+            allv = g_stats.cpu().numpy()                       # read-back A
+            if (allv[:, 1] <= allv[:, 6]).all():
+                break
+            # some rank's capacity guess was too small (its points were cut): everybody repeats - all see the same numbers
+            self._cap_hint = int(allv[self.rank, 1] * 1.25) + 1024
+        raw_off = raw_off_d.cpu().numpy().astype(np.int64)
+        raw = PointBatch(*outs, raw_off_d, int(raw_off[-1]))
         self._cap_hint = max(self._cap_hint, int(raw.n * 1.25) + 1024)
-        self._tick("spoke")
+        self._tick("spoke+stats")
 
         # ---- land / stationary persistence filter over ALL ranks' frames --------------------------
-        # collective 1: [frames built, points, xmin, xmax, ymin, ymax] of every rank (float64 holds them exactly)
-        pts, land, edges = raw, None, None
-        if cfg.land_filter:
-            raw_off = raw.frame_off.cpu().numpy()
-            mine = np.zeros(6, dtype=np.float64)
-            mine[0], mine[1] = np.count_nonzero(np.diff(raw_off)), raw.n
+        pts, land, edges, b4 = raw, None, None, None
+        built, n_all = int(allv[:, 0].sum()), int(allv[:, 1].sum())
+        if cfg.land_filter and n_all > 0 and built > cfg.land_min_frames:
+            have = allv[allv[:, 1] > 0]
+            b4 = np.array([have[:, 2].min(), have[:, 3].max(), have[:, 4].min(), have[:, 5].max()], dtype=np.float32)
+            xe, ye = trk.grid_edges_from_bounds(b4, cfg.land_resolution)
+            count, isum = eng.land_accumulate(raw, xe, ye)
+            if self.world > 1:
+                # collective 2: counts and sums in ONE float64 all-reduce (counts < 2^53 stay exact)
+                grids = torch.stack([count.to(f64), isum])
+                dist.all_reduce(grids, op=dist.ReduceOp.SUM, group=self.group)
+                count, isum = grids[0].to(torch.int32), grids[1].contiguous()
+            land = eng.land_cells(count, isum, built, cfg.land_persistence, cfg.land_min_intensity)
             if raw.n > 0:
-                mine[2:] = eng.bounds(raw.x[:raw.n], raw.y[:raw.n]).cpu().numpy().astype(np.float64)
-            allv = self._all_gather_vec(mine)
-            built, n_all = int(allv[:, 0].sum()), int(allv[:, 1].sum())
-            if n_all > 0 and built > cfg.land_min_frames:
-                have = allv[allv[:, 1] > 0]
-                b4 = np.array([have[:, 2].min(), have[:, 3].max(), have[:, 4].min(), have[:, 5].max()], dtype=np.float32)
-                xe, ye = trk.grid_edges_from_bounds(b4, cfg.land_resolution)
-                count, isum = eng.land_accumulate(raw, xe, ye)
-                if self.world > 1:
-                    # collective 2: counts and sums in ONE float64 all-reduce (counts < 2^53 stay exact)
-                    grids = torch.stack([count.to(torch.float64), isum])
-                    dist.all_reduce(grids, op=dist.ReduceOp.SUM, group=self.group)
-                    count, isum = grids[0].to(torch.int32), grids[1].contiguous()
-                land = eng.land_cells(count, isum, built, cfg.land_persistence, cfg.land_min_intensity)
-                if raw.n > 0:
-                    pts = eng.land_filter(raw, xe, ye, land)
-                edges = (xe, ye)
+                pts = eng.land_filter(raw, xe, ye, land)       # enqueued; its point count comes with read-back B
+            edges = (xe, ye)
+        off_d = pts.frame_off
 
-        self._tick("land")
+        # collective 3: per rank [points owned, start of the last-hh-frames zone, ids and per-frame counts of the first
+        # hh and last hh frames] -> global index bases and both neighbours' halo layouts at once
+        h_t = int(math.floor(cfg.eps_time)) if cfg.eps_time >= 0 else 0
+        if cluster and self.world > 1 and h_t > F:
+            raise RadarB200Error(f"time shard of {F} frames is shorter than the eps_time halo ({h_t} frames)")
+        hh = min(h_t, F)
+        g_meta = None
+        if cluster:
+            ids_d, per = self._up(ids), torch.diff(off_d)
+            g_meta = self._all_gather_dev(torch.cat([off_d[F:F + 1], off_d[F - hh:F - hh + 1], ids_d[:hh], per[:hh],
+                                                     ids_d[F - hh:], per[F - hh:]]))
+        yield 0
+        meta = g_meta.cpu().numpy() if cluster else None       # read-back B
+        off = off_d.cpu().numpy().astype(np.int64)
+        pts.n = int(off[-1])
+        self._tick("land+layout")
         labels = torch.empty(0, dtype=torch.int32, device=self.device)
         n_clusters, halo = 0, (0, 0)
         if cluster:
-            labels, n_clusters, halo = self._cluster(pts, ids)
+            labels, n_clusters, halo = yield from self._cluster_gen(pts, ids, off, meta, hh, b4)
         return ShardResult(ids, raw, pts, labels, n_clusters, halo, land, edges)
 
-    def _cluster(self, pts: PointBatch, ids: np.ndarray):
+    def _cluster_gen(self, pts: PointBatch, ids: np.ndarray, off: np.ndarray, meta: np.ndarray, hh: int, b4):
         cfg, eng = self.cfg, self.engine
         F = len(ids)
         n_own = pts.n
-        h = int(math.floor(cfg.eps_time)) if cfg.eps_time >= 0 else 0
-        if self.world > 1 and h > F:
-            raise RadarB200Error(f"time shard of {F} frames is shorter than the eps_time halo ({h} frames)")
-        hh = min(h, F)
-        off = pts.frame_off.cpu().numpy().astype(np.int64)
         lo_end, hi_start = int(off[hh]), int(off[F - hh])          # owned points [0, lo_end) go left, [hi_start, n) right
-
-        # collective 3: per rank [points owned, start of the last-hh-frames zone, ids and per-frame counts of the
-        # first hh and last hh frames] -> global index bases and both neighbours' halo layouts at once
-        mine = np.concatenate([[n_own, hi_start], ids[:hh], np.diff(off)[:hh], ids[F - hh:], np.diff(off)[F - hh:]]).astype(np.int64)
-        meta = self._all_gather_vec(mine, torch.int64)
         bases = np.concatenate([[0], np.cumsum(meta[:, 0])])
         gbase = int(bases[self.rank])
         lids = lcnt = rids = rcnt = np.zeros(0, np.int64)
@@ -370,7 +437,6 @@ class ShardedDetection:
 
         xy = torch.stack([pts.x[:n_own], pts.y[:n_own]]) if n_own else torch.zeros((2, 0), dtype=torch.float32, device=self.device)
         xl, xr = self._exchange(xy[:, :lo_end], xy[:, hi_start:], nl, nr, torch.float32, width=2)
-        self._tick("halo")
 
         # ---- local problem: [left halo | owned | right halo], times = frame ids --------------------------
         XY = torch.cat([t for t in (xl, xy, xr) if t is not None], dim=1)
@@ -378,7 +444,7 @@ class ShardedDetection:
         all_ids = np.concatenate([lids, ids, rids]).astype(np.float32)
         all_cnt = np.concatenate([lcnt, np.diff(off), rcnt]).astype(np.int64)
         head = np.concatenate([[0], np.cumsum(all_cnt)]).astype(np.int64)
-        aux = torch.from_numpy(np.concatenate([head, all_ids.astype(np.int64)])).to(self.device)      # one upload
+        aux = self._up(np.concatenate([head, all_ids.astype(np.int64)]))                               # one upload
         loc_off = aux[:len(head)]
         times = eng.expand_frame_times(loc_off, aux[len(head):].to(torch.float32), n_loc) if n_loc else \
             torch.zeros(0, dtype=torch.float32, device=self.device)
@@ -386,11 +452,15 @@ class ShardedDetection:
         gidx[:nl] += lbase
         gidx[nl:nl + n_own] += gbase - nl
         gidx[nl + n_own:] += rbase - nl - n_own
-        self._tick("prep")
+        self._tick("halo+prep")
 
-        ph = eng.phases(X, Y, times, cfg.eps_space, cfg.eps_time, cfg.min_samples) if n_loc else None
+        # every point (own or halo) lies inside the global raw bounds and every time is one of the ids: with that
+        # hint the plan needs neither a bounds pass nor a sync
+        hint = None
+        if b4 is not None and len(all_ids) and np.array_equal(all_ids, np.rint(all_ids)):
+            hint = (float(b4[0]), float(b4[1]), float(b4[2]), float(b4[3]), float(all_ids.min()), float(all_ids.max()))
+        ph = eng.phases(X, Y, times, cfg.eps_space, cfg.eps_time, cfg.min_samples, hint=hint) if n_loc else None
         core = ph.cores() if n_loc else torch.zeros(0, dtype=torch.uint8, device=self.device)
-        self._tick("plan+cores")
         # ---- exact core flags of the halo points come from their owners ----------------------------------
         own_core = core[nl:nl + n_own]
         cl, cr = self._exchange(own_core[None, :lo_end], own_core[None, hi_start:], nl, nr, torch.uint8)
@@ -403,61 +473,46 @@ class ShardedDetection:
             key = ph.components(gidx)
         else:
             key = torch.zeros(0, dtype=torch.int64, device=self.device)
-        self._tick("core-exchange+components")
 
-        # ---- stitch on rank 0 ---------------------------------------------------------------------------------
-        # what rank 0 needs from me: the local key of every CORE point of my four boundary zones (left halo, own
+        # ---- stitch (on every rank) -----------------------------------------------------------------------------
+        # what the stitch needs from me: the local key of every CORE point of my four boundary zones (left halo, own
         # first frames, own last frames, right halo - they pair up with the neighbours' zones by position) and my
-        # distinct component keys (= keys of the points that ARE their component's smallest core).
-        # One device->host read, then collectives 4 (sizes) and 5 (packed gather).
-        if n_loc:
-            zones = ((0, nl), (nl, nl + lo_end), (nl + hi_start, nl + n_own), (nl + n_own, n_loc))
-            is_core = key >= 0
-            seg_counts = [int(c) for c in torch.stack([is_core[a:b].sum() for a, b in zones]).cpu().numpy()]
-            parts = [key[a:b][is_core[a:b]] for a, b in zones] + [key[key == gidx]]
-            flat = torch.cat(parts).cpu().numpy()
-            segs = np.split(flat, np.cumsum(seg_counts))
-            my_segs, my_keys = segs[:4], segs[4]
-        else:
-            my_segs, my_keys = [np.zeros(0, np.int64)] * 4, np.zeros(0, np.int64)
-        self._tick("select")
-        packed = np.concatenate(list(my_segs) + [my_keys]).astype(np.int64)
-        sizes = self._all_gather_vec(np.array([len(x) for x in my_segs] + [len(my_keys)], dtype=np.int64), torch.int64)
-        cap_keys = int(sizes[:, 4].sum())
-        table = np.zeros(2 + 2 * cap_keys, dtype=np.int64)
-        if self.world == 1:
-            tk, ti, ncl = stitch_components([my_segs], [my_keys])
-        else:
-            cap = int(sizes.sum(axis=1).max())
-            pad = torch.zeros(max(cap, 1), dtype=torch.int64, device=self.device)
-            pad[:len(packed)] = torch.from_numpy(packed).to(self.device)
-            bufs = [torch.empty_like(pad) for _ in range(self.world)] if self.rank == 0 else None
-            dist.gather(pad, bufs, dst=0, group=self.group)
-            self._tick("gather")
-            if self.rank == 0:
-                got = torch.stack(bufs).cpu().numpy()
-                all_segs, all_keys = [], []
-                for r in range(self.world):
-                    pieces = np.split(got[r, :int(sizes[r].sum())], np.cumsum(sizes[r])[:-1])
-                    all_segs.append(pieces[:4]); all_keys.append(pieces[4])
-                tk, ti, ncl = stitch_components(all_segs, all_keys)
-                table[0], table[1] = len(tk), ncl
-                table[2:2 + len(tk)] = tk
-                table[2 + cap_keys:2 + cap_keys + len(tk)] = ti
-            self._tick("stitch")
-            # collective 6: the key -> id table
-            t_table = torch.from_numpy(table).to(self.device)
-            dist.broadcast(t_table, src=0, group=self.group)
-            table = t_table.cpu().numpy()
-            m, ncl = int(table[0]), int(table[1])
-            tk, ti = table[2:2 + m], table[2 + cap_keys:2 + cap_keys + m].astype(np.int32)
-            self._tick("broadcast")
+        # distinct component keys (= keys of the points that ARE their component's smallest core). They are compacted
+        # on the device into a fixed-capacity vector [5 counts | keys ...]; collective 4 all-gathers it.
+        zones = ((0, nl), (nl, nl + lo_end), (nl + hi_start, nl + n_own), (nl + n_own, n_loc))
+        while True:
+            cap_k = self._key_cap
+            if n_loc:
+                is_core, is_root = key >= 0, key == gidx
+                cand = torch.cat([key[a:b] for a, b in zones] + [key])
+                take = torch.cat([is_core[a:b] for a, b in zones] + [is_root])
+                pos = torch.cumsum(take, 0) - 1
+                buf = torch.zeros(5 + cap_k + 1, dtype=torch.int64, device=self.device)
+                buf[:5] = torch.stack([is_core[a:b].sum() for a, b in zones] + [is_root.sum()])
+                buf[torch.where(take & (pos < cap_k), pos + 5, 5 + cap_k)] = cand          # the last slot takes the rest
+                vec = buf[:5 + cap_k]
+            else:
+                vec = torch.zeros(5 + cap_k, dtype=torch.int64, device=self.device)
+            g_keys = self._all_gather_dev(vec)
+            self._tick("plan..components+pack")
+            yield 0
+            got = g_keys.cpu().numpy()                         # read-back C
+            sizes = got[:, :5]
+            need = int(sizes.sum(axis=1).max())
+            if need <= cap_k:
+                break
+            self._key_cap = int(need * 1.5) + 1024             # too small somewhere: everybody repeats with more room
+        all_segs, all_keys = [], []
+        for r in range(self.world):
+            pieces = np.split(got[r, 5:5 + int(sizes[r].sum())], np.cumsum(sizes[r])[:-1])
+            all_segs.append(pieces[:4]); all_keys.append(pieces[4])
+        tk, ti, ncl = stitch_components(all_segs, all_keys)
+        self._tick("stitch")
 
         # ---- labels of the owned points -------------------------------------------------------------------------
         if n_loc == 0:
             return torch.empty(0, dtype=torch.int32, device=self.device), int(ncl), (nl, nr)
-        core_label = eng.relabel(key, torch.from_numpy(np.ascontiguousarray(tk)).to(self.device),
-                                 torch.from_numpy(np.ascontiguousarray(ti, dtype=np.int32)).to(self.device))
+        core_label = eng.relabel(key, self._up(tk, torch.int64), self._up(ti, torch.int32))
         labels = ph.assign(core_label)
         out = labels[nl:nl + n_own].contiguous()
         self._tick("relabel+assign")

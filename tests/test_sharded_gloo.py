@@ -143,13 +143,13 @@ class OracleEngine:
         new_off = np.concatenate([[0], np.cumsum([keep[off[f]:off[f + 1]].sum() for f in range(len(off) - 1)])])
         k = torch.from_numpy(keep)
         return PointBatch(batch.x[:n][k], batch.y[:n][k], batch.inten[:n][k], batch.gain[:n][k],
-                          torch.from_numpy(new_off.astype(np.int64)), int(keep.sum()))
+                          torch.from_numpy(new_off.astype(np.int64)), -1)      # count read later, like the CUDA engine
 
     def expand_frame_times(self, frame_off, frame_ids, n):
         off = frame_off.numpy()
         return torch.from_numpy(np.repeat(frame_ids.numpy(), np.diff(off)).astype(np.float32))
 
-    def phases(self, x, y, times, eps_space, eps_time, min_samples):
+    def phases(self, x, y, times, eps_space, eps_time, min_samples, hint=None):
         return OraclePhases(x, y, times, eps_space, eps_time, min_samples)
 
     def relabel(self, keys, table_keys, table_ids):
@@ -194,8 +194,15 @@ def _worker(rank, world, port, spec_kw, cfg_kw, out_dir):
         per = spec.frames // world
         lo, hi = rank * per, (spec.frames if rank == world - 1 else (rank + 1) * per)
         sd = ShardedDetection(cfg, engine=OracleEngine(spec))
+        sd._key_cap = 3                      # far too small: exercises the collective "everybody repeats" path
         res = sd.run_device(torch.from_numpy(echo[lo:hi]), None, None, None, np.arange(lo, hi))
         n = res.points.n
+        # the same block three times with two in flight (interleaved generators): identical results
+        blk = (torch.from_numpy(echo[lo:hi]), None, None, None, np.arange(lo, hi))
+        for again in sd.run_blocks([blk] * 3, in_flight=2):
+            assert torch.equal(again.labels, res.labels) and again.n_clusters == res.n_clusters
+        assert len(sd.run_blocks([blk] * 3, keep=False, in_flight=3)) == 1
+        assert sd._key_cap > 3
         np.savez(Path(out_dir) / f"rank{rank}.npz", labels=res.labels.numpy(), x=res.points.x[:n].numpy(),
                  y=res.points.y[:n].numpy(), off=res.points.frame_off.numpy(), ncl=res.n_clusters, halo=np.array(res.halo_points))
     finally:

@@ -24,6 +24,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 12
 spec = syn.SweepSpec(seed=31, frames=B * world, spokes=512, bins=1024, clutter_p=0.004)
 cfg = DetectionConfig()
 sd = ShardedDetection(cfg, rank, world, local)
+sd._cap_hint = 1000 + 7 * rank          # far too small: the first block must repeat its spoke stage on every rank
 first = rank * B
 echo = dev.synth_echo(spec, first_frame=first, n_frames=B, device=device)
 c, s, r = sd.base.spoke_tables(spec.angle_units(), spec.scale(), B, spec.bins)
@@ -45,7 +46,7 @@ if rank == 0:
         all(g["ncl"] == ref.n_clusters for g in gathered)
     print(f"sharded x{world}: {len(got_l)} points, {ref.n_clusters} clusters, halo points per rank "
           f"{[g['halo'] for g in gathered]} -> {'IDENTICAL to single GPU' if ok else 'MISMATCH'}")
-# software-pipelined blocks (next block's spoke stage prefetched on a side stream): same labels per block
+# interleaved blocks (run_blocks: two generators in flight per rank): same labels per block
 tabs = tuple(torch.from_numpy(t).to(device) for t in sd.base.spoke_tables(spec.angle_units(), spec.scale(), B, spec.bins))
 many = sd.run_blocks([(echo, *tabs, np.arange(first, first + B))] * 4)
 torch.cuda.synchronize()
