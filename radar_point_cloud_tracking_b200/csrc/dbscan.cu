@@ -485,7 +485,8 @@ __global__ void __launch_bounds__(DB_THREADS) dbt_bucket_stats_kernel(int n, con
 // list of the buckets that hold core points; b_label[b] temporarily holds the bucket's slot in the list
 __global__ void __launch_bounds__(DB_THREADS) dbt_bucket_list_kernel(int64_t n_cells, const int* __restrict__ b_ncore,
                                                                     int* __restrict__ cb_list, int* __restrict__ n_cb,
-                                                                    int* __restrict__ cb_slot, int* __restrict__ cb_bbox) {
+                                                                    int* __restrict__ cb_slot, int* __restrict__ cb_bbox,
+                                                                    int* __restrict__ b_parent) {
     int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_cells) return;
     if (b_ncore[b] > 0) {
@@ -495,7 +496,9 @@ __global__ void __launch_bounds__(DB_THREADS) dbt_bucket_list_kernel(int64_t n_c
 #pragma unroll
         for (int k = 0; k < 3; ++k) { cb_bbox[slot * 6 + k] = INT_MAX; cb_bbox[slot * 6 + 3 + k] = INT_MIN; }
     } else {
-        cb_slot[b] = -1;                                 // "no core points here" for the window walk of dbt_union_kernel
+        cb_slot[b] = -1;
+        b_parent[b] = -1;                                // "no core points here": the window walk of dbt_union_kernel reads
+                                                         // ONE word per bucket (empty / same root as mine / look closer)
     }
 }
 
@@ -606,7 +609,7 @@ __device__ __forceinline__ int uf_find_cached(int* __restrict__ parent, int a) {
 // One LANE per bucket A that holds core points (a warp = 32 consecutive entries of the core-bucket list, i.e. mostly
 // neighbouring cells): connect A to the earlier buckets (B < A) in the OTHER cells of its window. The warp walks the
 // half window row by row (a row = the SIDE buckets with the same dt, dz, dy - consecutive bucket indices): every lane
-// loads the list slots and then the parents of its row together (independent loads in flight, and neighbouring lanes
+// loads the parents of its row together (independent loads in flight, and neighbouring lanes
 // read neighbouring words), drops the buckets that already share A's root - the common case once the big components
 // have formed - and only then looks for ONE core-core pair within eps in what is left: small pairs alone, 32 lanes at
 // a time; big pairs with the whole warp. Cells at Chebyshev distance 1 come in a first pass, the far ones in a
@@ -647,7 +650,6 @@ __global__ void __launch_bounds__(DB_THREADS, DIM == 2 ? 3 : 2) dbt_union_kernel
         for (int pass = 0; pass < 2; ++pass) {
             for (int dt = -g.tr; dt <= 0; ++dt) {
                 const bool t_ok = live && c.tb + dt >= 0;
-                if (live) root_a = __ldca(b_parent + root_a);                        // one hop keeps a merged-away root fresh
                 for (int dz = -RZ; dz <= RZ; ++dz) {
                     for (int dy = -RY; dy <= RY; ++dy) {
                         // rows after the centre belong to the other half of the window (their buckets look back at A)
@@ -659,26 +661,25 @@ __global__ void __launch_bounds__(DB_THREADS, DIM == 2 ? 3 : 2) dbt_union_kernel
                         const int yy = c.cy + dy, zz = c.cz + dz;
                         const bool row_ok = t_ok && yy >= 0 && yy < g.n[1] && zz >= 0 && zz < g.n[2];
                         const int row = A + dt * per_t + dz * nxy + dy * g.n[0];     // the bucket at dx = 0
-                        // ---- list slots of the row (-1 = no core points), then the parents of the occupied buckets ----
+                        // ---- parents of the row: -1 = no core points there, A's root = same set already ----
                         unsigned m = 0;
-                        int sl[SIDE];
+                        int par[SIDE];
 #pragma unroll
                         for (int k = 0; k < SIDE; ++k) {
                             const int dx = k - R;
                             const bool far = row_far || abs(dx) > 1;
                             const bool use = row_ok && (int)far == pass && !(centre_row && dx >= 0) && !(same_cell_row && dx == 0) &&
                                              c.cx + dx >= 0 && c.cx + dx < g.n[0];
-                            sl[k] = use ? __ldg(cb_slot + row + dx) : -1;
-                            if (sl[k] >= 0) m |= 1u << k;
+                            par[k] = use ? __ldca(b_parent + row + dx) : -1;
+                            if (par[k] >= 0 && par[k] != root_a) m |= 1u << k;
                         }
                         if (!__any_sync(FULL, m != 0)) continue;
-                        int par[SIDE];
-#pragma unroll
-                        for (int k = 0; k < SIDE; ++k) par[k] = (m >> k & 1) ? __ldca(b_parent + row + (k - R)) : root_a;
+                        // a different parent: bring A's root up to date (it may have been hooked since), finish the walk of
+                        // the other bucket (and compress); par[k] = its root
+                        if (m) root_a = uf_find_cached(b_parent, root_a);
 #pragma unroll
                         for (int k = 0; k < SIDE; ++k) {
                             if (!(m >> k & 1)) continue;
-                            // parent == A's root: same set. Otherwise finish the walk (and compress); par[k] = B's root.
                             if (par[k] != root_a) par[k] = uf_find_cached(b_parent, row + (k - R));
                             if (par[k] == root_a) m &= ~(1u << k);
                         }
@@ -690,10 +691,9 @@ __global__ void __launch_bounds__(DB_THREADS, DIM == 2 ? 3 : 2) dbt_union_kernel
                             BBox box_b = {};
                             int b0 = 0, b1 = 0, rb = root_a;
                             if (B >= 0) {
-                                int slot = -1;
 #pragma unroll
-                                for (int q = 0; q < SIDE; ++q) { slot = q == k ? sl[q] : slot; rb = q == k ? par[q] : rb; }   // no register indexing
-                                box_b = load_bbox<DIM>(cb_bbox, slot);
+                                for (int q = 0; q < SIDE; ++q) rb = q == k ? par[q] : rb;          // par[k] without register indexing
+                                box_b = load_bbox<DIM>(cb_bbox, __ldg(cb_slot + B));
                                 const double gap2 = box_gap2<DIM>(box_a, box_b);
                                 ++tests;
                                 if (gap2 > eps2) {
@@ -1158,7 +1158,7 @@ int phase_components(rb_ctx* ctx, rb_db_plan& P, const long long* gidx, cudaStre
         RB_LAUNCH_CHECK(ctx);
         dbt_bucket_stats_kernel<<<blocks, DB_THREADS, 0, stream>>>(n, P.core, P.scell, P.sidx, gidx, P.b_ncore, P.b_minkey);
         RB_LAUNCH_CHECK(ctx);
-        dbt_bucket_list_kernel<<<cblocks, DB_THREADS, 0, stream>>>(P.n_cells, P.b_ncore, P.cb_list, P.d_ncb, P.cb_slot, P.cb_bbox);
+        dbt_bucket_list_kernel<<<cblocks, DB_THREADS, 0, stream>>>(P.n_cells, P.b_ncore, P.cb_list, P.d_ncb, P.cb_slot, P.cb_bbox, P.b_parent);
         RB_LAUNCH_CHECK(ctx);
         dbt_bucket_bbox_kernel<DIM><<<blocks, DB_THREADS, 0, stream>>>(s, n, P.core, P.cb_slot, P.cb_bbox);
         RB_LAUNCH_CHECK(ctx);
