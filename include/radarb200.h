@@ -284,6 +284,16 @@ int rb_detect_block(rb_ctx* ctx, const float* echo, const float* cos_tab, const 
  * Returns the number of edges (> cap: nothing written beyond cap). */
 int64_t rb_arange_edges(float lo, float hi, double step, double* out, int64_t cap);
 
+/* HOST function of the time-sharded multi-GPU path (sharded.py): global cluster numbering from the ranks' local
+ * components. keys[n_keys] = every rank's distinct local component keys (key = smallest global core-point index the rank
+ * saw in the component; duplicates allowed). pair_a/pair_b[n_pairs] = the keys under which two neighbouring ranks hold
+ * the SAME boundary core point: each pair ties two local components together. Writes the sorted distinct keys to
+ * table_keys and, per key, the final cluster id to table_ids - the id of a cluster being the rank of its smallest key
+ * among all clusters, which is the reference's numbering (first core point in index order starts cluster 0; T4:481-500,
+ * SURVEY.md N4). Returns the table size (<= cap) or a negative RB_ERR_*; *n_clusters = number of clusters. */
+int64_t rb_stitch_components(const int64_t* keys, int64_t n_keys, const int64_t* pair_a, const int64_t* pair_b,
+                             int64_t n_pairs, int64_t* table_keys, int32_t* table_ids, int64_t cap, int64_t* n_clusters);
+
 /* ---- test/bench infrastructure (not part of the reference surface) ---------------------------
  * Device twin of radar_point_cloud_tracking_b200.synthetic.synth_echo: fills echo[W][S][E] for
  * sweeps w0 .. w0+n_sweeps-1 of the data set. sweep_keys uint32[n_sweeps], clutter_thr

@@ -180,6 +180,8 @@ __device__ __forceinline__ Pt<DIM> load_pt(const Sorted& s, int i) {
     return p;
 }
 
+// (A float32 pre-test that decides all pairs outside a 4e-6 band around eps^2 was measured in round 1: the kernels
+// are bound by divergence and loads, not by the float64 arithmetic - it made dbt_count_kernel 5 % slower. Not kept.)
 template <int DIM>
 __device__ __forceinline__ bool near_enough(const Pt<DIM>& a, const Pt<DIM>& b, double eps2) {
     double d = (double)a.x - (double)b.x;                 // sklearn rdist: d += tmp*tmp, float64, no FMA
@@ -468,7 +470,7 @@ __global__ void __launch_bounds__(DB_THREADS) dbt_bucket_init_kernel(int64_t n_c
                                                                     long long* __restrict__ b_minkey, int* __restrict__ n_cb) {
     int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b == 0) *n_cb = 0;
-    if (b < n_cells) { b_ncore[b] = 0; b_parent[b] = (int)b; b_minkey[b] = KEY_NONE; }
+    if (b < n_cells) { b_ncore[b] = 0; b_minkey[b] = KEY_NONE; }            // parents: dbt_bucket_list_kernel
     if (b == n_cells) b_ncore[b] = 0;                                        // scan sentinel
 }
 
@@ -482,23 +484,59 @@ __global__ void __launch_bounds__(DB_THREADS) dbt_bucket_stats_kernel(int n, con
     atomicMin(b_minkey + b, point_key(gidx, sidx[p]));
 }
 
-// list of the buckets that hold core points; b_label[b] temporarily holds the bucket's slot in the list
+// list of the buckets that hold core points; b_label[b] temporarily holds the bucket's slot in the list.
+// A block takes LIST_PER_THREAD consecutive buckets per thread, ranks its core buckets with a block scan and reserves
+// its part of the list with ONE atomic (one atomic per bucket - even warp aggregated - serialises on the counter's
+// address at ~3.4 ns each: 88 us for the 1.1 M core buckets of a 512-frame block). The list comes out sorted inside
+// each block's range, so neighbouring list entries are neighbouring buckets - what dbt_union_kernel's lanes want.
+// Also: parent = own index for core buckets, -1 for the others (see dbt_union_kernel).
+constexpr int LIST_PER_THREAD = 8;
 __global__ void __launch_bounds__(DB_THREADS) dbt_bucket_list_kernel(int64_t n_cells, const int* __restrict__ b_ncore,
                                                                     int* __restrict__ cb_list, int* __restrict__ n_cb,
                                                                     int* __restrict__ cb_slot, int* __restrict__ cb_bbox,
                                                                     int* __restrict__ b_parent) {
-    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n_cells) return;
-    if (b_ncore[b] > 0) {
-        const int slot = atomicAdd(n_cb, 1);
-        cb_list[slot] = (int)b;
-        cb_slot[b] = slot;
+    __shared__ int warp_tot[DB_THREADS / 32];
+    __shared__ int block_base;
+    const int64_t first = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * LIST_PER_THREAD;
+    unsigned has = 0;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { cb_bbox[slot * 6 + k] = INT_MAX; cb_bbox[slot * 6 + 3 + k] = INT_MIN; }
-    } else {
-        cb_slot[b] = -1;
-        b_parent[b] = -1;                                // "no core points here": the window walk of dbt_union_kernel reads
+    for (int j = 0; j < LIST_PER_THREAD; ++j)
+        if (first + j < n_cells && b_ncore[first + j] > 0) has |= 1u << j;
+    const int mine = __popc(has);
+    // exclusive rank inside the block: warp scan, then the warp totals
+    const unsigned lane = rb_lane(), wid = threadIdx.x >> 5;
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((int)lane >= d) incl += v;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+#pragma unroll
+        for (int w = 0; w < DB_THREADS / 32; ++w) { const int t = warp_tot[w]; warp_tot[w] = run; run += t; }
+        block_base = run ? atomicAdd(n_cb, run) : 0;
+    }
+    __syncthreads();
+    int slot = block_base + warp_tot[wid] + incl - mine;
+#pragma unroll
+    for (int j = 0; j < LIST_PER_THREAD; ++j) {
+        const int64_t bkt = first + j;
+        if (bkt >= n_cells) break;
+        if (has >> j & 1) {
+            cb_list[slot] = (int)bkt;
+            cb_slot[bkt] = slot;
+            b_parent[bkt] = (int)bkt;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { cb_bbox[slot * 6 + k] = INT_MAX; cb_bbox[slot * 6 + 3 + k] = INT_MIN; }
+            ++slot;
+        } else {
+            cb_slot[bkt] = -1;
+            b_parent[bkt] = -1;                          // "no core points here": the window walk of dbt_union_kernel reads
                                                          // ONE word per bucket (empty / same root as mine / look closer)
+        }
     }
 }
 
@@ -1158,7 +1196,8 @@ int phase_components(rb_ctx* ctx, rb_db_plan& P, const long long* gidx, cudaStre
         RB_LAUNCH_CHECK(ctx);
         dbt_bucket_stats_kernel<<<blocks, DB_THREADS, 0, stream>>>(n, P.core, P.scell, P.sidx, gidx, P.b_ncore, P.b_minkey);
         RB_LAUNCH_CHECK(ctx);
-        dbt_bucket_list_kernel<<<cblocks, DB_THREADS, 0, stream>>>(P.n_cells, P.b_ncore, P.cb_list, P.d_ncb, P.cb_slot, P.cb_bbox, P.b_parent);
+        const unsigned lblocks = (unsigned)rb_div_up(P.n_cells, (int64_t)DB_THREADS * LIST_PER_THREAD);
+        dbt_bucket_list_kernel<<<lblocks, DB_THREADS, 0, stream>>>(P.n_cells, P.b_ncore, P.cb_list, P.d_ncb, P.cb_slot, P.cb_bbox, P.b_parent);
         RB_LAUNCH_CHECK(ctx);
         dbt_bucket_bbox_kernel<DIM><<<blocks, DB_THREADS, 0, stream>>>(s, n, P.core, P.cb_slot, P.cb_bbox);
         RB_LAUNCH_CHECK(ctx);

@@ -8,6 +8,9 @@
 // time between launches.
 #include <math.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 
 // np.arange(lo, fl32(hi + step), step) with np.float32 scalars lo, hi and a Python float step, as
@@ -34,6 +37,56 @@ extern "C" int64_t rb_arange_edges(float lo, float hi, double step, double* out,
         }
     }
     return len;
+}
+
+// Host side of the time-sharded path: global cluster numbering from the ranks' local components (sharded.py,
+// stitch_components). keys = every rank's distinct component keys (a key = the smallest global core index the rank saw
+// in the component), pair_a/pair_b = keys of the same boundary core point as seen by two neighbouring ranks: each pair
+// ties two local components together. Union-find over the sorted distinct keys with "smaller index wins", so a set's
+// root is its smallest key; the id of a set is the rank of that key among all roots - the reference's numbering
+// (SURVEY.md N4). Returns the number of distinct keys (table size), or a negative error code.
+extern "C" int64_t rb_stitch_components(const int64_t* keys, int64_t n_keys, const int64_t* pair_a, const int64_t* pair_b,
+                                        int64_t n_pairs, int64_t* table_keys, int32_t* table_ids, int64_t cap,
+                                        int64_t* n_clusters) {
+    if (n_keys < 0 || n_pairs < 0 || (n_keys && !keys) || (n_pairs && (!pair_a || !pair_b)) || !n_clusters) {
+        rb_set_error("rb_stitch_components: bad arguments");
+        return RB_ERR_ARG;
+    }
+    std::vector<int64_t> uniq(keys, keys + n_keys);
+    std::sort(uniq.begin(), uniq.end());
+    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+    const int64_t m = (int64_t)uniq.size();
+    *n_clusters = 0;
+    if (m > cap || (m && (!table_keys || !table_ids))) {
+        rb_set_error("rb_stitch_components: %lld distinct keys need a table of at least that size (cap = %lld)", (long long)m, (long long)cap);
+        return RB_ERR_CAPACITY;
+    }
+    std::vector<int32_t> parent((size_t)m);
+    for (int64_t i = 0; i < m; ++i) parent[(size_t)i] = (int32_t)i;
+    auto find = [&](int32_t x) {
+        while (parent[(size_t)x] != x) { parent[(size_t)x] = parent[(size_t)parent[(size_t)x]]; x = parent[(size_t)x]; }
+        return x;
+    };
+    for (int64_t p = 0; p < n_pairs; ++p) {
+        const auto ia = std::lower_bound(uniq.begin(), uniq.end(), pair_a[p]);
+        const auto ib = std::lower_bound(uniq.begin(), uniq.end(), pair_b[p]);
+        if (ia == uniq.end() || *ia != pair_a[p] || ib == uniq.end() || *ib != pair_b[p]) {
+            rb_set_error("rb_stitch_components: pair %lld names a key that no rank listed", (long long)p);
+            return RB_ERR_ARG;
+        }
+        int32_t ra = find((int32_t)(ia - uniq.begin())), rb = find((int32_t)(ib - uniq.begin()));
+        if (ra == rb) continue;
+        if (ra < rb) parent[(size_t)rb] = ra; else parent[(size_t)ra] = rb;
+    }
+    std::vector<int32_t> root_rank((size_t)m);
+    int32_t n_roots = 0;
+    for (int64_t i = 0; i < m; ++i) root_rank[(size_t)i] = parent[(size_t)i] == (int32_t)i ? n_roots++ : -1;
+    for (int64_t i = 0; i < m; ++i) {
+        table_keys[i] = uniq[(size_t)i];
+        table_ids[i] = root_rank[(size_t)find((int32_t)i)];
+    }
+    *n_clusters = n_roots;
+    return m;
 }
 
 extern "C" int rb_detect_block(rb_ctx* ctx, const float* echo, const float* cos_tab, const float* sin_tab,

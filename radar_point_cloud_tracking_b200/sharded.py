@@ -50,31 +50,29 @@ def stitch_components(seg_keys: Sequence[Sequence[np.ndarray]], keys: Sequence[n
     position: each pair ties two local components together. Returns ``(table_keys sorted, table_ids,
     n_clusters)`` where the id of a component is the rank of its smallest global core index among all
     components — the reference's numbering."""
-    from scipy.sparse import coo_matrix
-    from scipy.sparse.csgraph import connected_components
+    import ctypes as C
 
-    uniq = np.unique(np.concatenate([np.asarray(k, dtype=np.int64) for k in keys] + [np.zeros(0, np.int64)]))
-    m = len(uniq)
-    if m == 0:
-        return uniq, np.zeros(0, np.int32), 0
-    pa, pb = [np.zeros(0, np.int64)], [np.zeros(0, np.int64)]
+    from . import _lib
+
+    lib = _lib.load()
+    i64 = lambda parts: np.ascontiguousarray(np.concatenate([np.asarray(k, dtype=np.int64).ravel() for k in parts] + [np.zeros(0, np.int64)]))
+    all_keys = i64(keys)
+    pa, pb = [], []
     for r in range(len(seg_keys) - 1):
         for mine, theirs in ((seg_keys[r][2], seg_keys[r + 1][0]), (seg_keys[r][3], seg_keys[r + 1][1])):
             if len(mine) != len(theirs):
                 raise RadarB200Error("stitch: boundary zones of neighbouring ranks do not match")
-            pa.append(np.asarray(mine, dtype=np.int64)); pb.append(np.asarray(theirs, dtype=np.int64))
-    a = np.searchsorted(uniq, np.concatenate(pa))
-    b = np.searchsorted(uniq, np.concatenate(pb))
-    pair = np.unique(a * m + b)                                 # few distinct component pairs
-    a, b = pair // m, pair % m
-    graph = coo_matrix((np.ones(len(a), np.int8), (a, b)), shape=(m, m))
-    ncomp, comp = connected_components(graph, directed=False)
-    first = np.full(ncomp, m, dtype=np.int64)
-    np.minimum.at(first, comp, np.arange(m))                  # uniq is sorted: smallest node = smallest key
-    final_key = uniq[first[comp]]
-    finals = np.unique(final_key)
-    ids = np.searchsorted(finals, final_key).astype(np.int32)
-    return uniq, ids, len(finals)
+            pa.append(mine); pb.append(theirs)
+    pa, pb = i64(pa), i64(pb)
+    table_keys = np.empty(max(len(all_keys), 1), dtype=np.int64)
+    table_ids = np.empty(max(len(all_keys), 1), dtype=np.int32)
+    ncl = C.c_int64(0)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    m = lib.rb_stitch_components(ptr(all_keys), len(all_keys), ptr(pa), ptr(pb), len(pa), ptr(table_keys), ptr(table_ids),
+                                 len(table_keys), C.byref(ncl))
+    if m < 0:
+        raise RadarB200Error(f"rb_stitch_components: {lib.rb_last_error().decode()}")
+    return table_keys[:m], table_ids[:m], int(ncl.value)
 
 
 # ------------------------------------------------------------------------------------------ engines
@@ -225,6 +223,10 @@ class ShardedDetection:
         pinned.copy_(t)
         return pinned.to(self.device, non_blocking=True)
 
+    def _wait_stream(self) -> None:
+        if self.device.type == "cuda":
+            torch.cuda.current_stream(self.device).synchronize()
+
     def _all_gather_dev(self, mine: torch.Tensor) -> torch.Tensor:
         """All-gather one fixed-length device vector per rank -> ``[world, len]``, still on the device (ONE
         collective, no sync); the caller yields before reading it."""
@@ -341,7 +343,8 @@ class ShardedDetection:
     def _run_gen(self, echo, cos_tab, sin_tab, range_res, frame_ids: Sequence[int], cluster: bool = True):
         """One block = three host read-backs (A: point count + every rank's statistics, B: filtered offsets + every
         rank's halo layout, C: every rank's component keys), each preceded by a ``yield``. What the collectives carry
-        is assembled ON THE DEVICE, so nothing between two read-backs waits for the GPU."""
+        is assembled ON THE DEVICE, so nothing between two read-backs waits for the GPU - except the two places where
+        a long GPU phase is waited for BEFORE its collective is issued (see below)."""
         cfg, eng = self.cfg, self.engine
         F, G, S, E = echo.shape
         ids = np.asarray(frame_ids, dtype=np.int64)
@@ -359,11 +362,16 @@ class ShardedDetection:
                                         cfg.point_stride, G, cap=None)
                 cap, outs, raw_off_d = r.n, (r.x, r.y, r.inten, r.gain), r.frame_off
                 b4_d = eng.bounds(r.x[:r.n], r.y[:r.n]) if r.n > 0 else torch.zeros(4, dtype=torch.float32, device=self.device)
+            # The spoke stage is the long GPU phase of a block (~2 ms for 512 frames). Its collective is issued only
+            # once it has finished: all blocks' collectives share NCCL's one stream, in issue order, so a collective
+            # queued behind unfinished work holds up every other block's collectives behind it.
+            yield SPOKE_SKIP if launch is not None else 0
+            self._wait_stream()
             # collective 1: [frames built, points, xmin, xmax, ymin, ymax, capacity] of every rank (exact in float64)
             stats = torch.cat([torch.count_nonzero(torch.diff(raw_off_d))[None].to(f64), raw_off_d[-1:].to(f64), b4_d.to(f64),
                                self._up(np.array([cap], dtype=np.float64))])
             g_stats = self._all_gather_dev(stats)
-            yield SPOKE_SKIP if launch is not None else 0
+            yield 0
             allv = g_stats.cpu().numpy()                       # read-back A
             if (allv[:, 1] <= allv[:, 6]).all():
                 break
@@ -493,8 +501,10 @@ class ShardedDetection:
                 vec = buf[:5 + cap_k]
             else:
                 vec = torch.zeros(5 + cap_k, dtype=torch.int64, device=self.device)
-            g_keys = self._all_gather_dev(vec)
             self._tick("plan..components+pack")
+            yield 1                                            # the clustering kernels (~1 ms): same reasoning as for the spoke stage
+            self._wait_stream()
+            g_keys = self._all_gather_dev(vec)
             yield 0
             got = g_keys.cpu().numpy()                         # read-back C
             sizes = got[:, :5]

@@ -128,3 +128,36 @@ def test_native_arange_edges_match_numpy():
         got = dev.arange_edges(lo, hi, step)
         assert ref.dtype == np.float64 and np.array_equal(ref, got)
     assert len(dev.arange_edges(3.0, 3.0, 5.0)) == 1 and len(dev.arange_edges(0.0, 10.0, 5.0)) == 3
+
+
+def test_stitch_components_matches_a_plain_union_find():
+    """Native rb_stitch_components (host function) against a dictionary union-find, random component graphs."""
+    from radar_point_cloud_tracking_b200.sharded import stitch_components
+
+    rng = np.random.default_rng(5)
+    e = np.zeros(0, np.int64)
+    for world in (2, 3, 5):
+        # rank r sees components keyed by random global indices; neighbouring ranks share boundary points
+        keys = [np.unique(rng.integers(0, 10_000, size=rng.integers(1, 40))).astype(np.int64) for _ in range(world)]
+        segs = [[e, e, e, e] for _ in range(world)]
+        for r in range(world - 1):
+            n_last, n_first = int(rng.integers(0, 30)), int(rng.integers(0, 30))
+            segs[r][2], segs[r + 1][0] = rng.choice(keys[r], n_last), rng.choice(keys[r + 1], n_last)
+            segs[r][3], segs[r + 1][1] = rng.choice(keys[r], n_first), rng.choice(keys[r + 1], n_first)
+        tk, ti, ncl = stitch_components(segs, keys)
+        parent = {int(k): int(k) for k in np.concatenate(keys)}
+
+        def find(x):
+            while parent[x] != x:
+                x = parent[x]
+            return x
+        for r in range(world - 1):
+            for a, b in ((segs[r][2], segs[r + 1][0]), (segs[r][3], segs[r + 1][1])):
+                for u, v in zip(a.tolist(), b.tolist()):
+                    ru, rv = find(u), find(v)
+                    if ru != rv:
+                        parent[max(ru, rv)] = min(ru, rv)
+        roots = sorted({find(k) for k in parent})
+        want = {k: roots.index(find(k)) for k in parent}
+        assert list(tk) == sorted(parent) and ncl == len(roots)
+        assert [want[int(k)] for k in tk] == list(ti)

@@ -1,4 +1,3 @@
 cd /root/repo
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
-timeout 300 $TR --master-port 29542 tools/trace_sharded.py 512 2 2>&1 | tail -3
-ls -la gpurun_out/
+timeout 300 $TR --master-port 29542 tools/trace_sharded.py 512 3 2>&1 | tail -1
