@@ -40,7 +40,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=512, help="frames per rank and step (device-resident `value`)")
+    ap.add_argument("--shard-in-flight", type=int, default=2, help="N>1: blocks interleaved per rank (one host thread, one communicator)")
+    ap.add_argument("--frames-per-step", type=int, default=1024, help="frames per rank and step (device-resident `value`)")
     ap.add_argument("--e2e-frames", type=int, default=128, help="frames per rank and step of the end-to-end measurement (bounds the "
                     "pinned host buffers: 3.2 GB float32 per rank at 128)")
     ap.add_argument("--spokes", type=int, default=2048)
@@ -59,8 +60,9 @@ def parse_args():
 def load_traffic(frames_per_launch: int):
     """DRAM bytes (read + write) of the mask kernel per launch, from the committed ncu --set full capture,
     scaled from the captured launch size to this run's (the kernel's traffic is proportional to its input)."""
-    p = REPO / "profiles" / "r01_ncu_spoke_v4_traffic.json"
-    if not p.exists():
+    cands = [REPO / "profiles" / n for n in ("r01_ncu_spoke_final_traffic.json", "r01_ncu_spoke_v4_traffic.json")]
+    p = next((c for c in cands if c.exists()), None)
+    if p is None:
         return None, None
     d = json.loads(p.read_text())
     per_frame = (d["dram_bytes_read"] + d["dram_bytes_write"]) / d["frames_per_launch"]
@@ -315,7 +317,7 @@ def run_ours(args):
             ms, launches = ev0.elapsed_time(ev1), overlapped.launch_count() - l0
         else:
             if world > 1:                                   # warm every block slot (stream, library context, allocator pool)
-                pipe.run_blocks([(echo, d_c, d_s, d_r, frame_ids)] * max(args.warmup, 2 * args.streams), keep=False, in_flight=args.streams)
+                pipe.run_blocks([(echo, d_c, d_s, d_r, frame_ids)] * max(args.warmup, 2 * args.shard_in_flight), keep=False, in_flight=args.shard_in_flight)
             else:
                 for _ in range(args.warmup):
                     pipe.run_device(echo, d_c, d_s, d_r, frame_ids)
@@ -329,7 +331,7 @@ def run_ours(args):
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 c0 = clocks.mark()
                 ev0.record()
-                results = pipe.run_blocks([blk] * args.steps, keep=False, in_flight=args.streams)
+                results = pipe.run_blocks([blk] * args.steps, keep=False, in_flight=args.shard_in_flight)
                 ev1.record()
                 barrier()
                 c1 = clocks.mark()
@@ -410,7 +412,7 @@ def run_ours(args):
         "dtype": "f32 (points) / f64 (neighbour test) / i32 (labels)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "spokes": args.spokes, "bins": args.bins,
                    "gains": [40, 50, 75], "seed": args.seed, "clutter_p": args.clutter_p,
-                   "parallelism": f"time-sharded x{world}, {args.streams} blocks interleaved per rank (one communicator)" if world > 1 else f"single GPU, {args.streams if overlapped else 1} block(s) in flight",
+                   "parallelism": f"time-sharded x{world}, {args.shard_in_flight} blocks interleaved per rank (one communicator)" if world > 1 else f"single GPU, {args.streams if overlapped else 1} block(s) in flight",
                    "l2_policy": "inputs larger than L2 (echo block %.2f GB per step)" % (echo.numel() * 4 / 1e9)},
         "points_per_s": n_raw_all * args.steps / (ms * 1e-3),
         "points_per_step": {"after_stride": n_raw_all, "after_land_filter": n_pts_all, "clusters": int(pts_t[2])},

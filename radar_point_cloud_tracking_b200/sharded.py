@@ -488,6 +488,7 @@ class ShardedDetection:
         # distinct component keys (= keys of the points that ARE their component's smallest core). They are compacted
         # on the device into a fixed-capacity vector [5 counts | keys ...]; collective 4 all-gathers it.
         zones = ((0, nl), (nl, nl + lo_end), (nl + hi_start, nl + n_own), (nl + n_own, n_loc))
+        seg_end = np.cumsum([b - a for a, b in zones] + [n_loc])        # ends of the five segments in the candidate vector
         while True:
             cap_k = self._key_cap
             if n_loc:
@@ -496,7 +497,9 @@ class ShardedDetection:
                 take = torch.cat([is_core[a:b] for a, b in zones] + [is_root])
                 pos = torch.cumsum(take, 0) - 1
                 buf = torch.zeros(5 + cap_k + 1, dtype=torch.int64, device=self.device)
-                buf[:5] = torch.stack([is_core[a:b].sum() for a, b in zones] + [is_root.sum()])
+                # head of the vector: how many keys were taken up to the end of each segment (0 for a leading empty one);
+                # the receiver turns them into the five counts
+                buf[:5] = torch.where(self._up(seg_end > 0), pos[self._up(np.maximum(seg_end - 1, 0))] + 1, 0)
                 buf[torch.where(take & (pos < cap_k), pos + 5, 5 + cap_k)] = cand          # the last slot takes the rest
                 vec = buf[:5 + cap_k]
             else:
@@ -507,7 +510,7 @@ class ShardedDetection:
             g_keys = self._all_gather_dev(vec)
             yield 0
             got = g_keys.cpu().numpy()                         # read-back C
-            sizes = got[:, :5]
+            sizes = np.diff(got[:, :5], prepend=0, axis=1)
             need = int(sizes.sum(axis=1).max())
             if need <= cap_k:
                 break
