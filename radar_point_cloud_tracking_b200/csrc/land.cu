@@ -105,6 +105,7 @@ __device__ __forceinline__ AxisGuess axis_guess(const double* __restrict__ edges
 // ---- accumulate -------------------------------------------------------------------------------------
 // Privatised histogram in shared memory (int32 count + float64 sum per cell), flushed with one
 // global atomic per touched cell and block.
+constexpr int ACC_ITEMS = 8;
 __global__ void __launch_bounds__(LD_THREADS) land_accumulate_smem(const float* __restrict__ x, const float* __restrict__ y,
                                                                   const float* __restrict__ inten, int64_t n,
                                                                   GridArgs g, int32_t* __restrict__ count,
@@ -120,12 +121,28 @@ __global__ void __launch_bounds__(LD_THREADS) land_accumulate_smem(const float* 
     for (int i = threadIdx.x; i < g.nye; i += blockDim.x) s_ye[i] = g.ye[i];
     __syncthreads();
     const AxisGuess gx = axis_guess(s_xe, g.nxe), gy = axis_guess(s_ye, g.nye);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        int ix = cell_of((double)x[i], s_xe, g.nxe, g.nx, gx.e0, gx.inv_step);
-        int iy = cell_of((double)y[i], s_ye, g.nye, g.ny, gy.e0, gy.inv_step);
-        int c = ix * g.ny + iy;
-        atomicAdd(&s_cnt[c], 1);
-        atomicAdd(&s_sum[c], (double)inten[i]);
+    // A thread takes ACC_ITEMS CONSECUTIVE points: neighbours in the batch are neighbouring range bins of one spoke, so
+    // over land (where most points are, and where the atomics on a few hot cells collide) several in a row fall into
+    // the same cell and are added with one pair of atomics instead of one pair each.
+    const int64_t chunk = (int64_t)gridDim.x * blockDim.x * ACC_ITEMS;
+    for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * ACC_ITEMS; base < n; base += chunk) {
+        int cur = -1, cnt = 0;
+        double sum = 0.0;
+#pragma unroll
+        for (int j = 0; j < ACC_ITEMS; ++j) {
+            const int64_t i = base + j;
+            if (i >= n) break;
+            const int ix = cell_of((double)x[i], s_xe, g.nxe, g.nx, gx.e0, gx.inv_step);
+            const int iy = cell_of((double)y[i], s_ye, g.nye, g.ny, gy.e0, gy.inv_step);
+            const int c = ix * g.ny + iy;
+            if (c != cur) {
+                if (cnt) { atomicAdd(&s_cnt[cur], cnt); atomicAdd(&s_sum[cur], sum); }
+                cur = c; cnt = 0; sum = 0.0;
+            }
+            ++cnt;
+            sum += (double)inten[i];
+        }
+        if (cnt) { atomicAdd(&s_cnt[cur], cnt); atomicAdd(&s_sum[cur], sum); }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < cells; i += blockDim.x) {
