@@ -1,0 +1,62 @@
+"""Kernel timeline (torch.profiler) of the single-GPU overlapped pipeline at bench size: GPU busy fraction and
+kernel concurrency across the worker streams.
+
+    python tools/trace_n1.py [frames] [workers]
+"""
+import collections
+import json
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import torch
+from torch.profiler import ProfilerActivity, profile
+
+from radar_point_cloud_tracking_b200 import device as dev, synthetic as syn
+from radar_point_cloud_tracking_b200.pipeline import DetectionConfig, DetectionPipeline, OverlappedPipeline
+
+frames = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+workers = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+spec = syn.SweepSpec(seed=2025, frames=frames, clutter_p=0.003)
+d = torch.device("cuda:0")
+cfg = DetectionConfig()
+base = DetectionPipeline(cfg, 0)
+echo = dev.synth_echo(spec, device=d)
+c, s, r = base.spoke_tables(spec.angle_units(), spec.scale(), frames, spec.bins)
+tabs = [torch.from_numpy(t).to(d) for t in (c, s, r)]
+ov = OverlappedPipeline(cfg, 0, workers=workers)
+blk = ((echo, *tabs), {})
+ov.map([blk] * (2 * workers), keep=False)
+torch.cuda.synchronize()
+n_blocks = 4 * workers
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+    ov.map([blk] * n_blocks, keep=False)
+    torch.cuda.synchronize()
+Path("gpurun_out").mkdir(exist_ok=True)
+path = f"gpurun_out/n1_trace_w{workers}.json"
+prof.export_chrome_trace(path)
+ev = [e for e in json.load(open(path))["traceEvents"] if e.get("ph") == "X" and e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
+t0 = min(e["ts"] for e in ev); t1 = max(e["ts"] + e["dur"] for e in ev)
+iv = sorted((e["ts"], e["ts"] + e["dur"]) for e in ev)
+busy = 0; cs, ce = iv[0]
+for a, b in iv[1:]:
+    if a > ce: busy += ce - cs; cs, ce = a, b
+    else: ce = max(ce, b)
+busy += ce - cs
+tot = sum(e["dur"] for e in ev)
+mask = [(e["ts"], e["ts"] + e["dur"]) for e in ev if "spoke_mask" in e["name"]]
+mask_t = sum(b - a for a, b in mask)
+# time of other kernels that runs while a mask kernel is running
+ovl = 0.0
+for e in ev:
+    if "spoke_mask" in e["name"]: continue
+    a, b = e["ts"], e["ts"] + e["dur"]
+    for ma, mb in mask:
+        lo, hi = max(a, ma), min(b, mb)
+        if hi > lo: ovl += hi - lo
+print(f"{n_blocks} blocks of {frames} frames, {workers} in flight: span {(t1 - t0) / 1e3:.2f} ms = {(t1 - t0) / 1e3 / n_blocks:.3f} ms/block; "
+      f"GPU busy {100 * busy / (t1 - t0):.1f} %; kernel time {tot / 1e3 / n_blocks:.3f} ms/block of which mask {mask_t / 1e3 / n_blocks:.3f}; "
+      f"non-mask kernel time overlapping a mask kernel {ovl / 1e3 / n_blocks:.3f} ms/block")
+agg = collections.defaultdict(float)
+for e in ev: agg[e["name"].split("(")[0][-44:]] += e["dur"]
+for k, v in sorted(agg.items(), key=lambda x: -x[1])[:8]: print(f"  {v / 1e3 / n_blocks:7.3f} ms/block  {k}")
