@@ -294,6 +294,25 @@ int64_t rb_arange_edges(float lo, float hi, double step, double* out, int64_t ca
 int64_t rb_stitch_components(const int64_t* keys, int64_t n_keys, const int64_t* pair_a, const int64_t* pair_b,
                              int64_t n_pairs, int64_t* table_keys, int32_t* table_ids, int64_t cap, int64_t* n_clusters);
 
+/* ---- ingest (SURVEY section 8 f, rank 2) --------------------------------------------------------------------------
+ * One radar sweep CSV parsed on the device; replaces the numeric part of pd.read_csv in load_radar_csv
+ * (4_temporal_object_tracker.py:189-206: header row skipped, columns Status, Scale, Range, Gain, Angle,
+ * Echo_0..Echo_{E-1}, NaN echoes -> 0). text[n_bytes] = the file's bytes on the device. Outputs, for data row r
+ * (line r + 1 of the file): echo[r * E + c] = Echo_c as uint8 (feeds rb_spoke_to_points_u8 directly);
+ * row_start[r] / prefix_end[r] = byte offsets of the row's first character and of its fifth comma - the caller parses
+ * the five leading fields [row_start, prefix_end) on the host with the reference's own parser (Scale may be a decimal).
+ * info[0] = number of lines in the file (rows = info[0] - 1), info[1] = OR of RB_CSV_* bits: 0 means every echo field
+ * was empty or 1..3 digits <= 255 and every row had exactly E + 5 fields. Any other input only sets a bit; the caller
+ * then parses that file with the reference's parser, so unusual files keep the reference's exact behaviour.
+ * max_rows = capacity of echo / row_start / prefix_end in rows. Enqueues only; read info after a stream sync. */
+#define RB_CSV_NOT_INTEGER 1   /* an echo field is not 1..3 plain digits (sign, decimal point, blank, quote, ...) */
+#define RB_CSV_OUT_OF_RANGE 2  /* an echo value above 255                                                         */
+#define RB_CSV_RAGGED 4        /* a row without exactly E + 5 fields                                              */
+#define RB_CSV_BLANK_LINE 8    /* an empty line among the rows                                                    */
+#define RB_CSV_CAPACITY 16     /* more rows than max_rows                                                         */
+int rb_csv_parse_sweep(rb_ctx* ctx, const uint8_t* text, int64_t n_bytes, int n_echo_columns, int64_t max_rows,
+                       uint8_t* echo, int32_t* row_start, int32_t* prefix_end, int32_t* info, void* stream);
+
 /* ---- test/bench infrastructure (not part of the reference surface) ---------------------------
  * Device twin of radar_point_cloud_tracking_b200.synthetic.synth_echo: fills echo[W][S][E] for
  * sweeps w0 .. w0+n_sweeps-1 of the data set. sweep_keys uint32[n_sweeps], clutter_thr

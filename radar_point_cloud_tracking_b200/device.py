@@ -398,6 +398,41 @@ def detect_block(echo: torch.Tensor, cos_tab: torch.Tensor, sin_tab: torch.Tenso
     return rc, res, t
 
 
+# --------------------------------------------------------------------------------------- ingest
+CSV_STATUS_BITS = {1: "an echo field is not a plain 0..255 integer", 2: "an echo value above 255", 4: "a row without exactly E + 5 fields",
+                   8: "a blank line among the rows", 16: "more rows than expected"}
+
+
+def csv_parse_sweep(raw, n_echo_columns: int, device=None):
+    """Parse the echo columns of one sweep CSV on the device (``rb_csv_parse_sweep``; T4:189-206).
+
+    ``raw``: the file's bytes (``bytes`` / ``bytearray`` / uint8 array). Returns ``(echo_u8[S, E] device tensor,
+    row_start int32[S], prefix_end int32[S], status)``: rows ``r`` of the file start at byte ``row_start[r]`` and their
+    five leading fields end at ``prefix_end[r]`` (host arrays - the caller parses those few bytes itself);
+    ``status == 0`` means the file fitted the device grammar, otherwise (see ``CSV_STATUS_BITS``) the caller must parse
+    the file with the reference's parser and the other outputs are meaningless."""
+    buf = np.frombuffer(raw, dtype=np.uint8) if not isinstance(raw, np.ndarray) else raw
+    dev_ = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    ctx = context(dev_.index)
+    n = int(buf.size)
+    E = int(n_echo_columns)
+    max_rows = n // (E + 5) + 1                       # a row has at least E + 4 commas and a newline
+    staged = torch.empty(max(n, 1), dtype=torch.uint8, pin_memory=True)
+    staged[:n].copy_(torch.from_numpy(buf if buf.flags.writeable else buf.copy()))
+    text = staged.to(dev_, non_blocking=True)
+    echo = torch.empty((max_rows, E), dtype=torch.uint8, device=dev_)
+    offs = torch.empty((2, max_rows), dtype=torch.int32, device=dev_)
+    info = torch.empty(2, dtype=torch.int32, device=dev_)
+    check(ctx.lib.rb_csv_parse_sweep(ctx.handle, ptr(text), n, E, max_rows, ptr(echo), ptr(offs[0]), ptr(offs[1]), ptr(info),
+                                     stream_ptr()), "rb_csv_parse_sweep")
+    n_lines, status = (int(v) for v in info.cpu().numpy())         # the one sync of the call
+    rows = max(n_lines - 1, 0)
+    if status or rows == 0:
+        return echo[:0], np.zeros(0, np.int32), np.zeros(0, np.int32), status
+    host_offs = offs[:, :rows].cpu().numpy()
+    return echo[:rows], host_offs[0], host_offs[1], 0
+
+
 # --------------------------------------------------------------------------------------- synthetic input
 def synth_echo(spec, first_frame: int = 0, n_frames: Optional[int] = None, device=None,
                out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -111,6 +111,41 @@ def read_sweep_csv(path: Path, num_echo_columns: int = NUM_ECHO_COLUMNS):
     return angle, scale, np.ascontiguousarray(echo), gain
 
 
+def read_sweep_csv_device(path: Path, num_echo_columns: int = NUM_ECHO_COLUMNS):
+    """:func:`read_sweep_csv` with the echo columns parsed on the GPU (``rb_csv_parse_sweep``): same return value
+    except that ``echo`` is a uint8 DEVICE tensor ``[S, E]`` - it goes straight into the uint8 spoke-to-point kernel
+    and never exists as float32 on the host. The five leading fields of every row (a few bytes) are parsed by pandas,
+    the reference's parser, from the offsets the device returns. A file outside the device grammar (non-integer or
+    > 255 echoes, ragged rows, blank lines, quotes) is handed to :func:`read_sweep_csv` whole, so it behaves exactly
+    as in the reference."""
+    import io
+
+    import pandas as pd
+
+    path = Path(path)
+    try:
+        raw = path.read_bytes()
+    except Exception as e:  # same message as the reference (T4:194)
+        print(f"Error loading {path}: {e}")
+        return None
+    echo, row_start, prefix_end, status = dev.csv_parse_sweep(raw, num_echo_columns, _cuda())
+    if status:
+        return read_sweep_csv(path, num_echo_columns)
+    if echo.shape[0] == 0:
+        return None                                               # header only / empty: df.empty (T4:197-198)
+    lead = b"\n".join(raw[a:b] for a, b in zip(row_start.tolist(), prefix_end.tolist()))
+    try:
+        df = pd.read_csv(io.BytesIO(lead), header=None, names=["Status", "Scale", "Range", "Gain", "Angle"], engine="c")
+        gain = int(df["Gain"].iloc[0])
+        angle = df["Angle"].to_numpy(np.float32)
+        scale = df["Scale"].to_numpy(np.float32)
+    except Exception:
+        return read_sweep_csv(path, num_echo_columns)              # let the reference's parser decide (and report)
+    if len(df) != echo.shape[0]:
+        return read_sweep_csv(path, num_echo_columns)
+    return angle, scale, echo, gain
+
+
 def sweep_tables(angle_units: np.ndarray, scale: np.ndarray, num_bins: int, angle_scale: float = ANGLE_SCALE
                  ) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """Per-spoke ``cos``, ``sin`` and range resolution with the reference's own numpy expressions
@@ -129,17 +164,20 @@ def _points_from_sweeps(sweeps: Sequence[Tuple[np.ndarray, np.ndarray, np.ndarra
     out: List[Tuple[np.ndarray, np.ndarray, np.ndarray]] = [None] * len(sweeps)      # type: ignore
     by_shape: Dict[Tuple[int, int], List[int]] = defaultdict(list)
     for i, (_, _, echo, _) in enumerate(sweeps):
-        by_shape[echo.shape].append(i)
+        by_shape[tuple(echo.shape)].append(i)
     for (S, E), idxs in by_shape.items():
         if S == 0 or E == 0:
             for i in idxs:
                 out[i] = (np.array([], np.float32), np.array([], np.float32), np.array([], np.float32))
             continue
-        stacked = np.stack([sweeps[i][2] for i in idxs])
-        # real echoes are 8-bit (PIPELINE_DOCUMENTATION.txt:47): when the parsed values are exactly 0..255 integers
-        # they travel as uint8 - a quarter of the PCIe bytes, identical points (rb_spoke_to_points_u8)
-        as_u8 = stacked.astype(np.uint8)
-        echo = torch.from_numpy(as_u8 if np.array_equal(as_u8, stacked) else stacked).to(d)
+        if all(isinstance(sweeps[i][2], torch.Tensor) for i in idxs):
+            echo = torch.stack([sweeps[i][2] for i in idxs])                  # parsed on the device (uint8), already there
+        else:
+            stacked = np.stack([sweeps[i][2].cpu().numpy() if isinstance(sweeps[i][2], torch.Tensor) else sweeps[i][2] for i in idxs])
+            # real echoes are 8-bit (PIPELINE_DOCUMENTATION.txt:47): when the parsed values are exactly 0..255 integers
+            # they travel as uint8 - a quarter of the PCIe bytes, identical points (rb_spoke_to_points_u8)
+            as_u8 = stacked.astype(np.uint8)
+            echo = torch.from_numpy(as_u8 if np.array_equal(as_u8, stacked) else stacked).to(d)
         cs, sn, rs = sweep_tables(np.stack([sweeps[i][0] for i in idxs]), np.stack([sweeps[i][1] for i in idxs]), E)
         gains = torch.tensor([sweeps[i][3] for i in idxs], dtype=torch.int32, device=d)
         batch = dev.spoke_to_points(echo, torch.from_numpy(cs).to(d), torch.from_numpy(sn).to(d),
@@ -156,7 +194,7 @@ def load_radar_csv(path: Path, _cfg=None) -> Tuple[np.ndarray, np.ndarray, np.nd
     """Load a radar CSV and convert to Cartesian. Returns ``(x, y, intensity, gain)`` (T4:184-232).
     Threshold and stride are the module globals, exactly as in the reference."""
     cfg = _cfg or _module_config()
-    sweep = read_sweep_csv(Path(path), cfg.NUM_ECHO_COLUMNS)
+    sweep = read_sweep_csv_device(Path(path), cfg.NUM_ECHO_COLUMNS)
     if sweep is None:
         return np.array([]), np.array([]), np.array([]), 0
     angle, scale, echo, gain = sweep
@@ -176,7 +214,7 @@ def build_frame(frame_files: Dict[int, Path], frame_id: int, _cfg=None, _frame_c
         path = Path(path)
         if first_ts is None:
             first_ts, first_ts_ms = parse_timestamp(path.name)
-        sweep = read_sweep_csv(path, cfg.NUM_ECHO_COLUMNS)
+        sweep = read_sweep_csv_device(path, cfg.NUM_ECHO_COLUMNS)
         if sweep is None:
             continue
         angle, scale, echo, _ = sweep
