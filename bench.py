@@ -354,6 +354,7 @@ def run_ours(args):
         pipe.run_device(echo, d_c, d_s, d_r, frame_ids)
         split.append([ctx.info(k) * 1e-6 for k in ("spoke_mask_ns", "spoke_offsets_ns", "spoke_emit_ns")])
     ctx.set_option("spoke_profile", 0)
+    st = dev.stdbscan_stats(device.index)              # counters of a device-resident block of the timed size (not of the e2e runs)
     mask_ms, offs_ms, emit_ms = (sum(r[i] for r in split) / len(split) for i in range(3))
     achieved = echo_bytes / (mask_ms * 1e-3) / 1e9 if mask_ms > 0 else 0.0
     spoke_ms_mean = mask_ms + offs_ms + emit_ms                               # first event to last event of the stage
@@ -405,7 +406,6 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    st = dev.stdbscan_stats(device.index)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
