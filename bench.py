@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--shard-in-flight", type=int, default=2, help="N>1: blocks interleaved per rank (one host thread, one communicator)")
+    ap.add_argument("--shard-in-flight", type=int, default=3, help="N>1: blocks interleaved per rank (one host thread, one communicator)")
     ap.add_argument("--frames-per-step", type=int, default=1024, help="frames per rank and step (device-resident `value`)")
     ap.add_argument("--e2e-frames", type=int, default=128, help="frames per rank and step of the end-to-end measurement (bounds the "
                     "pinned host buffers: 3.2 GB float32 per rank at 128)")
