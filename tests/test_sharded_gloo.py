@@ -244,3 +244,55 @@ def test_stitch_components_known_answer():
     assert list(tk) == [5, 38, 40, 90] and list(ti) == [0, 1, 1, 2] and n == 3
     tk, ti, n = stitch_components([[e, e, e, e]], [e])
     assert len(tk) == 0 and n == 0
+
+
+def _worker_sparse(rank, world, port, mode, out_dir):
+    """A rank without any points (mode 'one_empty') / no points anywhere (mode 'all_empty')."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        spec = syn.SweepSpec(**SPEC)
+        cfg = DetectionConfig(land_filter=False)
+        echo = syn.synth_echo(spec)
+        per = spec.frames // world
+        lo, hi = rank * per, (spec.frames if rank == world - 1 else (rank + 1) * per)
+        mine = echo[lo:hi].copy()
+        if mode == "all_empty" or rank == 1:
+            mine[:] = 0.0                                   # nothing above the threshold on this rank
+        sd = ShardedDetection(cfg, engine=OracleEngine(spec))
+        res = sd.run_device(torch.from_numpy(mine), None, None, None, np.arange(lo, hi))
+        many = sd.run_blocks([(torch.from_numpy(mine), None, None, None, np.arange(lo, hi))] * 2, in_flight=2)
+        assert all(torch.equal(m.labels, res.labels) and m.n_clusters == res.n_clusters for m in many)
+        np.savez(Path(out_dir) / f"rank{rank}.npz", labels=res.labels.numpy(), n=res.points.n, ncl=res.n_clusters)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["one_empty", "all_empty"])
+def test_sharded_with_empty_ranks(tmp_path, mode):
+    """Ranks without points must walk through the same collectives as the others (no hang, right labels)."""
+    world = 3
+    spec = syn.SweepSpec(**SPEC)
+    cfg = DetectionConfig(land_filter=False)
+    echo = syn.synth_echo(spec)
+    per = spec.frames // world
+    if mode == "all_empty":
+        echo[:] = 0.0
+    else:
+        echo[per:2 * per] = 0.0                             # rank 1's frames
+    ang, scale = spec.angle_units(), spec.scale()
+    frames = []
+    for f in range(spec.frames):
+        per_gain = {g: O.sweep_to_points(echo[f, gi], ang, scale, cfg.intensity_threshold, cfg.point_stride) for gi, g in enumerate(spec.gains)}
+        fused = O.fuse_concat(per_gain)
+        frames.append(fused[0] if fused is not None else np.zeros((0, 3), np.float32))
+    pts = np.concatenate(frames)
+    fid = np.concatenate([np.full(len(p), i) for i, p in enumerate(frames)]).astype(np.float32)
+    want = st_dbscan_c(pts[:, :2], fid, cfg.eps_space, cfg.eps_time, cfg.min_samples)[0] if len(pts) else np.zeros(0, np.int32)
+    mp.spawn(_worker_sparse, args=(world, _free_port(), mode, str(tmp_path)), nprocs=world, join=True)
+    got = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    assert np.array_equal(np.concatenate([g["labels"] for g in got]), want)
+    assert {int(g["ncl"]) for g in got} == {int(want.max()) + 1 if len(want) and want.max() >= 0 else 0}
+    if mode == "one_empty":
+        assert int(got[1]["n"]) == 0 and want.max() >= 1
