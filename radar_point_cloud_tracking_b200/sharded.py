@@ -4,17 +4,22 @@
 Rank r owns a contiguous block of frames. Spoke-to-point is embarrassingly parallel; the land filter
 needs two tiny reductions; ST-DBSCAN couples frame f only to frames within ``eps_time``, so every rank
 clusters its own frames plus a ``floor(eps_time)``-frame halo from each neighbour and the cluster ids are
-stitched on rank 0:
+stitched from the ranks' component keys. Per block (details and measurements: DESIGN.md section 6):
 
-1. ``all_reduce(MIN)`` of ``[xmin, -xmax, ymin, -ymax]``            -> identical ``np.arange`` edges everywhere
-2. ``all_reduce(SUM)`` of the per-cell point counts / intensity sums -> identical land mask everywhere
-3. neighbour send/recv of the boundary frames' filtered points (x, y) -> exact core flags of OWNED points
-4. neighbour send/recv of those points' core flags (1 B/point)        -> exact core flags of HALO points
-5. components over owned + halo cores, keyed by GLOBAL point index; gather of
-   (global index, local component key) of every boundary-zone core point to rank 0, union of the keys
-   that share a point, canonical numbering (rank of the smallest core index, exactly the reference's),
-   ``broadcast`` of the key -> id table
-6. ``rb_relabel`` + border assignment (all neighbours of an owned point are present locally)
+1. ``all_gather`` of ``[frames built, points, x/y bounds, capacity]``   -> identical ``np.arange`` edges everywhere
+2. ``all_reduce(SUM)`` of the per-cell point counts / intensity sums    -> identical land mask everywhere
+3. ``all_gather`` of the ranks' halo layouts (points owned, ids and per-frame counts of the boundary frames)
+4. neighbour send/recv of the boundary frames' filtered points (x, y)   -> exact core flags of OWNED points
+5. neighbour send/recv of those points' core flags (1 B/point)          -> exact core flags of HALO points
+6. components over owned + halo cores, keyed by GLOBAL point index; ``all_gather`` of the local component key of
+   every boundary-zone core point and of every rank's distinct keys; EVERY rank unions the keys that share a point
+   and numbers the components by their smallest core index - exactly the reference's numbering
+   (``rb_stitch_components``)
+7. ``rb_relabel`` + border assignment (all neighbours of an owned point are present locally)
+
+What the collectives carry is assembled on the device; a block reads back to the host three times. A block is a
+generator that yields before each read-back, so one host thread can interleave several blocks over one
+communicator (:meth:`ShardedDetection.run_blocks`).
 
 The result equals the single-GPU labels of the concatenated recording, id for id.
 

@@ -3,7 +3,7 @@
 The numeric stages are played by an ORACLE-backed engine (numpy / scipy restatement, test
 infrastructure), so what is under test is exactly the part of ``sharded.py`` that has no kernel:
 the bounds / grid reductions, the ``floor(eps_time)``-frame halo exchange, the core-flag exchange,
-the component stitching on rank 0 and the canonical global numbering. The result must equal the
+the component stitching (on every rank) and the canonical global numbering. The result must equal the
 single-process oracle on the concatenated recording, label for label.
 """
 from __future__ import annotations
