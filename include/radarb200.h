@@ -313,6 +313,14 @@ int64_t rb_stitch_components(const int64_t* keys, int64_t n_keys, const int64_t*
 int rb_csv_parse_sweep(rb_ctx* ctx, const uint8_t* text, int64_t n_bytes, int n_echo_columns, int64_t max_rows,
                        uint8_t* echo, int32_t* row_start, int32_t* prefix_end, int32_t* info, void* stream);
 
+/* ---- PLY output (SURVEY section 8 f, rank 4) ------------------------------------------------------------------------
+ * HOST function: appends the vertex lines of an ASCII PLY to the file at `path` - the bytes that
+ * np.savetxt(fh, data, fmt="%.4f %.4f %.4f %d %d %d") writes in write_ply_fast (5_gain_fusion_ply_builder.py:370-403;
+ * identical to write_ply's per-point loop T5:345-367 and to the ASCII branch of
+ * PointCloudWorkF/stdbscan_denoising_pipeline.py:828-851) for float32 coordinates and uint8 colours rgb[n][3].
+ * All pointers are host pointers. The header is the caller's business. */
+int rb_ply_append_ascii(const char* path, const float* x, const float* y, const float* z, const uint8_t* rgb, int64_t n);
+
 /* ---- test/bench infrastructure (not part of the reference surface) ---------------------------
  * Device twin of radar_point_cloud_tracking_b200.synthetic.synth_echo: fills echo[W][S][E] for
  * sweeps w0 .. w0+n_sweeps-1 of the data set. sweep_keys uint32[n_sweeps], clutter_thr

@@ -86,6 +86,7 @@ SIGNATURES = {
     "rb_arange_edges": (c_i64, [c_f32, c_f32, c_f64, c_vp, c_i64]),
     "rb_stitch_components": (c_i64, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
     "rb_csv_parse_sweep": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "rb_ply_append_ascii": (c_i32, [C.c_char_p, c_vp, c_vp, c_vp, c_vp, c_i64]),
     "rb_synth_echo": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "rb_set_option": (c_i32, [c_vp, C.c_char_p, c_i64]),
     "rb_get_info": (c_i64, [c_vp, C.c_char_p]),
