@@ -296,3 +296,33 @@ def test_sharded_with_empty_ranks(tmp_path, mode):
     assert {int(g["ncl"]) for g in got} == {int(want.max()) + 1 if len(want) and want.max() >= 0 else 0}
     if mode == "one_empty":
         assert int(got[1]["n"]) == 0 and want.max() >= 1
+
+
+def test_run_blocks_schedule_is_deterministic_round_robin_with_skips():
+    """The interleaving of blocks depends only on what the generators yield (constants), never on timing: that is what
+    lets every rank issue its collectives in the same order. Scripted generators record the order of their steps."""
+    spec = syn.SweepSpec(**SPEC)
+    sd = ShardedDetection(DetectionConfig(), rank=0, world=1, engine=OracleEngine(spec))
+    trace = []
+
+    def scripted(name, yields):
+        def gen(*_):
+            for step, y in enumerate(yields):
+                trace.append((name, step))
+                yield y
+            trace.append((name, "done"))
+            return name
+        return gen
+
+    scripts = {"A": [3, 0, 0], "B": [0, 0], "C": [0]}
+    order = iter(scripts)
+    sd._run_gen = lambda *a: scripted(n := next(order), scripts[n])()
+    out = sd.run_blocks([("A",), ("B",), ("C",)], in_flight=2)
+    assert out == ["A", "B", "C"]                                   # results in block order
+    # A steps once and sits out 3 rounds while B runs to its end; C takes B's slot; then A and C alternate
+    assert trace == [("A", 0), ("B", 0), ("B", 1), ("B", "done"), ("C", 0), ("A", 1), ("C", "done"), ("A", 2), ("A", "done")]
+    # a block alone never waits for its own skip count
+    trace.clear()
+    order = iter(["A"])
+    assert sd.run_blocks([("A",)], in_flight=2) == ["A"]
+    assert trace == [("A", 0), ("A", 1), ("A", 2), ("A", "done")]
