@@ -431,7 +431,10 @@ def run_ours(args):
                                        "library on the launch stream; bytes = echo + spoke tables + 16 B per kept point"}},
         "stdbscan": {"pair_tests_per_step": st["pair_tests_count"] + st["pair_tests_union"] + st["pair_tests_border"],
                      "pair_tests": [st["pair_tests_count"], st["pair_tests_union"], st["pair_tests_border"]], "tight": st["tight"],
-                     "cells": st["n_cells"], "dims": st["dims"], "time_radius": st["time_radius"]},
+                     "cells": st["n_cells"], "dims": st["dims"], "time_radius": st["time_radius"],
+                     "pair_tests_per_s": (st["pair_tests_count"] + st["pair_tests_union"] + st["pair_tests_border"]) * (value / B),
+                     "note": "counters of one device-resident block on rank 0 (neighbour-count / union / border kernels); per second = "
+                             "per block x blocks per second of the whole job"},
         "gpu_launches": launches,
         "clocks": clocks.summary(c0, c1),
     }
