@@ -216,7 +216,8 @@ def _free_port():
 
 
 @pytest.mark.parametrize("world,cfg_kw", [(2, {}), (3, {"eps_time": 1.0, "min_samples": 8}),
-                                          (2, {"eps_time": 0.5, "land_filter": False})])
+                                          (2, {"eps_time": 0.5, "land_filter": False}),
+                                          (4, {"eps_time": 3.0, "min_samples": 10})])      # shard = halo = 3 frames
 def test_sharded_equals_single_process(tmp_path, world, cfg_kw):
     cfg = DetectionConfig(**cfg_kw)
     spec = syn.SweepSpec(**SPEC)
