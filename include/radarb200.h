@@ -305,7 +305,8 @@ int64_t rb_stitch_components(const int64_t* keys, int64_t n_keys, const int64_t*
  * was empty or 1..3 digits <= 255 and every row had exactly E + 5 fields. Any other input only sets a bit; the caller
  * then parses that file with the reference's parser, so unusual files keep the reference's exact behaviour.
  * max_rows = capacity of echo / row_start / prefix_end in rows. Enqueues only; read info after a stream sync. */
-#define RB_CSV_NOT_INTEGER 1   /* an echo field is not 1..3 plain digits (sign, decimal point, blank, quote, ...) */
+#define RB_CSV_NOT_INTEGER 1   /* an echo field is not 1..3 plain digits (sign, decimal point, blank, quote, ...), or a
+                                  carriage return that is not followed by a line feed (pandas ends a line there)   */
 #define RB_CSV_OUT_OF_RANGE 2  /* an echo value above 255                                                         */
 #define RB_CSV_RAGGED 4        /* a row without exactly E + 5 fields                                              */
 #define RB_CSV_BLANK_LINE 8    /* an empty line among the rows                                                    */

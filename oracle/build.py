@@ -17,7 +17,7 @@ LIB = HERE / "liboracle_stdbscan.so"
 def build(force: bool = False) -> Path:
     if LIB.exists() and not force and LIB.stat().st_mtime >= SRC.stat().st_mtime:
         return LIB
-    cmd = ["gcc", "-O2", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC",
+    cmd = ["gcc", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-shared", "-fPIC",
            "-o", str(LIB), str(SRC), "-lm"]
     subprocess.run(cmd, check=True)
     return LIB

@@ -13,7 +13,16 @@ Drop-in for the hot functions of ``4_temporal_object_tracker.py`` / ``radar_pipe
 All compute is hand-written CUDA behind the C ABI of ``include/radarb200.h``
 (``libradarb200.so``); there is no CPU fallback.
 """
+import numpy as _np
+
 from ._lib import RadarB200Error, load as load_library  # noqa: F401
+
+# The library restates numpy >= 2 scalar promotion (NEP 50: `np.float32 + python float` stays float32) where the
+# reference computes its grid edges (rb_arange_edges, T4:372-373). Under numpy 1.x the reference itself would produce
+# different edges, and the two could disagree silently - refuse to load instead.
+if int(_np.__version__.split(".")[0]) < 2:
+    raise ImportError(f"radar_point_cloud_tracking_b200 needs numpy >= 2 (found {_np.__version__}): the land-grid edges "
+                      "follow numpy 2's scalar promotion rules")
 
 __all__ = ["RadarB200Error", "load_library"]
 __version__ = "0.1.0"

@@ -38,16 +38,39 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
+    """One nvcc process per source file (in parallel, objects under ``build/``; only stale ones are recompiled), then
+    one link. ``build.log`` (git-ignored) keeps the ptxas -v output of the files compiled last."""
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc_path(), "-shared", *NVCC_FLAGS, "-I", str(INCLUDE), "-I", str(CSRC),
-           "-o", str(LIB), *[str(CSRC / s) for s in SOURCES]]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    log = res.stdout + res.stderr
-    (PKG / "build.log").write_text(" ".join(cmd) + "\n" + log)
-    if res.returncode != 0:
+    from concurrent.futures import ThreadPoolExecutor
+
+    obj_dir = PKG / "build"
+    obj_dir.mkdir(exist_ok=True)
+    common = [CSRC / "common.cuh", INCLUDE / "radarb200.h", Path(__file__)]
+    nvcc = nvcc_path()
+
+    def compile_one(name: str):
+        src, obj = CSRC / name, obj_dir / (name + ".o")
+        if not force and obj.exists() and all(obj.stat().st_mtime >= d.stat().st_mtime for d in [src, *common]):
+            return name, 0, ""
+        cmd = [nvcc, "-c", *NVCC_FLAGS, "-I", str(INCLUDE), "-I", str(CSRC), "-o", str(obj), str(src)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        return name, res.returncode, " ".join(cmd) + "\n" + res.stdout + res.stderr
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    log = "".join(r[2] for r in results)
+    failed = [r[0] for r in results if r[1] != 0]
+    if not failed:
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *[str(obj_dir / (s + ".o")) for s in SOURCES]]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        log += " ".join(cmd) + "\n" + res.stdout + res.stderr
+        if res.returncode != 0:
+            failed = ["link"]
+    (PKG / "build.log").write_text(log)
+    if failed:
         sys.stderr.write(log)
-        raise RuntimeError("nvcc failed building libradarb200.so")
+        raise RuntimeError(f"nvcc failed building libradarb200.so ({', '.join(failed)})")
     if verbose:
         print(log)
     return LIB

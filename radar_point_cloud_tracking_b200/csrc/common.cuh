@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <utility>
 #include <vector>
 
 #include "radarb200.h"
@@ -64,6 +65,11 @@ struct rb_ctx {
     int opt_spoke_mask_variant = 0;  // 0 = auto, 1 = register-staged mask kernel, 2 = require the TMA-staged one
     int spoke_last_variant = 0;      // mask kernel the last rb_spoke_to_points launched (1 / 2)
     int opt_spoke_profile = 0;       // 1: record events around the three spoke-to-point kernels
+    int opt_spoke_ring = 0;          // TMA ring of the mask kernel: 0 = 64 KiB x 3, 1 = 32 KiB x 4, 2 = 32 KiB x 3, 3 = 64 KiB x 2, 4 = 16 KiB x 4
+    int opt_spoke_l2_hint = 0;       // 1: the mask kernel's bulk loads carry an L2 evict-first policy
+    int opt_carveout = -1;           // >= 0: every launch asks for this shared-memory carve-out (percent), see rb_launch
+    unsigned attr_spoke_mask = 0;    // per-context "function attribute set" flags (a context = one device)
+    bool attr_land = false;
     cudaEvent_t spoke_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -105,6 +111,31 @@ int rb_scratch_get(rb_ctx* ctx, rb_slot slot, size_t bytes, void** out);
     } while (0)
 
 static inline int64_t rb_div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Every kernel of the library is launched through here. With the "carveout" option set, each launch carries the same
+// preferred shared-memory carve-out: an SM runs CTAs of different kernels side by side only when they agree on its
+// L1 / shared-memory split, so this is what lets the latency-bound clustering kernels of one block be resident next to
+// the HBM-bound mask kernel of the next (blocks in flight on different streams).
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t rb_launch(rb_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                             Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    if (ctx->opt_carveout >= 0) {
+        attr[0].id = cudaLaunchAttributePreferredSharedMemoryCarveout;
+        attr[0].val.sharedMemCarveout = (unsigned)ctx->opt_carveout;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif
 
 // ---- device helpers ---------------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -26,6 +26,11 @@ extern "C" int rb_create(int device, rb_ctx** out) {
         return RB_ERR_CUDA;
     }
     if (device < 0 || device >= n) { rb_set_error("rb_create: bad device %d of %d", device, n); return RB_ERR_ARG; }
+    // the caller's current device is left as it was: every entry point works on the device of the buffers / stream it is
+    // given (one process per GPU is the norm; a caller that drives several devices sets the current device itself)
+    int prev = -1;
+    RB_CUDA(cudaGetDevice(&prev));
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev == device ? -1 : prev};
     RB_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     RB_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -86,6 +91,17 @@ extern "C" int rb_set_option(rb_ctx* ctx, const char* name, int64_t value) {
         ctx->opt_spoke_mask_variant = (int)value;
         return RB_OK;
     }
+    if (!strcmp(name, "spoke_ring")) {
+        RB_REQUIRE(value >= 0 && value <= 4, "spoke_ring: 0 = 64 KiB x 3, 1 = 32 KiB x 4, 2 = 32 KiB x 3, 3 = 64 KiB x 2, 4 = 16 KiB x 4");
+        ctx->opt_spoke_ring = (int)value;
+        return RB_OK;
+    }
+    if (!strcmp(name, "spoke_l2_hint")) { ctx->opt_spoke_l2_hint = value != 0; return RB_OK; }
+    if (!strcmp(name, "carveout")) {
+        RB_REQUIRE(value >= -1 && value <= 100, "carveout: -1 = the driver's choice per kernel, 0..100 = percent of the SM's shared memory");
+        ctx->opt_carveout = (int)value;
+        return RB_OK;
+    }
     rb_set_error("rb_set_option: unknown option '%s'", name);
     return RB_ERR_ARG;
 }
@@ -97,6 +113,9 @@ extern "C" int64_t rb_get_info(rb_ctx* ctx, const char* name) {
     if (!strcmp(name, "spoke_mask_variant")) return ctx->opt_spoke_mask_variant;
     if (!strcmp(name, "dbscan_mode")) return ctx->opt_dbscan_mode;
     if (!strcmp(name, "spoke_last_variant")) return ctx->spoke_last_variant;
+    if (!strcmp(name, "spoke_ring")) return ctx->opt_spoke_ring;
+    if (!strcmp(name, "spoke_l2_hint")) return ctx->opt_spoke_l2_hint;
+    if (!strcmp(name, "carveout")) return ctx->opt_carveout;
     // device time of the last profiled rb_spoke_to_points, per kernel, in nanoseconds (syncs on its last event)
     int k = !strcmp(name, "spoke_mask_ns") ? 0 : !strcmp(name, "spoke_offsets_ns") ? 1 : !strcmp(name, "spoke_emit_ns") ? 2 : -1;
     if (k >= 0) {
@@ -174,7 +193,7 @@ __device__ __forceinline__ int block_excl_scan(int v, int* total) {
     return excl;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums(const int32_t* __restrict__ in, int64_t n,
+__global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums(const int32_t* in, int64_t n,
                                                                int32_t* __restrict__ sums) {
     int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
     int s = 0;
@@ -211,7 +230,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_sums_serial(int32_t* __rest
     if (threadIdx.x == 0 && total_out) *total_out = carry;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) scan_apply(const int32_t* __restrict__ in, int32_t* __restrict__ out,
+// in and out may be the SAME array (the bucket table is scanned in place): no __restrict__ on them - every thread reads
+// its own items before it writes them
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply(const int32_t* in, int32_t* out,
                                                           int64_t n, const int32_t* __restrict__ sums) {
     int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
     int v[SCAN_ITEMS];
@@ -239,11 +260,11 @@ int rb_exclusive_scan_i32(rb_ctx* ctx, const int32_t* in, int32_t* out, int64_t 
     int64_t nb = rb_div_up(n, SCAN_TILE);
     void* sums;
     RB_TRY(rb_scratch_get(ctx, RB_S_BLOCKSUM, sizeof(int32_t) * (size_t)nb, &sums));
-    scan_block_sums<<<(unsigned)nb, SCAN_THREADS, 0, stream>>>(in, n, (int32_t*)sums);
+    RB_CUDA(rb_launch(ctx, scan_block_sums, dim3((unsigned)nb), dim3(SCAN_THREADS), 0, stream, in, n, (int32_t*)sums));
     RB_LAUNCH_CHECK(ctx);
-    scan_sums_serial<<<1, SCAN_THREADS, 0, stream>>>((int32_t*)sums, nb, total_out);
+    RB_CUDA(rb_launch(ctx, scan_sums_serial, dim3(1), dim3(SCAN_THREADS), 0, stream, (int32_t*)sums, nb, total_out));
     RB_LAUNCH_CHECK(ctx);
-    scan_apply<<<(unsigned)nb, SCAN_THREADS, 0, stream>>>(in, out, n, (const int32_t*)sums);
+    RB_CUDA(rb_launch(ctx, scan_apply, dim3((unsigned)nb), dim3(SCAN_THREADS), 0, stream, in, out, n, (const int32_t*)sums));
     RB_LAUNCH_CHECK(ctx);
     return RB_OK;
 }

@@ -47,13 +47,20 @@ template <bool FILL>
 __global__ void __launch_bounds__(CSV_THREADS) csv_newline_kernel(const uint8_t* __restrict__ text, int64_t n_bytes,
                                                                  int32_t* __restrict__ chunk_count,
                                                                  const int32_t* __restrict__ chunk_base, int32_t* __restrict__ nl,
-                                                                 int64_t nl_cap) {
+                                                                 int64_t nl_cap, int32_t* __restrict__ info) {
     __shared__ int s_warp[CSV_THREADS / 32];
     const int64_t first = (int64_t)blockIdx.x * CSV_CHUNK + (int64_t)threadIdx.x * 16;
     unsigned hits = 0;
+    bool lone_cr = false;
 #pragma unroll
-    for (int j = 0; j < 16; ++j)
-        if (first + j < n_bytes && text[first + j] == '\n') hits |= 1u << j;
+    for (int j = 0; j < 16; ++j) {
+        if (first + j >= n_bytes) break;
+        const uint8_t ch = text[first + j];
+        if (ch == '\n') hits |= 1u << j;
+        // a carriage return that is not part of "\r\n": the reference's parser ends a line there, this grammar does not
+        if (!FILL && ch == '\r' && (first + j + 1 >= n_bytes || text[first + j + 1] != '\n')) lone_cr = true;
+    }
+    if (!FILL && lone_cr) atomicOr(info + 1, RB_CSV_NOT_INTEGER);
     int total;
     const int rank = block_exclusive(__popc(hits), s_warp, &total);
     if (!FILL) {
@@ -139,15 +146,15 @@ extern "C" int rb_csv_parse_sweep(rb_ctx* ctx, const uint8_t* text, int64_t n_by
     int32_t* chunk_count = (int32_t*)scratch;
     int32_t* chunk_base = chunk_count + chunks + 1;
     int32_t* nl = chunk_base + chunks + 1;
-    csv_newline_kernel<false><<<(unsigned)chunks, CSV_THREADS, 0, stream>>>(text, n_bytes, chunk_count, nullptr, nullptr, 0);
+    RB_CUDA(rb_launch(ctx, csv_newline_kernel<false>, dim3((unsigned)chunks), dim3(CSV_THREADS), 0, stream, text, n_bytes, chunk_count, nullptr, nullptr, 0, info));
     RB_LAUNCH_CHECK(ctx);
     RB_TRY(rb_exclusive_scan_i32(ctx, chunk_count, chunk_base, chunks, chunk_base + chunks, stream));      // [chunks] = total
-    csv_newline_kernel<true><<<(unsigned)chunks, CSV_THREADS, 0, stream>>>(text, n_bytes, nullptr, chunk_base, nl, nl_cap);
+    RB_CUDA(rb_launch(ctx, csv_newline_kernel<true>, dim3((unsigned)chunks), dim3(CSV_THREADS), 0, stream, text, n_bytes, nullptr, chunk_base, nl, nl_cap, info));
     RB_LAUNCH_CHECK(ctx);
     if (max_rows > 0) RB_CUDA(cudaMemsetAsync(echo, 0, (size_t)max_rows * (size_t)n_echo_columns, stream));
     // one block per possible row; a file with more lines than max_rows + 1 reports RB_CSV_CAPACITY
-    csv_parse_rows_kernel<<<(unsigned)(max_rows + 1), CSV_THREADS, 0, stream>>>(text, n_bytes, nl, chunk_base + chunks, n_echo_columns,
-                                                                              max_rows, echo, row_start, prefix_end, info);
+    RB_CUDA(rb_launch(ctx, csv_parse_rows_kernel, dim3((unsigned)(max_rows + 1)), dim3(CSV_THREADS), 0, stream, text, n_bytes, nl, chunk_base + chunks, n_echo_columns,
+                                                                              max_rows, echo, row_start, prefix_end, info));
     RB_LAUNCH_CHECK(ctx);
     return RB_OK;
 }

@@ -123,6 +123,13 @@ __device__ __forceinline__ int axis_cell(float v, double lo, double inv, int n) 
     return c < 0 ? 0 : (c >= n ? n - 1 : c);
 }
 
+// a coordinate outside the grid's box (only possible when the caller's HINT was wrong): clamping it into an edge cell
+// would make "same tight cell => neighbour" silently false, so the plan records it and the final read-back fails
+__device__ __forceinline__ bool axis_outside(float v, double lo, double inv, int n) {
+    const double c = floor(((double)v - lo) * inv);
+    return !(c >= 0.0 && c < (double)n);
+}
+
 __device__ __forceinline__ int cell_index(const DbGrid& g, float x, float y, float z, float t) {
     int cx = axis_cell(x, g.lo[0], g.inv_cell, g.n[0]);
     int cy = g.dim > 1 ? axis_cell(y, g.lo[1], g.inv_cell, g.n[1]) : 0;
@@ -133,13 +140,20 @@ __device__ __forceinline__ int cell_index(const DbGrid& g, float x, float y, flo
 
 // cell id per point + slot of the point inside its cell (the atomic's return value)
 __global__ void __launch_bounds__(DB_THREADS) db_cell_kernel(DbPoints p, DbGrid g, int64_t n, int* __restrict__ cell_id,
-                                                            int* __restrict__ slot, int* __restrict__ cell_count) {
+                                                            int* __restrict__ slot, int* __restrict__ cell_count,
+                                                            int* __restrict__ outside /* NULL: bounds were measured */) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float x = p.x[i * p.stride];
     float y = g.dim > 1 ? p.y[i * p.stride] : 0.f;
     float z = g.dim > 2 ? p.z[i * p.stride] : 0.f;
-    int c = cell_index(g, x, y, z, p.t[i]);
+    const float t = p.t[i];
+    if (outside) {
+        const bool bad = axis_outside(x, g.lo[0], g.inv_cell, g.n[0]) || (g.dim > 1 && axis_outside(y, g.lo[1], g.inv_cell, g.n[1])) ||
+                         (g.dim > 2 && axis_outside(z, g.lo[2], g.inv_cell, g.n[2])) || axis_outside(t, g.tmin, g.inv_wt, g.nt);
+        if (bad) atomicOr(outside, 1);
+    }
+    int c = cell_index(g, x, y, z, t);
     cell_id[i] = c;
     slot[i] = atomicAdd(cell_count + c, 1);
 }
@@ -660,7 +674,7 @@ __global__ void __launch_bounds__(DB_THREADS, DIM == 2 ? 3 : 2) dbt_union_kernel
                                                               const int* __restrict__ b_ncore, int* __restrict__ b_parent,
                                                               const int* __restrict__ cb_slot, const int* __restrict__ cb_bbox,
                                                               double eps2, unsigned long long* __restrict__ ctr) {
-    constexpr int SIDE = DIM == 1 ? 3 : 5;                          // tight grids search (2R+1)^DIM cells, R = 2 (1 in 1-D)
+    constexpr int SIDE = 5;                                         // tight grids search (2R+1)^DIM cells, R = 2
     constexpr int R = SIDE / 2;
     constexpr int RY = DIM > 1 ? R : 0, RZ = DIM > 2 ? R : 0;
     constexpr int SMALL_PAIR = 96;                                  // |A| * |B| up to which ONE lane searches the pair
@@ -1003,7 +1017,8 @@ int choose_grid(const float mn[4], const float mx[4], bool times_integer, int di
             g->inv_cell = 1.0 / cell;
             g->inv_wt = 1.0;
             g->tr = (int)fmin(floor(et), 1e6);
-            g->R = dim == 1 ? 1 : 2;                     // ceil(sqrt(dim)) cells cover eps
+            g->R = 2;                                    // cell < eps <= 2 cells in every dimension (1-D included: a pair at
+                                                         // cell < d <= eps can straddle a whole cell)
             g->tight = 1;
             *cell_out = cell;
             *wt_out = 1.0;
@@ -1104,7 +1119,7 @@ int plan_build(rb_ctx* ctx, rb_db_plan& P, const DbPoints& pts, int64_t n64, dou
     RB_TRY(scratch(ctx, RB_S_MISC, 64, &P.d_misc));
     P.d_ctr = (unsigned long long*)(P.d_misc + 16);
     P.d_ncb = P.d_misc + 32;
-    RB_CUDA(cudaMemsetAsync(P.d_ctr, 0, sizeof(unsigned long long) * 4, stream));
+    RB_CUDA(cudaMemsetAsync(P.d_ctr, 0, sizeof(unsigned long long) * 5, stream));     // [4] = "a point outside the hinted box"
     float mn[4], mx[4];
     bool times_integer;
     if (hint) {
@@ -1113,11 +1128,11 @@ int plan_build(rb_ctx* ctx, rb_db_plan& P, const DbPoints& pts, int64_t n64, dou
         for (int k = 0; k < 4; ++k) { mn[k] = hint->lo[k]; mx[k] = hint->hi[k]; }
         times_integer = hint->times_integer != 0;
     } else {
-        db_bounds_init<<<1, 32, 0, stream>>>(P.d_misc);
+        RB_CUDA(rb_launch(ctx, db_bounds_init, dim3(1), dim3(32), 0, stream, P.d_misc));
         RB_LAUNCH_CHECK(ctx);
         const unsigned want_b = (unsigned)rb_div_up(n, DB_THREADS * 4);
         int bblocks = (int)(want_b < (unsigned)ctx->sm_count * 4 ? want_b : (unsigned)ctx->sm_count * 4);
-        db_bounds_kernel<<<bblocks, DB_THREADS, 0, stream>>>(pts, DIM, n64, P.d_misc);
+        RB_CUDA(rb_launch(ctx, db_bounds_kernel, dim3(bblocks), dim3(DB_THREADS), 0, stream, pts, DIM, n64, P.d_misc));
         RB_LAUNCH_CHECK(ctx);
         int* h = (int*)ctx->pinned;
         RB_CUDA(cudaMemcpyAsync(h, P.d_misc, sizeof(int) * 9, cudaMemcpyDeviceToHost, stream));
@@ -1160,11 +1175,11 @@ int plan_build(rb_ctx* ctx, rb_db_plan& P, const DbPoints& pts, int64_t n64, dou
         P.cb_slot = P.b_label;                   // the label array is free until the assign phase
     }
     RB_CUDA(cudaMemsetAsync(P.cell_start, 0, sizeof(int) * ((size_t)P.n_cells + 1), stream));
-    db_cell_kernel<<<blocks, DB_THREADS, 0, stream>>>(pts, g, n64, cell_id, slot, P.cell_start);
+    RB_CUDA(rb_launch(ctx, db_cell_kernel, dim3(blocks), dim3(DB_THREADS), 0, stream, pts, g, n64, cell_id, slot, P.cell_start, hint ? (int*)(P.d_ctr + 4) : nullptr));
     RB_LAUNCH_CHECK(ctx);
     RB_TRY(rb_exclusive_scan_i32(ctx, P.cell_start, P.cell_start, P.n_cells + 1, nullptr, stream));
-    db_scatter_kernel<<<blocks, DB_THREADS, 0, stream>>>(pts, DIM, n64, cell_id, slot, P.cell_start, P.sidx, P.scell, P.sx, P.sy, P.sz,
-                                                        P.st);
+    RB_CUDA(rb_launch(ctx, db_scatter_kernel, dim3(blocks), dim3(DB_THREADS), 0, stream, pts, DIM, n64, cell_id, slot, P.cell_start, P.sidx, P.scell, P.sx, P.sy, P.sz,
+                                                        P.st));
     RB_LAUNCH_CHECK(ctx);
     P.valid = true;
     return RB_OK;
@@ -1175,10 +1190,10 @@ int phase_cores(rb_ctx* ctx, rb_db_plan& P, cudaStream_t stream) {
     const unsigned blocks = (unsigned)rb_div_up(P.n, DB_THREADS);
     const Sorted s = sorted_view(P);
     const bool wf = P.min_frames > 0;
-    if (P.g.tight && wf) dbt_count_kernel<DIM, true><<<blocks, DB_THREADS, 0, stream>>>(s, P.g, P.n, P.eps2, P.min_samples, P.min_frames, P.core, P.d_ctr + 0);
-    else if (P.g.tight) dbt_count_kernel<DIM, false><<<blocks, DB_THREADS, 0, stream>>>(s, P.g, P.n, P.eps2, P.min_samples, 0, P.core, P.d_ctr + 0);
-    else if (wf) dbg_count_kernel<DIM, true><<<blocks, DB_THREADS, 0, stream>>>(s, P.g, P.n, P.eps2, P.eps_t, P.min_samples, P.min_frames, P.core, P.d_ctr + 0);
-    else dbg_count_kernel<DIM, false><<<blocks, DB_THREADS, 0, stream>>>(s, P.g, P.n, P.eps2, P.eps_t, P.min_samples, 0, P.core, P.d_ctr + 0);
+    if (P.g.tight && wf) RB_CUDA(rb_launch(ctx, dbt_count_kernel<DIM, true>, dim3(blocks), dim3(DB_THREADS), 0, stream, s, P.g, P.n, P.eps2, P.min_samples, P.min_frames, P.core, P.d_ctr + 0));
+    else if (P.g.tight) RB_CUDA(rb_launch(ctx, dbt_count_kernel<DIM, false>, dim3(blocks), dim3(DB_THREADS), 0, stream, s, P.g, P.n, P.eps2, P.min_samples, 0, P.core, P.d_ctr + 0));
+    else if (wf) RB_CUDA(rb_launch(ctx, dbg_count_kernel<DIM, true>, dim3(blocks), dim3(DB_THREADS), 0, stream, s, P.g, P.n, P.eps2, P.eps_t, P.min_samples, P.min_frames, P.core, P.d_ctr + 0));
+    else RB_CUDA(rb_launch(ctx, dbg_count_kernel<DIM, false>, dim3(blocks), dim3(DB_THREADS), 0, stream, s, P.g, P.n, P.eps2, P.eps_t, P.min_samples, 0, P.core, P.d_ctr + 0));
     RB_LAUNCH_CHECK(ctx);
     P.have_cores = true;
     P.have_components = false;
@@ -1192,14 +1207,14 @@ int phase_components(rb_ctx* ctx, rb_db_plan& P, const long long* gidx, cudaStre
     const Sorted s = sorted_view(P);
     if (P.g.tight) {
         const unsigned cblocks = (unsigned)rb_div_up(P.n_cells + 1, DB_THREADS);
-        dbt_bucket_init_kernel<<<cblocks, DB_THREADS, 0, stream>>>(P.n_cells, P.b_ncore, P.b_parent, P.b_minkey, P.d_ncb);
+        RB_CUDA(rb_launch(ctx, dbt_bucket_init_kernel, dim3(cblocks), dim3(DB_THREADS), 0, stream, P.n_cells, P.b_ncore, P.b_parent, P.b_minkey, P.d_ncb));
         RB_LAUNCH_CHECK(ctx);
-        dbt_bucket_stats_kernel<<<blocks, DB_THREADS, 0, stream>>>(n, P.core, P.scell, P.sidx, gidx, P.b_ncore, P.b_minkey);
+        RB_CUDA(rb_launch(ctx, dbt_bucket_stats_kernel, dim3(blocks), dim3(DB_THREADS), 0, stream, n, P.core, P.scell, P.sidx, gidx, P.b_ncore, P.b_minkey));
         RB_LAUNCH_CHECK(ctx);
         const unsigned lblocks = (unsigned)rb_div_up(P.n_cells, (int64_t)DB_THREADS * LIST_PER_THREAD);
-        dbt_bucket_list_kernel<<<lblocks, DB_THREADS, 0, stream>>>(P.n_cells, P.b_ncore, P.cb_list, P.d_ncb, P.cb_slot, P.cb_bbox, P.b_parent);
+        RB_CUDA(rb_launch(ctx, dbt_bucket_list_kernel, dim3(lblocks), dim3(DB_THREADS), 0, stream, P.n_cells, P.b_ncore, P.cb_list, P.d_ncb, P.cb_slot, P.cb_bbox, P.b_parent));
         RB_LAUNCH_CHECK(ctx);
-        dbt_bucket_bbox_kernel<DIM><<<blocks, DB_THREADS, 0, stream>>>(s, n, P.core, P.cb_slot, P.cb_bbox);
+        RB_CUDA(rb_launch(ctx, dbt_bucket_bbox_kernel<DIM>, dim3(blocks), dim3(DB_THREADS), 0, stream, s, n, P.core, P.cb_slot, P.cb_bbox));
         RB_LAUNCH_CHECK(ctx);
         RB_TRY(rb_exclusive_scan_i32(ctx, P.b_ncore, P.core_start, P.n_cells + 1, nullptr, stream));
         const int64_t max_buckets = P.n_cells < n ? P.n_cells : n;
@@ -1207,25 +1222,25 @@ int phase_components(rb_ctx* ctx, rb_db_plan& P, const long long* gidx, cudaStre
         const unsigned ublocks = (unsigned)(want < (int64_t)ctx->sm_count * 16 ? (want > 0 ? want : 1) : (int64_t)ctx->sm_count * 16);
         const int64_t want2 = rb_div_up(max_buckets, DB_THREADS);
         const unsigned mblocks = (unsigned)(want2 < (int64_t)ctx->sm_count * 8 ? (want2 > 0 ? want2 : 1) : (int64_t)ctx->sm_count * 8);
-        dbt_link_time_kernel<<<mblocks, DB_THREADS, 0, stream>>>(P.g, P.cb_list, P.d_ncb, P.b_ncore, P.b_parent);
+        RB_CUDA(rb_launch(ctx, dbt_link_time_kernel, dim3(mblocks), dim3(DB_THREADS), 0, stream, P.g, P.cb_list, P.d_ncb, P.b_ncore, P.b_parent));
         RB_LAUNCH_CHECK(ctx);
-        dbt_flatten_kernel<<<mblocks, DB_THREADS, 0, stream>>>(P.cb_list, P.d_ncb, P.b_parent);
+        RB_CUDA(rb_launch(ctx, dbt_flatten_kernel, dim3(mblocks), dim3(DB_THREADS), 0, stream, P.cb_list, P.d_ncb, P.b_parent));
         RB_LAUNCH_CHECK(ctx);
-        dbt_union_kernel<DIM><<<ublocks, DB_THREADS, 0, stream>>>(s, P.g, P.cb_list, P.d_ncb, P.core, P.b_ncore, P.b_parent, P.cb_slot,
-                                                                  P.cb_bbox, P.eps2, P.d_ctr + 1);
+        RB_CUDA(rb_launch(ctx, dbt_union_kernel<DIM>, dim3(ublocks), dim3(DB_THREADS), 0, stream, s, P.g, P.cb_list, P.d_ncb, P.core, P.b_ncore, P.b_parent, P.cb_slot,
+                                                                  P.cb_bbox, P.eps2, P.d_ctr + 1));
         RB_LAUNCH_CHECK(ctx);
-        dbt_compmin_kernel<<<mblocks, DB_THREADS, 0, stream>>>(P.cb_list, P.d_ncb, P.b_parent, P.b_minkey);
+        RB_CUDA(rb_launch(ctx, dbt_compmin_kernel, dim3(mblocks), dim3(DB_THREADS), 0, stream, P.cb_list, P.d_ncb, P.b_parent, P.b_minkey));
         RB_LAUNCH_CHECK(ctx);
-        dbt_keyout_kernel<<<blocks, DB_THREADS, 0, stream>>>(n, P.core, P.scell, P.sidx, P.b_parent, P.b_minkey, P.comp_key);
+        RB_CUDA(rb_launch(ctx, dbt_keyout_kernel, dim3(blocks), dim3(DB_THREADS), 0, stream, n, P.core, P.scell, P.sidx, P.b_parent, P.b_minkey, P.comp_key));
         RB_LAUNCH_CHECK(ctx);
     } else {
-        dbg_init_kernel<<<blocks, DB_THREADS, 0, stream>>>(n, P.parent, P.minkey);
+        RB_CUDA(rb_launch(ctx, dbg_init_kernel, dim3(blocks), dim3(DB_THREADS), 0, stream, n, P.parent, P.minkey));
         RB_LAUNCH_CHECK(ctx);
-        dbg_union_kernel<DIM><<<blocks, DB_THREADS, 0, stream>>>(s, P.g, n, P.eps2, P.eps_t, P.core, P.parent, P.d_ctr + 1);
+        RB_CUDA(rb_launch(ctx, dbg_union_kernel<DIM>, dim3(blocks), dim3(DB_THREADS), 0, stream, s, P.g, n, P.eps2, P.eps_t, P.core, P.parent, P.d_ctr + 1));
         RB_LAUNCH_CHECK(ctx);
-        dbg_minkey_kernel<<<blocks, DB_THREADS, 0, stream>>>(n, P.core, P.parent, P.sidx, gidx, P.minkey);
+        RB_CUDA(rb_launch(ctx, dbg_minkey_kernel, dim3(blocks), dim3(DB_THREADS), 0, stream, n, P.core, P.parent, P.sidx, gidx, P.minkey));
         RB_LAUNCH_CHECK(ctx);
-        dbg_keyout_kernel<<<blocks, DB_THREADS, 0, stream>>>(n, P.core, P.parent, P.sidx, P.minkey, P.comp_key);
+        RB_CUDA(rb_launch(ctx, dbg_keyout_kernel, dim3(blocks), dim3(DB_THREADS), 0, stream, n, P.core, P.parent, P.sidx, P.minkey, P.comp_key));
         RB_LAUNCH_CHECK(ctx);
     }
     P.have_components = true;
@@ -1237,22 +1252,22 @@ int phase_assign(rb_ctx* ctx, rb_db_plan& P, const int32_t* core_label, int32_t*
     const int n = P.n;
     const unsigned blocks = (unsigned)rb_div_up(n, DB_THREADS);
     const Sorted s = sorted_view(P);
-    db_gather_labels_kernel<<<blocks, DB_THREADS, 0, stream>>>(n, P.core, P.sidx, P.scell, core_label, P.slabel,
-                                                              P.g.tight ? P.b_label : nullptr);
+    RB_CUDA(rb_launch(ctx, db_gather_labels_kernel, dim3(blocks), dim3(DB_THREADS), 0, stream, n, P.core, P.sidx, P.scell, core_label, P.slabel,
+                                                              P.g.tight ? P.b_label : nullptr));
     RB_LAUNCH_CHECK(ctx);
     const bool wf = P.min_frames > 0;
     if (P.g.tight && wf)
-        dbt_border_kernel<DIM, true><<<blocks, DB_THREADS, 0, stream>>>(s, P.g, n, P.eps2, P.core, P.slabel, P.sidx, P.b_ncore, P.core_start,
-                                                                        P.b_label, P.b_parent, P.b_minkey, labels, P.d_ctr + 2);
+        RB_CUDA(rb_launch(ctx, dbt_border_kernel<DIM, true>, dim3(blocks), dim3(DB_THREADS), 0, stream, s, P.g, n, P.eps2, P.core, P.slabel, P.sidx, P.b_ncore, P.core_start,
+                                                                        P.b_label, P.b_parent, P.b_minkey, labels, P.d_ctr + 2));
     else if (P.g.tight)
-        dbt_border_kernel<DIM, false><<<blocks, DB_THREADS, 0, stream>>>(s, P.g, n, P.eps2, P.core, P.slabel, P.sidx, P.b_ncore, P.core_start,
-                                                                         P.b_label, P.b_parent, P.b_minkey, labels, P.d_ctr + 2);
+        RB_CUDA(rb_launch(ctx, dbt_border_kernel<DIM, false>, dim3(blocks), dim3(DB_THREADS), 0, stream, s, P.g, n, P.eps2, P.core, P.slabel, P.sidx, P.b_ncore, P.core_start,
+                                                                         P.b_label, P.b_parent, P.b_minkey, labels, P.d_ctr + 2));
     else if (wf)
-        dbg_border_kernel<DIM, true><<<blocks, DB_THREADS, 0, stream>>>(s, P.g, n, P.eps2, P.eps_t, P.core, P.slabel, P.sidx, P.comp_key, labels,
-                                                                        P.d_ctr + 2);
+        RB_CUDA(rb_launch(ctx, dbg_border_kernel<DIM, true>, dim3(blocks), dim3(DB_THREADS), 0, stream, s, P.g, n, P.eps2, P.eps_t, P.core, P.slabel, P.sidx, P.comp_key, labels,
+                                                                        P.d_ctr + 2));
     else
-        dbg_border_kernel<DIM, false><<<blocks, DB_THREADS, 0, stream>>>(s, P.g, n, P.eps2, P.eps_t, P.core, P.slabel, P.sidx, P.comp_key, labels,
-                                                                         P.d_ctr + 2);
+        RB_CUDA(rb_launch(ctx, dbg_border_kernel<DIM, false>, dim3(blocks), dim3(DB_THREADS), 0, stream, s, P.g, n, P.eps2, P.eps_t, P.core, P.slabel, P.sidx, P.comp_key, labels,
+                                                                         P.d_ctr + 2));
     RB_LAUNCH_CHECK(ctx);
     return RB_OK;
 }
@@ -1262,8 +1277,12 @@ int phase_assign(rb_ctx* ctx, rb_db_plan& P, const int32_t* core_label, int32_t*
 
 int fetch_stats(rb_ctx* ctx, rb_db_plan& P, int64_t* n_clusters, cudaStream_t stream) {
     unsigned long long* hc = (unsigned long long*)ctx->pinned;
-    RB_CUDA(cudaMemcpyAsync(hc, P.d_ctr, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, stream));
+    RB_CUDA(cudaMemcpyAsync(hc, P.d_ctr, sizeof(unsigned long long) * 5, cudaMemcpyDeviceToHost, stream));
     RB_CUDA(cudaStreamSynchronize(stream));
+    if (hc[4] != 0) {
+        rb_set_error("ST-DBSCAN: the hinted box does not contain every point / time (rb_stdbscan_hint); the result is invalid");
+        return RB_ERR_ARG;
+    }
     rb_dbscan_stats& stt = ctx->last_stats;
     memset(&stt, 0, sizeof stt);
     stt.n_points = P.n;
@@ -1318,7 +1337,7 @@ extern "C" int rb_stdbscan_cores(rb_ctx* ctx, uint8_t* core_out, void* stream_) 
     rb_db_plan& P = *ctx->db_plan;
     RB_TRY(DB_DISPATCH(P, phase_cores)(ctx, P, stream));
     if (core_out) {
-        db_core_out_kernel<<<(unsigned)rb_div_up(P.n, DB_THREADS), DB_THREADS, 0, stream>>>(P.n, P.core, P.sidx, core_out);
+        RB_CUDA(rb_launch(ctx, db_core_out_kernel, dim3((unsigned)rb_div_up(P.n, DB_THREADS)), dim3(DB_THREADS), 0, stream, P.n, P.core, P.sidx, core_out));
         RB_LAUNCH_CHECK(ctx);
     }
     return RB_OK;
@@ -1329,7 +1348,7 @@ extern "C" int rb_stdbscan_set_cores(rb_ctx* ctx, const uint8_t* core_in, void* 
     RB_REQUIRE(core_in, "core_in is NULL");
     cudaStream_t stream = (cudaStream_t)stream_;
     rb_db_plan& P = *ctx->db_plan;
-    db_core_in_kernel<<<(unsigned)rb_div_up(P.n, DB_THREADS), DB_THREADS, 0, stream>>>(P.n, core_in, P.sidx, P.core);
+    RB_CUDA(rb_launch(ctx, db_core_in_kernel, dim3((unsigned)rb_div_up(P.n, DB_THREADS)), dim3(DB_THREADS), 0, stream, P.n, core_in, P.sidx, P.core));
     RB_LAUNCH_CHECK(ctx);
     P.have_components = false;
     return RB_OK;
@@ -1359,8 +1378,8 @@ extern "C" int rb_relabel(rb_ctx* ctx, const int64_t* keys, int64_t n, const int
     if (n == 0) return RB_OK;
     RB_REQUIRE(keys && out && (m == 0 || (table_keys && table_ids)), "NULL argument");
     cudaStream_t stream = (cudaStream_t)stream_;
-    db_relabel_kernel<<<(unsigned)rb_div_up(n, DB_THREADS), DB_THREADS, 0, stream>>>(n, (const long long*)keys, (const long long*)table_keys,
-                                                                                    table_ids, m, out);
+    RB_CUDA(rb_launch(ctx, db_relabel_kernel, dim3((unsigned)rb_div_up(n, DB_THREADS)), dim3(DB_THREADS), 0, stream, n, (const long long*)keys, (const long long*)table_keys,
+                                                                                    table_ids, m, out));
     RB_LAUNCH_CHECK(ctx);
     return RB_OK;
 }
@@ -1376,11 +1395,11 @@ int rb_stdbscan_enqueue(rb_ctx* ctx, const float* x, const float* y, const float
     RB_TRY(rb_stdbscan_components(ctx, nullptr, nullptr, stream_));
     // canonical numbering: rank of every component's smallest core index
     const unsigned blocks = (unsigned)rb_div_up(P.n, DB_THREADS);
-    db_rootflag_kernel<<<blocks, DB_THREADS, 0, stream>>>(P.n, P.comp_key, P.flags);
+    RB_CUDA(rb_launch(ctx, db_rootflag_kernel, dim3(blocks), dim3(DB_THREADS), 0, stream, P.n, P.comp_key, P.flags));
     RB_LAUNCH_CHECK(ctx);
     int* d_total = (int*)(P.d_ctr + 3);
     RB_TRY(rb_exclusive_scan_i32(ctx, P.flags, P.rank, P.n, d_total, stream));
-    db_rank_labels_kernel<<<blocks, DB_THREADS, 0, stream>>>(P.n, P.comp_key, P.rank, labels);
+    RB_CUDA(rb_launch(ctx, db_rank_labels_kernel, dim3(blocks), dim3(DB_THREADS), 0, stream, P.n, P.comp_key, P.rank, labels));
     RB_LAUNCH_CHECK(ctx);
     return rb_stdbscan_assign(ctx, labels, labels, stream_);         // in place: core labels are copied before any write
 }
@@ -1419,11 +1438,11 @@ extern "C" int rb_stdbscan_wf(rb_ctx* ctx, const float* x, const float* y, const
     RB_TRY(rb_stdbscan_cores(ctx, core, stream_));
     RB_TRY(rb_stdbscan_components(ctx, nullptr, nullptr, stream_));
     const unsigned blocks = (unsigned)rb_div_up(P.n, DB_THREADS);
-    db_rootflag_kernel<<<blocks, DB_THREADS, 0, stream>>>(P.n, P.comp_key, P.flags);
+    RB_CUDA(rb_launch(ctx, db_rootflag_kernel, dim3(blocks), dim3(DB_THREADS), 0, stream, P.n, P.comp_key, P.flags));
     RB_LAUNCH_CHECK(ctx);
     int* d_total = (int*)(P.d_ctr + 3);
     RB_TRY(rb_exclusive_scan_i32(ctx, P.flags, P.rank, P.n, d_total, stream));
-    db_rank_labels_kernel<<<blocks, DB_THREADS, 0, stream>>>(P.n, P.comp_key, P.rank, labels);
+    RB_CUDA(rb_launch(ctx, db_rank_labels_kernel, dim3(blocks), dim3(DB_THREADS), 0, stream, P.n, P.comp_key, P.rank, labels));
     RB_LAUNCH_CHECK(ctx);
     RB_TRY(rb_stdbscan_assign(ctx, labels, labels, stream_));
     return rb_stdbscan_fetch_stats(ctx, n_clusters, stream_);

@@ -56,13 +56,13 @@ extern "C" int rb_fuse_max(rb_ctx* ctx, const float* x, const float* y, const fl
     int* pos = flags + cells;
     RB_CUDA(cudaMemsetAsync(grid, 0, sizeof(int) * (size_t)cells, stream));
     int blocks = (int)(rb_div_up(n, 256) < (int64_t)ctx->sm_count * 8 ? rb_div_up(n, 256) : (int64_t)ctx->sm_count * 8);
-    fuse_pool_kernel<<<blocks, 256, 0, stream>>>(x, y, inten, n, x_min, y_min, resolution, nx, ny, grid);
+    RB_CUDA(rb_launch(ctx, fuse_pool_kernel, dim3(blocks), dim3(256), 0, stream, x, y, inten, n, x_min, y_min, resolution, nx, ny, grid));
     RB_LAUNCH_CHECK(ctx);
     unsigned cb = (unsigned)rb_div_up(cells, 256);
-    fuse_flag_kernel<<<cb, 256, 0, stream>>>(grid, nx, ny, flags);
+    RB_CUDA(rb_launch(ctx, fuse_flag_kernel, dim3(cb), dim3(256), 0, stream, grid, nx, ny, flags));
     RB_LAUNCH_CHECK(ctx);
     RB_TRY(rb_exclusive_scan_i32(ctx, flags, pos, cells, pos + cells, stream));
-    fuse_emit_kernel<<<cb, 256, 0, stream>>>(grid, flags, pos, nx, ny, cap_cells, cell_ix, cell_iy, cell_max);
+    RB_CUDA(rb_launch(ctx, fuse_emit_kernel, dim3(cb), dim3(256), 0, stream, grid, flags, pos, nx, ny, cap_cells, cell_ix, cell_iy, cell_max));
     RB_LAUNCH_CHECK(ctx);
     int* h = (int*)ctx->pinned;
     RB_CUDA(cudaMemcpyAsync(h, pos + cells, sizeof(int), cudaMemcpyDeviceToHost, stream));

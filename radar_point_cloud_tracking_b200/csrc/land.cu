@@ -283,9 +283,9 @@ extern "C" int rb_bounds(rb_ctx* ctx, const float* x, const float* y, int64_t n,
                                                                                  : (int64_t)ctx->sm_count * 8);
     void* partial;
     RB_TRY(rb_scratch_get(ctx, RB_S_REDUCE, sizeof(Bounds4) * (size_t)blocks, &partial));
-    bounds_partial<<<blocks, LD_THREADS, 0, stream>>>(x, y, n, nullptr, (Bounds4*)partial);
+    RB_CUDA(rb_launch(ctx, bounds_partial, dim3(blocks), dim3(LD_THREADS), 0, stream, x, y, n, nullptr, (Bounds4*)partial));
     RB_LAUNCH_CHECK(ctx);
-    bounds_final<<<1, LD_THREADS, 0, stream>>>((const Bounds4*)partial, blocks, out4);
+    RB_CUDA(rb_launch(ctx, bounds_final, dim3(1), dim3(LD_THREADS), 0, stream, (const Bounds4*)partial, blocks, out4));
     RB_LAUNCH_CHECK(ctx);
     return RB_OK;
 }
@@ -296,9 +296,9 @@ int rb_bounds_devn(rb_ctx* ctx, const float* x, const float* y, const int64_t* n
                                                                                      : (int64_t)ctx->sm_count * 4);
     void* partial;
     RB_TRY(rb_scratch_get(ctx, RB_S_REDUCE, sizeof(Bounds4) * (size_t)blocks, &partial));
-    bounds_partial<<<blocks, LD_THREADS, 0, stream>>>(x, y, n_max, n_dev, (Bounds4*)partial);
+    RB_CUDA(rb_launch(ctx, bounds_partial, dim3(blocks), dim3(LD_THREADS), 0, stream, x, y, n_max, n_dev, (Bounds4*)partial));
     RB_LAUNCH_CHECK(ctx);
-    bounds_final<<<1, LD_THREADS, 0, stream>>>((const Bounds4*)partial, blocks, out4);
+    RB_CUDA(rb_launch(ctx, bounds_final, dim3(1), dim3(LD_THREADS), 0, stream, (const Bounds4*)partial, blocks, out4));
     RB_LAUNCH_CHECK(ctx);
     return RB_OK;
 }
@@ -324,12 +324,15 @@ extern "C" int rb_land_accumulate(rb_ctx* ctx, const float* x, const float* y, c
     int blocks = (int)(rb_div_up(n, LD_THREADS * 4) < (int64_t)ctx->sm_count * per_sm ? rb_div_up(n, LD_THREADS * 4)
                                                                                       : (int64_t)ctx->sm_count * per_sm);
     if (smem <= 220 * 1024) {
-        RB_CUDA(cudaFuncSetAttribute(land_accumulate_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        land_accumulate_smem<<<blocks, LD_THREADS, smem, stream>>>(x, y, inten, n, g, count, isum);
+        if (!ctx->attr_land) {                          // once per context (= per device): allow the largest grid that fits
+            RB_CUDA(cudaFuncSetAttribute(land_accumulate_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            ctx->attr_land = true;
+        }
+        RB_CUDA(rb_launch(ctx, land_accumulate_smem, dim3(blocks), dim3(LD_THREADS), smem, stream, x, y, inten, n, g, count, isum));
     } else {
         blocks = (int)(rb_div_up(n, LD_THREADS) < (int64_t)ctx->sm_count * 8 ? rb_div_up(n, LD_THREADS)
                                                                            : (int64_t)ctx->sm_count * 8);
-        land_accumulate_global<<<blocks, LD_THREADS, 0, stream>>>(x, y, inten, n, g, count, isum);
+        RB_CUDA(rb_launch(ctx, land_accumulate_global, dim3(blocks), dim3(LD_THREADS), 0, stream, x, y, inten, n, g, count, isum));
     }
     RB_LAUNCH_CHECK(ctx);
     return RB_OK;
@@ -342,8 +345,8 @@ extern "C" int rb_land_cells(rb_ctx* ctx, const int32_t* count, const double* is
     if (n_cells <= 0) return RB_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     double frames = (double)(num_frames > 1 ? num_frames : 1);       // max(num_frames, 1), T4:401
-    land_cells_kernel<<<(unsigned)rb_div_up(n_cells, 256), 256, 0, stream>>>(count, isum, n_cells, frames,
-                                                                            persistence, min_intensity, land);
+    RB_CUDA(rb_launch(ctx, land_cells_kernel, dim3((unsigned)rb_div_up(n_cells, 256)), dim3(256), 0, stream, count, isum, n_cells, frames,
+                                                                            persistence, min_intensity, land));
     RB_LAUNCH_CHECK(ctx);
     return RB_OK;
 }
@@ -369,15 +372,14 @@ extern "C" int rb_land_filter(rb_ctx* ctx, const float* x, const float* y, const
     void* tile_count;
     RB_TRY(rb_scratch_get(ctx, RB_S_BLOCKSUM2, sizeof(int32_t) * (size_t)(tiles + 1), &tile_count));
     int32_t* tc = (int32_t*)tile_count;
-    land_keep_kernel<<<(unsigned)tiles, LD_THREADS, 0, stream>>>(x, y, n, g, land, (uint8_t*)keep, tc);
+    RB_CUDA(rb_launch(ctx, land_keep_kernel, dim3((unsigned)tiles), dim3(LD_THREADS), 0, stream, x, y, n, g, land, (uint8_t*)keep, tc));
     RB_LAUNCH_CHECK(ctx);
     RB_TRY(rb_exclusive_scan_i32(ctx, tc, tc, tiles, tc + tiles, stream));
-    land_scatter_kernel<<<(unsigned)tiles, LD_THREADS, 0, stream>>>(x, y, inten, gain, n, (const uint8_t*)keep, tc,
-                                                                   x_out, y_out, inten_out, gain_out);
+    RB_CUDA(rb_launch(ctx, land_scatter_kernel, dim3((unsigned)tiles), dim3(LD_THREADS), 0, stream, x, y, inten, gain, n, (const uint8_t*)keep, tc,
+                                                                   x_out, y_out, inten_out, gain_out));
     RB_LAUNCH_CHECK(ctx);
     unsigned warps = (unsigned)(n_frames + 1);
-    land_frame_offsets_kernel<<<(unsigned)rb_div_up((int64_t)warps * 32, 256), 256, 0, stream>>>(
-        frame_off, n_frames, n, (const uint8_t*)keep, tc, tc + tiles, frame_off_out);
+    RB_CUDA(rb_launch(ctx, land_frame_offsets_kernel, dim3((unsigned)rb_div_up((int64_t)warps * 32, 256)), dim3(256), 0, stream, frame_off, n_frames, n, (const uint8_t*)keep, tc, tc + tiles, frame_off_out));
     RB_LAUNCH_CHECK(ctx);
     return RB_OK;
 }

@@ -118,16 +118,25 @@ extern "C" int rb_detect_block(rb_ctx* ctx, const float* echo, const float* cos_
     RB_TRY(rb_frame_offsets(ctx, sweep_base, F, prm->gains_per_frame, buf->frame_off, stream_));
     if (buf->cap > 0) RB_TRY(rb_bounds_devn(ctx, buf->x, buf->y, sweep_base + W, buf->cap, d_bounds, stream));
     // read-back 1: frame offsets (point count, frames built) + bounds
+    // pinned staging of the context: [frame offsets | bounds | grid edges (x, y) | frame ids]. Everything the host uploads
+    // below goes through it, so no copy waits for the stream the way a copy from pageable memory does; a region is
+    // rewritten only after a stream sync.
     const size_t off_bytes = sizeof(int64_t) * (size_t)(F + 1);
-    if (ctx->pinned_cap < off_bytes + 64) {
+    const size_t edge_cap = (size_t)(buf->max_edges > 0 ? buf->max_edges : 0);
+    const size_t edges_at = off_bytes + 64, ids_at = edges_at + sizeof(double) * 2 * edge_cap;
+    const size_t pinned_need = ids_at + sizeof(float) * (size_t)F + 64;
+    if (ctx->pinned_cap < pinned_need) {
         RB_CUDA(cudaStreamSynchronize(stream));
         if (ctx->pinned) RB_CUDA(cudaFreeHost(ctx->pinned));
         ctx->pinned = nullptr; ctx->pinned_cap = 0;
-        RB_CUDA(cudaMallocHost(&ctx->pinned, off_bytes + 4096));
-        ctx->pinned_cap = off_bytes + 4096;
+        RB_CUDA(cudaMallocHost(&ctx->pinned, pinned_need + 4096));
+        ctx->pinned_cap = pinned_need + 4096;
     }
     int64_t* h_off = (int64_t*)ctx->pinned;
     float* h_bounds = (float*)((unsigned char*)ctx->pinned + off_bytes);
+    double* h_xe = (double*)((unsigned char*)ctx->pinned + edges_at);
+    double* h_ye = h_xe + edge_cap;
+    float* h_ids = (float*)((unsigned char*)ctx->pinned + ids_at);
     RB_CUDA(cudaMemcpyAsync(h_off, buf->frame_off, off_bytes, cudaMemcpyDeviceToHost, stream));
     if (buf->cap > 0) RB_CUDA(cudaMemcpyAsync(h_bounds, d_bounds, sizeof(float) * 4, cudaMemcpyDeviceToHost, stream));
     RB_CUDA(cudaStreamSynchronize(stream));
@@ -156,8 +165,8 @@ extern "C" int rb_detect_block(rb_ctx* ctx, const float* echo, const float* cos_
     const int64_t* p_off = buf->frame_off;
     int64_t n_pts = n_raw;
     if (prm->land_filter && n_raw > 0 && built > prm->land_min_frames) {
-        const int64_t nxe = rb_arange_edges(res->bounds[0], res->bounds[1], prm->land_resolution, buf->x_edges, buf->max_edges);
-        const int64_t nye = rb_arange_edges(res->bounds[2], res->bounds[3], prm->land_resolution, buf->y_edges, buf->max_edges);
+        const int64_t nxe = rb_arange_edges(res->bounds[0], res->bounds[1], prm->land_resolution, h_xe, buf->max_edges);
+        const int64_t nye = rb_arange_edges(res->bounds[2], res->bounds[3], prm->land_resolution, h_ye, buf->max_edges);
         res->n_x_edges = (int32_t)nxe;
         res->n_y_edges = (int32_t)nye;
         const int64_t cells = (nxe - 1) * (nye - 1);
@@ -167,13 +176,15 @@ extern "C" int rb_detect_block(rb_ctx* ctx, const float* echo, const float* cos_
             return RB_ERR_CAPACITY;
         }
         RB_REQUIRE(nxe >= 2 && nye >= 2, "degenerate land grid");
+        memcpy(buf->x_edges, h_xe, sizeof(double) * (size_t)nxe);          // the caller's copy (an output)
+        memcpy(buf->y_edges, h_ye, sizeof(double) * (size_t)nye);
         RB_REQUIRE(buf->count && buf->isum && buf->land && buf->fx && buf->fy && buf->finten && buf->fgain, "NULL land buffers");
         void* e_v;
         RB_TRY(rb_scratch_get(ctx, RB_S_PIPE_EDGES, sizeof(double) * (size_t)(nxe + nye), &e_v));
         double* d_xe = (double*)e_v;
         double* d_ye = d_xe + nxe;
-        RB_CUDA(cudaMemcpyAsync(d_xe, buf->x_edges, sizeof(double) * (size_t)nxe, cudaMemcpyHostToDevice, stream));
-        RB_CUDA(cudaMemcpyAsync(d_ye, buf->y_edges, sizeof(double) * (size_t)nye, cudaMemcpyHostToDevice, stream));
+        RB_CUDA(cudaMemcpyAsync(d_xe, h_xe, sizeof(double) * (size_t)nxe, cudaMemcpyHostToDevice, stream));
+        RB_CUDA(cudaMemcpyAsync(d_ye, h_ye, sizeof(double) * (size_t)nye, cudaMemcpyHostToDevice, stream));
         RB_CUDA(cudaMemsetAsync(buf->count, 0, sizeof(int32_t) * (size_t)cells, stream));
         RB_CUDA(cudaMemsetAsync(buf->isum, 0, sizeof(double) * (size_t)cells, stream));
         RB_TRY(rb_land_accumulate(ctx, buf->x, buf->y, buf->inten, n_raw, d_xe, (int)nxe, d_ye, (int)nye, buf->count, buf->isum, stream_));
@@ -198,7 +209,8 @@ extern "C" int rb_detect_block(rb_ctx* ctx, const float* echo, const float* cos_
         RB_TRY(rb_scratch_get(ctx, RB_S_PIPE_TIMES, sizeof(float) * (size_t)(n_pts + F), &t_v));
         float* d_times = (float*)t_v;
         float* d_ids = d_times + n_pts;
-        RB_CUDA(cudaMemcpyAsync(d_ids, frame_ids, sizeof(float) * (size_t)F, cudaMemcpyHostToDevice, stream));
+        memcpy(h_ids, frame_ids, sizeof(float) * (size_t)F);
+        RB_CUDA(cudaMemcpyAsync(d_ids, h_ids, sizeof(float) * (size_t)F, cudaMemcpyHostToDevice, stream));
         RB_TRY(rb_expand_frame_times(ctx, p_off, d_ids, F, n_pts, d_times, stream_));
         rb_stdbscan_hint hint;
         hint.lo[0] = res->bounds[0]; hint.hi[0] = res->bounds[1];      // filtered points lie inside the raw bounds

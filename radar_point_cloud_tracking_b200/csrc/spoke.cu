@@ -104,8 +104,8 @@ inline ThrArg make_thr(float thr) {
     return a;
 }
 template <typename T> struct Elem;
-template <> struct Elem<float>   { static constexpr int STAGE_TILES = 4;  static constexpr int ALIGN_CELLS = 4;  static constexpr int WARPS = 8; };    // 64 KiB stages,
-template <> struct Elem<uint8_t> { static constexpr int STAGE_TILES = 16; static constexpr int ALIGN_CELLS = 16; static constexpr int WARPS = 16; };   // 16-byte bulk copies; 4x the cells per stage: twice the consumer warps
+template <> struct Elem<float>   { static constexpr int ALIGN_CELLS = 4;  static constexpr int WARPS = 8; };    // 16-byte bulk copies;
+template <> struct Elem<uint8_t> { static constexpr int ALIGN_CELLS = 16; static constexpr int WARPS = 16; };   // 4x the cells per stage: twice the consumer warps
 
 __device__ __forceinline__ unsigned u8_bits4(unsigned word, const ThrArg& t) {              // survivor flags of 4 cells in bits 0..3
     const unsigned r = t.none ? 0u : __vcmpgeu4(word, t.lb4);
@@ -164,8 +164,9 @@ __device__ __forceinline__ TileRef<T> tile_ref(const T* echo, const SpokeGeom& g
 // that the producer flushes to global memory when it recycles the slot. Stages are handed out by one
 // atomic ticket per CTA and stage (a ticket per WARP and tile serialises on the atomic unit: measured
 // 4.8 instead of 7.0 TB/s, tools/mask_bench.cu).
-constexpr int MT_STAGES = 3;
-constexpr int MT_STAGE_BYTES = 64 * 1024;                                  // 4 float32 tiles or 16 uint8 tiles
+// The ring is a template parameter pair (stage bytes x stages). 64 KiB x 3 (197 KB) is the default: the most bytes in
+// flight. The smaller rings (rb_set_option "spoke_ring") leave shared memory / L1 to other kernels, so that the
+// latency-bound clustering kernels of the previous block can be RESIDENT next to this HBM-bound one ("carveout" option).
 template <typename T> constexpr int mt_threads() { return Elem<T>::WARPS * 32 + 32; }    // consumer warps + the producer warp
 
 template <int TILES>
@@ -175,14 +176,17 @@ struct MtMeta {
     int valid[TILES];                     // cells of each tile inside its sweep
     unsigned cnt[TILES];                  // survivors, accumulated by the consumers
 };
-template <int TILES>
+template <int TILES, int STAGE_BYTES, int STAGES>
 struct __align__(128) MtSmem {
-    unsigned char ring[MT_STAGES][MT_STAGE_BYTES];
-    unsigned long long full[MT_STAGES];
-    unsigned long long empty[MT_STAGES];
-    MtMeta<TILES> meta[MT_STAGES];
+    unsigned char ring[STAGES][STAGE_BYTES];
+    unsigned long long full[STAGES];
+    unsigned long long empty[STAGES];
+    MtMeta<TILES> meta[STAGES];
 };
-template <typename T> constexpr int mt_smem_bytes() { return (int)sizeof(MtSmem<Elem<T>::STAGE_TILES>) + 128; }
+template <typename T, int STAGE_BYTES> __host__ __device__ constexpr int mt_tiles() { return STAGE_BYTES / (SK_TILE * (int)sizeof(T)); }
+template <typename T, int STAGE_BYTES, int STAGES> constexpr int mt_smem_bytes() {
+    return (int)sizeof(MtSmem<mt_tiles<T, STAGE_BYTES>(), STAGE_BYTES, STAGES>) + 128;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
@@ -205,22 +209,34 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
         "MT_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-// global -> shared bulk async copy (TMA engine, 1-D), completion counted in bytes on an mbarrier
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+// global -> shared bulk async copy (TMA engine, 1-D), completion counted in bytes on an mbarrier. The echo stream is
+// read exactly once: with `policy` != 0 (an L2 evict-first policy) its lines are the first to leave L2, so the working
+// set of kernels running beside this one (bucket tables, sorted points of the previous block) stays resident.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar, unsigned long long policy) {
+    if (policy)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                     ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+    else
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
 
-template <typename T>
+template <typename T, int MT_STAGE_BYTES, int MT_STAGES>
 __global__ void __launch_bounds__(mt_threads<T>(), 1)
 spoke_mask_tma_kernel(const T* __restrict__ echo, const SpokeGeom g, const ThrArg threshold,
-                      uint32_t* __restrict__ mask, uint32_t* __restrict__ tile_count, unsigned* __restrict__ ticket) {
-    constexpr int MT_TILES = Elem<T>::STAGE_TILES;
+                      uint32_t* __restrict__ mask, uint32_t* __restrict__ tile_count, unsigned* __restrict__ ticket, const int l2_hint) {
+    constexpr int MT_TILES = mt_tiles<T, MT_STAGE_BYTES>();
     constexpr int MT_WARPS = Elem<T>::WARPS;
     constexpr int MT_STAGE_BATCHES = MT_TILES * SK_BATCHES;
-    static_assert(MT_TILES * SK_TILE * sizeof(T) == MT_STAGE_BYTES, "a stage is 64 KiB");
+    static_assert(MT_TILES >= 1 && MT_TILES * SK_TILE * sizeof(T) == MT_STAGE_BYTES, "a stage is a whole number of tiles");
+    using Smem = MtSmem<MT_TILES, MT_STAGE_BYTES, MT_STAGES>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    MtSmem<MT_TILES>& sm = *reinterpret_cast<MtSmem<MT_TILES>*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
     const unsigned lane = rb_lane();
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
@@ -248,6 +264,7 @@ spoke_mask_tma_kernel(const T* __restrict__ echo, const SpokeGeom g, const ThrAr
             }
             __syncwarp();
         };
+        const unsigned long long policy = l2_hint ? l2_evict_first_policy() : 0ull;
         long long st = blockIdx.x;
         int it = 0;
         while (true) {
@@ -285,9 +302,9 @@ spoke_mask_tma_kernel(const T* __restrict__ echo, const SpokeGeom g, const ThrAr
             if (lane == 0) mbar_expect_tx(&sm.full[s], bytes);             // releases the meta data to the consumers
             __syncwarp();
             if (all_full) {                                                // the common case: ONE 64 KiB copy per stage
-                if (lane == 0) bulk_g2s(&sm.ring[s][0], src, bytes, &sm.full[s]);
+                if (lane == 0) bulk_g2s(&sm.ring[s][0], src, bytes, &sm.full[s], policy);
             } else if (v > 0) {                                            // ragged stage: every lane copies its own tile
-                bulk_g2s(&sm.ring[s][(size_t)lane * SK_TILE * sizeof(T)], src, (uint32_t)v * (uint32_t)sizeof(T), &sm.full[s]);
+                bulk_g2s(&sm.ring[s][(size_t)lane * SK_TILE * sizeof(T)], src, (uint32_t)v * (uint32_t)sizeof(T), &sm.full[s], policy);
             }
             st = (long long)gridDim.x + (long long)__shfl_sync(0xffffffffu, tk, 0);
             ++it;
@@ -640,8 +657,28 @@ extern "C" int rb_polar_to_cartesian(rb_ctx* ctx, const float* ranges, const flo
     cudaStream_t stream = (cudaStream_t)stream_;
     int blocks = (int)(rb_div_up(total, 256 * 4) < (int64_t)ctx->sm_count * 16 ? rb_div_up(total, 256 * 4)
                                                                                : (int64_t)ctx->sm_count * 16);
-    polar_grid_kernel<<<blocks, 256, 0, stream>>>(ranges, cos_tab, sin_tab, total, n_cols, x, y);
+    RB_CUDA(rb_launch(ctx, polar_grid_kernel, dim3(blocks), dim3(256), 0, stream, ranges, cos_tab, sin_tab, total, n_cols, x, y));
     RB_LAUNCH_CHECK(ctx);
+    return RB_OK;
+}
+
+// launches the TMA-staged mask kernel with the ring <STAGE_BYTES x STAGES>; the dynamic shared-memory limit of each
+// instance is raised once per context (= per device), in the context's own flags
+template <typename T, int STAGE_BYTES, int STAGES>
+int launch_mask_tma(rb_ctx* ctx, const T* echo, const SpokeGeom& g, const ThrArg& thr, uint32_t* mask, uint32_t* tile_count,
+                    unsigned* ticket, cudaStream_t stream) {
+    constexpr int smem = mt_smem_bytes<T, STAGE_BYTES, STAGES>();
+    constexpr int ring_id = (STAGE_BYTES == 64 * 1024 ? (STAGES == 3 ? 0 : 3) : STAGE_BYTES == 32 * 1024 ? (STAGES == 4 ? 1 : 2) : 4);
+    const unsigned bit = 1u << (ring_id * 2 + (sizeof(T) == 1 ? 1 : 0));
+    auto kernel = spoke_mask_tma_kernel<T, STAGE_BYTES, STAGES>;
+    if (!(ctx->attr_spoke_mask & bit)) {
+        RB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ctx->attr_spoke_mask |= bit;
+    }
+    const int64_t want_blocks = rb_div_up(g.total_tiles, mt_tiles<T, STAGE_BYTES>());
+    const unsigned blocks = (unsigned)(want_blocks < ctx->sm_count ? want_blocks : ctx->sm_count);
+    RB_CUDA(rb_launch(ctx, kernel, dim3(blocks), dim3(mt_threads<T>()), (size_t)smem, stream, echo, g, thr, mask, tile_count, ticket,
+                      ctx->opt_spoke_l2_hint));
     return RB_OK;
 }
 
@@ -702,29 +739,28 @@ int spoke_to_points_impl(rb_ctx* ctx, const T* echo, const float* cos_tab, const
     const int variant = ctx->opt_spoke_mask_variant;
     RB_REQUIRE(variant != 2 || vec, "TMA-staged mask kernel needs sweeps of a multiple of 16 bytes and a 16-byte aligned echo pointer");
     if (vec && variant != 1) {
-        static bool attr_set = false;                   // one flag per element type (template instance)
-        constexpr int smem = mt_smem_bytes<T>();
-        if (!attr_set) {
-            RB_CUDA(cudaFuncSetAttribute(spoke_mask_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            attr_set = true;
+        const ThrArg thr = make_thr(threshold);
+        switch (ctx->opt_spoke_ring) {
+            case 1: RB_TRY((launch_mask_tma<T, 32 * 1024, 4>(ctx, echo, g, thr, mask, tile_count, ticket, stream))); break;
+            case 2: RB_TRY((launch_mask_tma<T, 32 * 1024, 3>(ctx, echo, g, thr, mask, tile_count, ticket, stream))); break;
+            case 3: RB_TRY((launch_mask_tma<T, 64 * 1024, 2>(ctx, echo, g, thr, mask, tile_count, ticket, stream))); break;
+            case 4: RB_TRY((launch_mask_tma<T, 16 * 1024, 4>(ctx, echo, g, thr, mask, tile_count, ticket, stream))); break;
+            default: RB_TRY((launch_mask_tma<T, 64 * 1024, 3>(ctx, echo, g, thr, mask, tile_count, ticket, stream))); break;
         }
-        const int64_t want_blocks = rb_div_up(g.total_tiles, Elem<T>::STAGE_TILES);
-        const unsigned blocks = (unsigned)(want_blocks < ctx->sm_count ? want_blocks : ctx->sm_count);
-        spoke_mask_tma_kernel<T><<<blocks, mt_threads<T>(), smem, stream>>>(echo, g, make_thr(threshold), mask, tile_count, ticket);
         ctx->spoke_last_variant = 2;
     } else {
         const int64_t want_blocks = rb_div_up(g.total_tiles, SK_WARPS);
         const int64_t max_blocks = (int64_t)ctx->sm_count * SK_CTAS_PER_SM;
         const unsigned blocks = (unsigned)(want_blocks < max_blocks ? want_blocks : max_blocks);
-        if (vec && sizeof(T) == 4) spoke_mask_kernel<T, sizeof(T) == 4><<<blocks, SK_THREADS, 0, stream>>>(echo, g, threshold, mask, tile_count);
-        else spoke_mask_kernel<T, false><<<blocks, SK_THREADS, 0, stream>>>(echo, g, threshold, mask, tile_count);
+        if (vec && sizeof(T) == 4) RB_CUDA(rb_launch(ctx, spoke_mask_kernel<T, sizeof(T) == 4>, dim3(blocks), dim3(SK_THREADS), 0, stream, echo, g, threshold, mask, tile_count));
+        else RB_CUDA(rb_launch(ctx, spoke_mask_kernel<T, false>, dim3(blocks), dim3(SK_THREADS), 0, stream, echo, g, threshold, mask, tile_count));
         ctx->spoke_last_variant = 1;
     }
     RB_LAUNCH_CHECK(ctx);
     if (prof) RB_CUDA(cudaEventRecord(ctx->spoke_ev[1], stream));
 
-    spoke_offsets_kernel<<<(unsigned)n_sweeps, SO_THREADS, 0, stream>>>(tile_count, tile_prefix, g.tiles_per_sweep, n_sweeps,
-                                                                       stride, sweep_total, sweep_base, done, ticket);
+    RB_CUDA(rb_launch(ctx, spoke_offsets_kernel, dim3((unsigned)n_sweeps), dim3(SO_THREADS), 0, stream, tile_count, tile_prefix, g.tiles_per_sweep, n_sweeps,
+                                                                       stride, sweep_total, sweep_base, done, ticket));
     RB_LAUNCH_CHECK(ctx);
     if (prof) RB_CUDA(cudaEventRecord(ctx->spoke_ev[2], stream));
 
@@ -743,7 +779,7 @@ int spoke_to_points_impl(rb_ctx* ctx, const T* echo, const float* cos_tab, const
         a.div_bins = make_fastdiv((uint32_t)n_bins);
         const int64_t eblocks = rb_div_up(a.total_groups, SK_WARPS);
         RB_REQUIRE(eblocks < (int64_t)1 << 31, "too many tiles in one batch; split the batch");
-        spoke_emit_kernel<T><<<(unsigned)eblocks, SK_THREADS, 0, stream>>>(a);
+        RB_CUDA(rb_launch(ctx, spoke_emit_kernel<T>, dim3((unsigned)eblocks), dim3(SK_THREADS), 0, stream, a));
         RB_LAUNCH_CHECK(ctx);
     }
     if (prof) RB_CUDA(cudaEventRecord(ctx->spoke_ev[3], stream));
@@ -772,7 +808,7 @@ extern "C" int rb_frame_offsets(rb_ctx* ctx, const int64_t* sweep_base, int64_t 
     RB_REQUIRE(n_frames >= 0 && gains_per_frame >= 1, "bad sizes");
     cudaStream_t stream = (cudaStream_t)stream_;
     unsigned blocks = (unsigned)rb_div_up(n_frames + 1, 256);
-    frame_offsets_kernel<<<blocks, 256, 0, stream>>>(sweep_base, n_frames, gains_per_frame, frame_off);
+    RB_CUDA(rb_launch(ctx, frame_offsets_kernel, dim3(blocks), dim3(256), 0, stream, sweep_base, n_frames, gains_per_frame, frame_off));
     RB_LAUNCH_CHECK(ctx);
     return RB_OK;
 }
@@ -784,7 +820,7 @@ extern "C" int rb_expand_frame_times(rb_ctx* ctx, const int64_t* frame_off, cons
     RB_REQUIRE(times, "times is NULL");
     cudaStream_t stream = (cudaStream_t)stream_;
     unsigned blocks = (unsigned)(n_frames < 4096 ? n_frames : 4096);
-    expand_times_kernel<<<blocks, 256, 0, stream>>>(frame_off, frame_ids, n_frames, times);
+    RB_CUDA(rb_launch(ctx, expand_times_kernel, dim3(blocks), dim3(256), 0, stream, frame_off, frame_ids, n_frames, times));
     RB_LAUNCH_CHECK(ctx);
     return RB_OK;
 }

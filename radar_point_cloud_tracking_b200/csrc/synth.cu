@@ -49,8 +49,8 @@ extern "C" int rb_synth_echo(rb_ctx* ctx, float* echo, int64_t n_sweeps, int n_s
     int64_t total = cells * n_sweeps;
     int blocks = (int)(rb_div_up(total, 256 * 8) < (int64_t)ctx->sm_count * 16 ? rb_div_up(total, 256 * 8)
                                                                                : (int64_t)ctx->sm_count * 16);
-    synth_kernel<<<blocks, 256, 0, stream>>>(echo, total, (int)cells, n_bins, gains_per_frame, first_frame, sweep_keys,
-                                             clutter_thr, rects, rect_off);
+    RB_CUDA(rb_launch(ctx, synth_kernel, dim3(blocks), dim3(256), 0, stream, echo, total, (int)cells, n_bins, gains_per_frame, first_frame, sweep_keys,
+                                             clutter_thr, rects, rect_off));
     RB_LAUNCH_CHECK(ctx);
     return RB_OK;
 }

@@ -53,6 +53,13 @@ class DetectionResult:
     count: Optional[torch.Tensor] = None
     isum: Optional[torch.Tensor] = None
 
+    def tensors(self):
+        """Every device tensor the result holds (for stream bookkeeping)."""
+        for b in (self.raw, self.points):
+            yield from (b.x, b.y, b.inten, b.gain, b.frame_off)
+        yield self.labels
+        yield from (t for t in (self.land, self.count, self.isum) if t is not None)
+
     def to_host(self) -> dict:
         """One device->host read of everything the consumers need."""
         n = self.points.n
@@ -260,24 +267,31 @@ class OverlappedPipeline:
             self._ctxs.append(st[0].ctx)
         return st
 
-    def _run(self, start_event, args, kwargs):
+    def _run(self, start_event, consumer, args, kwargs):
         pipe, stream = self._worker_state()
         with torch.cuda.stream(stream):
-            if start_event is not None:
-                stream.wait_event(start_event)
+            stream.wait_event(start_event)                  # inputs still being written on the caller's stream
             res = pipe.run_device(*args, **kwargs)          # ends with the block's final read-back (stream sync)
             done = torch.cuda.Event()
             done.record(stream)
+        # the outputs were allocated in the worker stream's pool but are consumed (and freed) on the caller's stream:
+        # tell the caching allocator, or a later block could get their memory while the consumer still reads it
+        for t in res.tensors():
+            t.record_stream(consumer)
         return res, done, pipe.ctx.launch_count()
 
     def map(self, blocks, start_event=None, keep: bool = True) -> List[DetectionResult]:
-        """``blocks``: iterable of ``(args, kwargs)`` for :meth:`DetectionPipeline.run_device`. Returns the results
+        """``blocks``: iterable of ``(args, kwargs)`` for :meth:`DetectionPipeline.run_device`. Every block starts after
+        ``start_event`` (default: everything queued on the current stream at the time of the call). Returns the results
         in order (``keep=False``: only the last one - earlier results are released as soon as they are complete,
         so their buffers are recycled by the following blocks instead of growing the pool); the current stream
         waits for all of them."""
-        futs = [self._pool.submit(self._run, start_event, a, k) for a, k in blocks]
-        out = []
         cur = torch.cuda.current_stream(self.device)
+        if start_event is None:                             # order every block after what the caller has queued so far
+            start_event = torch.cuda.Event()
+            start_event.record(cur)
+        futs = [self._pool.submit(self._run, start_event, cur, a, k) for a, k in blocks]
+        out = []
         for i in range(len(futs)):
             res, done, _ = futs[i].result()
             futs[i] = None

@@ -77,6 +77,11 @@ def test_csv_variants(trk, tmp_path):
         r = rows[5].split(",")
         r[20] = field
         _same(trk, variant(name, rows[:5] + [",".join(r)] + rows[6:]), E, expect_device=False)
+    # carriage returns that are not part of "\r\n" end a line for pandas: a CR-only file and a stray CR inside a row
+    _same(trk, variant("cr_only.csv", rows, "\r"), E, expect_device=False)
+    r = rows[6].split(",")
+    r[2] = "3\r"
+    _same(trk, variant("stray_cr.csv", rows[:6] + [",".join(r)] + rows[7:]), E, expect_device=False)
     _same(trk, variant("blank_line.csv", rows[:4] + [""] + rows[4:]), E, expect_device=False)
     _same(trk, variant("short_row.csv", rows[:4] + [",".join(rows[4].split(",")[:-3])] + rows[5:]), E, expect_device=False)
 
