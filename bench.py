@@ -31,7 +31,27 @@ sys.path.insert(0, str(REPO))
 
 METRIC = "fused_frames_per_s_through_stdbscan"
 UNIT = "frames/s"
-WORKLOAD = "config3-shard: gain-fused 40/50/75, 2048x1024 sweeps, land filter, ST-DBSCAN eps 8/2/15 (thr 10, stride 4)"
+
+# BASELINE.json configs 2-5 as bench workloads (config 1 is the reference's CPU-runnable case: a parity test, not a bench
+# line). `cfg` = what differs from the reference defaults (thr 10 / stride 4 / eps 8, 2, 15, land filter on);
+# `frames` / `e2e_frames` = default block lengths; `cpu_*` = the bounded sample of the reference arm: frames per worker
+# and the divisor of the angular sector it takes (1 = whole sweeps; config 4's neighbour lists do not fit a host at full
+# density: SURVEY 8(d) "a documented subset ... and/or an angular sector").
+WORKLOADS = {
+    "config3": dict(desc="config3-shard: gain-fused 40/50/75, 2048x1024 sweeps, land filter, ST-DBSCAN eps 8/2/15 (thr 10, stride 4)",
+                    gains=(40, 50, 75), cfg={}, frames=1024, e2e_frames=128, cpu_frames=64, cpu_sector=1),
+    "config2": dict(desc="config2: single-gain (50) stacked cloud of 500 sweeps, 3-D ST-DBSCAN on (x, y, intensity) with time = frame "
+                         "index, eps 5/1/10, no land filter (3_stdbscan_point_clouds.py:177-182), thr 10 / stride 4",
+                    gains=(50,), cfg=dict(land_filter=False, eps_space=5.0, eps_time=1.0, min_samples=10, cluster_3d=True),
+                    frames=500, e2e_frames=250, cpu_frames=32, cpu_sector=1),
+    "config4": dict(desc="config4: dense clutter stress, gain-fused 40/50/75, thr 2 / stride 2 / eps 12 (~2.2 M points per frame), "
+                         "land filter, ST-DBSCAN eps 12/2/15",
+                    gains=(40, 50, 75), cfg=dict(intensity_threshold=2.0, point_stride=2, eps_space=12.0),
+                    frames=64, e2e_frames=32, cpu_frames=11, cpu_sector=1024),
+    "config5": dict(desc="config5: long horizon, gain-fused 40/50/75, land filter, ST-DBSCAN eps 8/5/15 (eps_time 5: an 11-frame window, "
+                         "5-frame halo between time shards), thr 10 / stride 4",
+                    gains=(40, 50, 75), cfg=dict(eps_time=5.0), frames=1024, e2e_frames=128, cpu_frames=64, cpu_sector=1),
+}
 
 
 def parse_args():
@@ -41,9 +61,11 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shard-in-flight", type=int, default=3, help="N>1: blocks interleaved per rank (one host thread, one communicator)")
-    ap.add_argument("--frames-per-step", type=int, default=1024, help="frames per rank and step (device-resident `value`)")
-    ap.add_argument("--e2e-frames", type=int, default=128, help="frames per rank and step of the end-to-end measurement (bounds the "
-                    "pinned host buffers: 3.2 GB float32 per rank at 128)")
+    ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS), help="BASELINE.json configuration (default: config 3, the "
+                    "one the metric is quoted on)")
+    ap.add_argument("--frames-per-step", type=int, default=0, help="frames per rank and step (device-resident `value`); 0 = the workload's default")
+    ap.add_argument("--e2e-frames", type=int, default=0, help="frames per rank and step of the end-to-end measurement (bounds the "
+                    "pinned host buffers: 3.2 GB float32 per rank at 128); 0 = the workload's default")
     ap.add_argument("--spokes", type=int, default=2048)
     ap.add_argument("--bins", type=int, default=1024)
     ap.add_argument("--seed", type=int, default=2025)
@@ -52,9 +74,23 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--streams", type=int, default=3, help="N=1: blocks in flight (host threads x CUDA streams x library contexts) "
                     "for `value`; the time-sharded path (N>1) always has one block in flight per rank")
-    ap.add_argument("--cpu-frames", type=int, default=64, help="frames per CPU worker in the reference/cpu_baseline sample")
+    ap.add_argument("--cpu-frames", type=int, default=0, help="frames per CPU worker in the reference/cpu_baseline sample; 0 = the workload's default")
     ap.add_argument("--shard-profile", action="store_true", help="N>1: print per-stage wall-clock of the sharded driver to stderr")
-    return ap.parse_args()
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    args.frames_per_step = args.frames_per_step or w["frames"]
+    args.e2e_frames = args.e2e_frames or w["e2e_frames"]
+    args.cpu_frames = args.cpu_frames or w["cpu_frames"]
+    return args
+
+
+def workload_config(args) -> dict:
+    """The `config` object of the JSON line: identical keys and values in both arms (ours / reference)."""
+    w = WORKLOADS[args.workload]
+    p = dict(intensity_threshold=10.0, point_stride=4, land_filter=True, eps_space=8.0, eps_time=2.0, min_samples=15, cluster_3d=False)
+    p.update(w["cfg"])
+    return {"workload": w["desc"], "name": args.workload, "spokes": args.spokes, "bins": args.bins, "gains": list(w["gains"]),
+            "seed": args.seed, "clutter_p": args.clutter_p, "params": p}
 
 
 def load_traffic(frames_per_launch: int):
@@ -167,33 +203,43 @@ def cpu_block_sample(args_tuple):
     land filter and the reference's sequential ST-DBSCAN (numpy + scikit-learn BallTree + the reference's
     Python expansion loop). Input generation and imports are outside the timed region.
     Returns (seconds per stage, points, clusters)."""
-    seed, first_frame, frames, total_frames, spokes, bins, clutter_p = args_tuple
+    seed, first_frame, frames, total_frames, spokes, bins, clutter_p, gains, sector, prm = args_tuple
+    prm = dict(prm)
     from oracle import numpy_oracle as O
     from radar_point_cloud_tracking_b200 import synthetic as syn
 
-    spec = syn.SweepSpec(seed=seed, frames=max(total_frames, first_frame + frames), spokes=spokes, bins=bins, clutter_p=clutter_p)
+    spec = syn.SweepSpec(seed=seed, frames=max(total_frames, first_frame + frames), spokes=spokes, bins=bins, clutter_p=clutter_p,
+                         gains=tuple(gains))
     key = args_tuple
+    keep_spokes = max(1, spokes // max(sector, 1))                         # the angular sector of the sample (all spokes when 1)
     if key not in _CPU_CACHE:
         _CPU_CACHE.clear()
         rects = syn.build_rects(spec)
-        _CPU_CACHE[key] = [[syn.synth_sweep(spec, first_frame + f, g, rects) for g in range(len(spec.gains))] for f in range(frames)]
+        _CPU_CACHE[key] = [[np.ascontiguousarray(syn.synth_sweep(spec, first_frame + f, g, rects)[:keep_spokes])
+                            for g in range(len(spec.gains))] for f in range(frames)]
         O._query_radius(np.zeros((4, 2), np.float32), 1.0)               # import scikit-learn before the clock starts
     echo = _CPU_CACHE[key]
-    ang, scale = spec.angle_units(), spec.scale()
+    ang, scale = spec.angle_units()[:keep_spokes], spec.scale()[:keep_spokes]
     t0 = time.perf_counter()
     pts = []
     for f in range(frames):
-        per_gain = {gain: O.sweep_to_points(echo[f][gi], ang, scale, 10.0, 4) for gi, gain in enumerate(spec.gains)}
+        per_gain = {gain: O.sweep_to_points(echo[f][gi], ang, scale, prm["intensity_threshold"], prm["point_stride"])
+                    for gi, gain in enumerate(spec.gains)}
         fused = O.fuse_concat(per_gain)
         pts.append(fused[0] if fused is not None else np.zeros((0, 3), np.float32))
     t1 = time.perf_counter()
     built = [p for p in pts if len(p)]
-    if len(built) > 10:
+    if prm["land_filter"] and len(built) > 10:
         count, isum, edges = O.occupancy_grid(built)
         land = O.land_cells(count, isum, len(built))
         pts = [p[O.land_keep_mask(p, land, edges)] if len(p) else p for p in pts]
     t2 = time.perf_counter()
-    labels, _ = O.st_dbscan_frames(list(enumerate(pts)), 8.0, 2.0, 15, sequential=True)
+    if prm["cluster_3d"]:                                                 # T3:177-182: coords = (x, y, z), flat labels
+        coords = np.concatenate(pts) if pts else np.zeros((0, 3), np.float32)
+        times = np.concatenate([np.full(len(p), f, np.float32) for f, p in enumerate(pts)]) if pts else np.zeros(0, np.float32)
+        labels = O.st_dbscan_sequential(coords, times, prm["eps_space"], prm["eps_time"], prm["min_samples"])
+    else:
+        labels, _ = O.st_dbscan_frames(list(enumerate(pts)), prm["eps_space"], prm["eps_time"], prm["min_samples"], sequential=True)
     t3 = time.perf_counter()
     return (t1 - t0, t2 - t1, t3 - t2, int(sum(len(p) for p in pts)), int(labels.max() + 1 if len(labels) else 0))
 
@@ -208,8 +254,12 @@ def run_cpu_reference(args, steps: int, warmup: int, workers: int, frames: int =
     ctx = mp.get_context("spawn")
     times, detail = [], None
     total = frames * workers
+    w = WORKLOADS[args.workload]
+    sector = int(w["cpu_sector"])
+    prm = tuple(sorted(workload_config(args)["params"].items()))
     with ctx.Pool(workers) as pool:
-        jobs = [(args.seed, i * frames, frames, total, args.spokes, args.bins, args.clutter_p) for i in range(workers)]
+        jobs = [(args.seed, i * frames, frames, total, args.spokes, args.bins, args.clutter_p, tuple(w["gains"]), sector, prm)
+                for i in range(workers)]
         for it in range(warmup + steps):
             res = pool.map(cpu_block_sample, jobs, chunksize=1)
             dt = max(r[0] + r[1] + r[2] for r in res)
@@ -217,8 +267,12 @@ def run_cpu_reference(args, steps: int, warmup: int, workers: int, frames: int =
                 times.append(dt)
                 detail = res
     mean_t = sum(times) / len(times)
-    return {"value": frames * workers / mean_t, "ms_per_step": mean_t * 1e3, "cores": workers,
-            "sample": f"{workers} worker(s) x {frames} consecutive full-size frames ({args.spokes}x{args.bins} x 3 gains) of the same "
+    what = (f"consecutive full-size frames ({args.spokes}x{args.bins} x {len(w['gains'])} gain(s))" if sector == 1 else
+            f"consecutive frames cut to an angular sector of 1/{sector} of the spokes ({max(1, args.spokes // sector)}x{args.bins} x "
+            f"{len(w['gains'])} gains, at the recording's true density; value = frames x 1/{sector} per second, which FAVOURS the CPU: "
+            f"its cost grows faster than the sector)")
+    return {"value": frames * workers / sector / mean_t, "ms_per_step": mean_t * 1e3, "cores": workers,
+            "sample": f"{workers} worker(s) x {frames} {what} of the same "
                       f"synthetic recording, numpy/scikit-learn oracle port of T4 incl. the reference's sequential ST-DBSCAN "
                       f"expansion; input generation untimed; the reference's cost per frame grows with the block length "
                       f"(spatial-only BallTree over all frames, T4:474-475)",
@@ -227,6 +281,48 @@ def run_cpu_reference(args, steps: int, warmup: int, workers: int, frames: int =
 
 
 # ------------------------------------------------------------------------------------ ours
+def check_sharded_labels(args, cfg, wl, rank, world, device):
+    """Before anything is timed at N > 1: a small recording (same workload parameters, 12 frames x 512 spokes per rank)
+    through the time-sharded path on all ranks AND, on rank 0, through the single-GPU path as one block; labels and
+    points must be identical id for id. The JSON line carries the outcome (`sharded_labels_identical`)."""
+    import torch
+    import torch.distributed as dist
+
+    from radar_point_cloud_tracking_b200 import device as dev
+    from radar_point_cloud_tracking_b200 import synthetic as syn
+    from radar_point_cloud_tracking_b200.pipeline import DetectionPipeline
+    from radar_point_cloud_tracking_b200.sharded import ShardedDetection
+
+    Bc = 12
+    spec = syn.SweepSpec(seed=args.seed + 1, frames=Bc * world, spokes=512, bins=args.bins, clutter_p=max(args.clutter_p, 0.004),
+                         gains=tuple(wl["gains"]))
+    sd = ShardedDetection(cfg, rank, world, device.index)
+    first = rank * Bc
+    echo = dev.synth_echo(spec, first_frame=first, n_frames=Bc, device=device)
+    tabs = [torch.from_numpy(t).to(device) for t in sd.base.spoke_tables(spec.angle_units(), spec.scale(), Bc, spec.bins)]
+    res = sd.run_device(echo, *tabs, np.arange(first, first + Bc))
+    host = res.to_host()
+    gathered = [None] * world
+    dist.gather_object({"labels": host["labels"], "points": host["points"], "ncl": res.n_clusters}, gathered if rank == 0 else None, dst=0)
+    out = None
+    if rank == 0:
+        pipe = DetectionPipeline(cfg, device.index)
+        full = dev.synth_echo(spec, device=device)
+        tabs = [torch.from_numpy(t).to(device) for t in pipe.spoke_tables(spec.angle_units(), spec.scale(), spec.frames, spec.bins)]
+        want = pipe.run_device(full, *tabs)
+        wh = want.to_host()
+        got_l = np.concatenate([g["labels"] for g in gathered])
+        got_p = np.concatenate([g["points"] for g in gathered])
+        same = bool(np.array_equal(got_p, wh["points"]) and np.array_equal(got_l, wh["labels"]) and
+                    all(g["ncl"] == want.n_clusters for g in gathered))
+        out = {"identical": same, "points": int(len(got_l)), "clusters": int(want.n_clusters), "frames": int(spec.frames),
+               "what": f"{Bc} frames x 512 spokes per rank, workload parameters, sharded x{world} vs one block on rank 0"}
+    flag = torch.tensor([1 if (out is None or out["identical"]) else 0], device=device)
+    dist.broadcast(flag, src=0)
+    torch.cuda.synchronize()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -246,12 +342,18 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
 
     B = args.frames_per_step
-    G = 3
-    spec = syn.SweepSpec(seed=args.seed, frames=B * world, spokes=args.spokes, bins=args.bins, clutter_p=args.clutter_p)
-    cfg = DetectionConfig()
+    wl = WORKLOADS[args.workload]
+    G = len(wl["gains"])
+    spec = syn.SweepSpec(seed=args.seed, frames=B * world, spokes=args.spokes, bins=args.bins, clutter_p=args.clutter_p,
+                         gains=tuple(wl["gains"]))
+    cfg = DetectionConfig(gains=tuple(wl["gains"]), **wl["cfg"])
+    sharded_check = None
     if world > 1:
+        if cfg.cluster_3d:
+            raise SystemExit("bench.py: config2 (3-D single-gain clustering) is a single-GPU workload (BASELINE.json: '1 B200')")
         from radar_point_cloud_tracking_b200.sharded import ShardedDetection
         pipe = ShardedDetection(cfg, rank, world, device.index)
+        sharded_check = check_sharded_labels(args, cfg, wl, rank, world, device)
     else:
         pipe = DetectionPipeline(cfg, device.index)
     first = rank * B
@@ -410,10 +512,10 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (points) / f64 (neighbour test) / i32 (labels)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "spokes": args.spokes, "bins": args.bins,
-                   "gains": [40, 50, 75], "seed": args.seed, "clutter_p": args.clutter_p,
-                   "parallelism": f"time-sharded x{world}, {args.shard_in_flight} blocks interleaved per rank (one communicator)" if world > 1 else f"single GPU, {args.streams if overlapped else 1} block(s) in flight",
-                   "l2_policy": "inputs larger than L2 (echo block %.2f GB per step)" % (echo.numel() * 4 / 1e9)},
+        "config": workload_config(args),
+        "run": {"frames_per_step_per_gpu": B,
+                "parallelism": f"time-sharded x{world}, {args.shard_in_flight} blocks interleaved per rank (one communicator)" if world > 1 else f"single GPU, {args.streams if overlapped else 1} block(s) in flight",
+                "l2_policy": "inputs larger than L2 (echo block %.2f GB per step)" % (echo.numel() * 4 / 1e9)},
         "points_per_s": n_raw_all * args.steps / (ms * 1e-3),
         "points_per_step": {"after_stride": n_raw_all, "after_land_filter": n_pts_all, "clusters": int(pts_t[2])},
         "roofline": {"bound": "hbm", "kernel": "spoke_mask_tma_kernel", "achieved": achieved, "peak": hbm_peak,
@@ -438,6 +540,9 @@ def run_ours(args):
         "gpu_launches": launches,
         "clocks": clocks.summary(c0, c1),
     }
+    if sharded_check is not None:
+        line["sharded_labels_identical"] = sharded_check["identical"]
+        line["sharded_check"] = sharded_check
     if e2e:
         line["e2e"] = e2e
         line["e2e_uint8_echoes"] = e2e_u8
@@ -455,7 +560,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    workers = max(1, min(os.cpu_count() or 1, 8))
+    workers = max(1, min(os.cpu_count() or 1, 32))
     steps = max(1, min(args.steps, 2))
     warm = min(args.warmup, 1)
     cb = run_cpu_reference(args, steps=steps, warmup=warm, workers=workers, frames=args.cpu_frames)
@@ -463,8 +568,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 (numpy, scikit-learn)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "spokes": args.spokes, "bins": args.bins, "gains": [40, 50, 75],
-                   "seed": args.seed, "clutter_p": args.clutter_p},
+        "config": workload_config(args),
         "cpu_baseline": {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "port", "sample": cb["sample"],
                          "stage_seconds": cb["stage_seconds"], "host_cpus": os.cpu_count()},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -257,6 +257,8 @@ typedef struct rb_detect_params {
     int32_t min_samples;
     int32_t cluster;                /* 0 = stop after the land filter */
     int32_t echo_u8;                /* 1 = `echo` points at uint8 cells (rb_spoke_to_points_u8) */
+    int32_t cluster_3d;             /* 1 = cluster on (x, y, z = intensity) like 3_stdbscan_point_clouds.py (T3:177-182:
+                                       coords = column_stack((x, y, z))) instead of (x, y) */
 } rb_detect_params;
 
 typedef struct rb_detect_buffers {

@@ -31,7 +31,8 @@ class DetectParams(C.Structure):
     _fields_ = [("n_frames", c_i32), ("gains_per_frame", c_i32), ("n_spokes", c_i32), ("n_bins", c_i32),
                 ("intensity_threshold", c_f32), ("point_stride", c_i32), ("land_filter", c_i32), ("land_min_frames", c_i32),
                 ("land_resolution", c_f64), ("land_persistence", c_f64), ("land_min_intensity", c_f64),
-                ("eps_space", c_f64), ("eps_time", c_f32), ("min_samples", c_i32), ("cluster", c_i32), ("echo_u8", c_i32)]
+                ("eps_space", c_f64), ("eps_time", c_f32), ("min_samples", c_i32), ("cluster", c_i32), ("echo_u8", c_i32),
+                ("cluster_3d", c_i32)]
 
 
 class DetectBuffers(C.Structure):

@@ -1,5 +1,6 @@
 // Context, error text, scratch arena and the device-wide exclusive scan used by the other stages.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -51,6 +52,17 @@ extern "C" int rb_create(int device, rb_ctx** out) {
         rb_set_error("rb_create: cudaMallocHost -> %s", cudaGetErrorString(e));
         delete ctx;
         return RB_ERR_NOMEM;
+    }
+    // diagnostic defaults from the environment (experiments that must reach every context of a process, worker threads'
+    // included): RB_OPT_<NAME>=<integer> is rb_set_option(ctx, "<name>", value)
+    static const char* const env_opts[] = {"carveout", "spoke_ring", "spoke_l2_hint", "dbscan_mode", "spoke_mask_variant"};
+    for (const char* name : env_opts) {
+        char var[64] = "RB_OPT_";
+        size_t k = strlen(var);
+        for (const char* c = name; *c && k + 1 < sizeof var; ++c) var[k++] = (char)(*c >= 'a' && *c <= 'z' ? *c - 32 : *c);
+        var[k] = 0;
+        const char* v = getenv(var);
+        if (v && *v && rb_set_option(ctx, name, atoll(v)) != RB_OK) { rb_destroy(ctx); return RB_ERR_ARG; }
     }
     *out = ctx;
     return RB_OK;

@@ -161,7 +161,7 @@ extern "C" int rb_detect_block(rb_ctx* ctx, const float* echo, const float* cos_
     }
 
     // ---- a4-a6: land / stationary persistence filter ----------------------------------------------------------
-    const float *px = buf->x, *py = buf->y;
+    const float *px = buf->x, *py = buf->y, *pz = buf->inten;
     const int64_t* p_off = buf->frame_off;
     int64_t n_pts = n_raw;
     if (prm->land_filter && n_raw > 0 && built > prm->land_min_frames) {
@@ -197,7 +197,7 @@ extern "C" int rb_detect_block(rb_ctx* ctx, const float* echo, const float* cos_
         n_pts = h_off[0];
         res->land_applied = 1;
         res->filtered_is_raw = 0;
-        px = buf->fx; py = buf->fy;
+        px = buf->fx; py = buf->fy; pz = buf->finten;
         p_off = buf->f_frame_off;
     }
     res->n_points = n_pts;
@@ -218,8 +218,9 @@ extern "C" int rb_detect_block(rb_ctx* ctx, const float* echo, const float* cos_
         hint.lo[2] = hint.hi[2] = 0.f;
         hint.lo[3] = fmin_id; hint.hi[3] = fmax_id;
         hint.times_integer = ids_integer;
-        RB_TRY(rb_stdbscan_enqueue(ctx, px, py, nullptr, 1, d_times, n_pts, prm->eps_space, prm->eps_time, prm->min_samples,
-                                   buf->labels, nullptr, &hint, stream_));
+        // 3-D (z = intensity): the intensity range is not known on the host, so the plan measures its own bounds (one more sync)
+        RB_TRY(rb_stdbscan_enqueue(ctx, px, py, prm->cluster_3d ? pz : nullptr, 1, d_times, n_pts, prm->eps_space, prm->eps_time,
+                                   prm->min_samples, buf->labels, nullptr, prm->cluster_3d ? nullptr : &hint, stream_));
         int64_t ncl = 0;
         RB_TRY(rb_stdbscan_fetch_stats(ctx, &ncl, stream_));             // read-back 3 (final)
         res->n_clusters = ncl;

@@ -38,6 +38,7 @@ class DetectionConfig:
     eps_time: float = trk.EPS_TIME
     min_samples: int = trk.MIN_SAMPLES
     angle_scale: float = trk.ANGLE_SCALE
+    cluster_3d: bool = False                     # cluster on (x, y, z = intensity) like 3_stdbscan_point_clouds.py (T3:177)
 
 
 @dataclass
@@ -155,7 +156,8 @@ class DetectionPipeline:
                                 land_filter=int(bool(cfg.land_filter)), land_min_frames=int(cfg.land_min_frames),
                                 land_resolution=float(cfg.land_resolution), land_persistence=float(cfg.land_persistence),
                                 land_min_intensity=float(cfg.land_min_intensity), eps_space=float(cfg.eps_space),
-                                eps_time=float(np.float32(cfg.eps_time)), min_samples=int(cfg.min_samples), cluster=int(bool(cluster)))
+                                eps_time=float(np.float32(cfg.eps_time)), min_samples=int(cfg.min_samples), cluster=int(bool(cluster)),
+                                cluster_3d=int(bool(cfg.cluster_3d)))
         cap = self._cap_hint or dev.default_capacity(F * G, S, E, cfg.point_stride)
         echo3 = echo.view(F * G, S, E)
         for _ in range(4):
@@ -214,8 +216,8 @@ class DetectionPipeline:
         n_clusters = 0
         if cluster and pts.n > 0:
             times = dev.expand_frame_times(pts.frame_off, torch.from_numpy(ids.astype(np.float32)).to(d), pts.n)
-            labels, n_clusters = dev.stdbscan(pts.x, pts.y, None, times, cfg.eps_space, cfg.eps_time,
-                                              cfg.min_samples, stride=1, n=pts.n)
+            labels, n_clusters = dev.stdbscan(pts.x, pts.y, pts.inten if cfg.cluster_3d else None, times, cfg.eps_space,
+                                              cfg.eps_time, cfg.min_samples, stride=1, n=pts.n)
         return DetectionResult(ids, raw, pts, labels, n_clusters, land, edges, count, isum)
 
     # ---- host entry (the call a user of the reference makes with parsed sweeps) -----------------

@@ -215,14 +215,18 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("world,cfg_kw", [(2, {}), (3, {"eps_time": 1.0, "min_samples": 8}),
-                                          (2, {"eps_time": 0.5, "land_filter": False}),
-                                          (4, {"eps_time": 3.0, "min_samples": 10})])      # shard = halo = 3 frames
-def test_sharded_equals_single_process(tmp_path, world, cfg_kw):
+SPEC_LONG = dict(SPEC, frames=22, seed=23)       # 4 ranks x 5 frames (+2 on the last): room for a 5-frame halo
+
+
+@pytest.mark.parametrize("world,cfg_kw,spec_kw", [(2, {}, SPEC), (3, {"eps_time": 1.0, "min_samples": 8}, SPEC),
+                                                  (2, {"eps_time": 0.5, "land_filter": False}, SPEC),
+                                                  (4, {"eps_time": 3.0, "min_samples": 10}, SPEC),      # shard = halo = 3 frames
+                                                  (4, {"eps_time": 5.0}, SPEC_LONG)])                   # BASELINE config 5: halo 5 = shard
+def test_sharded_equals_single_process(tmp_path, world, cfg_kw, spec_kw):
     cfg = DetectionConfig(**cfg_kw)
-    spec = syn.SweepSpec(**SPEC)
+    spec = syn.SweepSpec(**spec_kw)
     _, frames, want = expected(spec, cfg)
-    mp.spawn(_worker, args=(world, _free_port(), SPEC, cfg_kw, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), spec_kw, cfg_kw, str(tmp_path)), nprocs=world, join=True)
     got, xs, ncl = [], [], set()
     for r in range(world):
         d = np.load(tmp_path / f"rank{r}.npz")

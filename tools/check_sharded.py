@@ -1,7 +1,7 @@
 """Parity of the time-sharded path on real GPUs: run under torchrun with N ranks; every rank runs its shard,
 rank 0 also runs the whole recording on one GPU and compares labels / points id for id.
 
-    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/check_sharded.py [frames_per_rank]
+    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/check_sharded.py [frames_per_rank] [eps_time]
 """
 import os
 import sys
@@ -22,7 +22,7 @@ device = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=device)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 12
 spec = syn.SweepSpec(seed=31, frames=B * world, spokes=512, bins=1024, clutter_p=0.004)
-cfg = DetectionConfig()
+cfg = DetectionConfig(eps_time=float(sys.argv[2])) if len(sys.argv) > 2 else DetectionConfig()
 sd = ShardedDetection(cfg, rank, world, local)
 sd._cap_hint = 1000 + 7 * rank          # far too small: the first block must repeat its spoke stage on every rank
 first = rank * B
@@ -44,7 +44,7 @@ if rank == 0:
     got_p = np.concatenate([g["points"] for g in gathered])
     ok = np.array_equal(got_p, want["points"]) and np.array_equal(got_l, want["labels"]) and \
         all(g["ncl"] == ref.n_clusters for g in gathered)
-    print(f"sharded x{world}: {len(got_l)} points, {ref.n_clusters} clusters, halo points per rank "
+    print(f"sharded x{world} (eps_time {cfg.eps_time}): {len(got_l)} points, {ref.n_clusters} clusters, halo points per rank "
           f"{[g['halo'] for g in gathered]} -> {'IDENTICAL to single GPU' if ok else 'MISMATCH'}")
 # interleaved blocks (run_blocks: two generators in flight per rank): same labels per block
 tabs = tuple(torch.from_numpy(t).to(device) for t in sd.base.spoke_tables(spec.angle_units(), spec.scale(), B, spec.bins))
