@@ -668,7 +668,8 @@ template <typename T, int STAGE_BYTES, int STAGES>
 int launch_mask_tma(rb_ctx* ctx, const T* echo, const SpokeGeom& g, const ThrArg& thr, uint32_t* mask, uint32_t* tile_count,
                     unsigned* ticket, cudaStream_t stream) {
     constexpr int smem = mt_smem_bytes<T, STAGE_BYTES, STAGES>();
-    constexpr int ring_id = (STAGE_BYTES == 64 * 1024 ? (STAGES == 3 ? 0 : 3) : STAGE_BYTES == 32 * 1024 ? (STAGES == 4 ? 1 : 2) : 4);
+    constexpr int ring_id = STAGE_BYTES == 64 * 1024 ? (STAGES == 3 ? 0 : 3) : STAGE_BYTES == 32 * 1024 ? (STAGES == 4 ? 1 : 2) :
+                            STAGE_BYTES == 48 * 1024 ? (STAGES == 3 ? 5 : 6) : STAGE_BYTES == 80 * 1024 ? 7 : 4;
     const unsigned bit = 1u << (ring_id * 2 + (sizeof(T) == 1 ? 1 : 0));
     auto kernel = spoke_mask_tma_kernel<T, STAGE_BYTES, STAGES>;
     if (!(ctx->attr_spoke_mask & bit)) {
@@ -745,6 +746,9 @@ int spoke_to_points_impl(rb_ctx* ctx, const T* echo, const float* cos_tab, const
             case 2: RB_TRY((launch_mask_tma<T, 32 * 1024, 3>(ctx, echo, g, thr, mask, tile_count, ticket, stream))); break;
             case 3: RB_TRY((launch_mask_tma<T, 64 * 1024, 2>(ctx, echo, g, thr, mask, tile_count, ticket, stream))); break;
             case 4: RB_TRY((launch_mask_tma<T, 16 * 1024, 4>(ctx, echo, g, thr, mask, tile_count, ticket, stream))); break;
+            case 5: RB_TRY((launch_mask_tma<T, 48 * 1024, 3>(ctx, echo, g, thr, mask, tile_count, ticket, stream))); break;
+            case 6: RB_TRY((launch_mask_tma<T, 48 * 1024, 2>(ctx, echo, g, thr, mask, tile_count, ticket, stream))); break;
+            case 7: RB_TRY((launch_mask_tma<T, 80 * 1024, 2>(ctx, echo, g, thr, mask, tile_count, ticket, stream))); break;
             default: RB_TRY((launch_mask_tma<T, 64 * 1024, 3>(ctx, echo, g, thr, mask, tile_count, ticket, stream))); break;
         }
         ctx->spoke_last_variant = 2;

@@ -1,0 +1,33 @@
+#!/bin/bash
+# Round-2 experiment, part 2: the mask kernel's TMA ring with the DRIVER's carve-outs (part 1 showed that a forced common
+# carve-out costs the other kernels their L1 and gains nothing, while a ring that leaves shared memory free lets their
+# CTAs become resident beside it). Usage (GPU box): bash tools/sweep_ring.sh > gpurun_out/sweep_ring.txt
+cd "$(dirname "$0")/.."
+run() {
+    label="$1"; shift
+    out=$(env "$@" python bench.py --no-e2e --no-cpu-baseline --steps ${STEPS:-24} --warmup 3 ${EXTRA} 2>/dev/null | tail -1)
+    python - "$label" "$out" <<'PY'
+import json, sys
+label, line = sys.argv[1], sys.argv[2]
+try:
+    d = json.loads(line)
+    r = d["roofline"]
+    print(f"{label:44s} value {d['value']:9.0f} frames/s  step {d['ms_per_step']:6.3f} ms  mask alone {r['kernel_ms']:6.3f} ms ({r['achieved']:6.0f} GB/s)  "
+          f"emit {r['stage']['kernels_ms']['spoke_emit_kernel']:5.3f} ms  sm {d['clocks']['sm_mhz']}", flush=True)
+except Exception as e:
+    print(f"{label:44s} FAILED: {e}: {line[:200]}", flush=True)
+PY
+}
+run "64Kx3 (197 KB), 3 in flight"   RB_OPT_SPOKE_RING=0
+run "80Kx2 (164 KB), 3 in flight"   RB_OPT_SPOKE_RING=7
+run "48Kx3 (148 KB), 3 in flight"   RB_OPT_SPOKE_RING=5
+run "64Kx2 (131 KB), 3 in flight"   RB_OPT_SPOKE_RING=3
+run "48Kx2 ( 98 KB), 3 in flight"   RB_OPT_SPOKE_RING=6
+run "32Kx3 ( 98 KB), 3 in flight"   RB_OPT_SPOKE_RING=2
+run "64Kx2 + l2 hint, 3 in flight"  RB_OPT_SPOKE_RING=3 RB_OPT_SPOKE_L2_HINT=1
+run "48Kx3 + l2 hint, 3 in flight"  RB_OPT_SPOKE_RING=5 RB_OPT_SPOKE_L2_HINT=1
+EXTRA="--streams 2" run "64Kx2, 2 in flight"  RB_OPT_SPOKE_RING=3
+EXTRA="--streams 4" run "64Kx2, 4 in flight"  RB_OPT_SPOKE_RING=3
+EXTRA="--streams 4" run "48Kx3, 4 in flight"  RB_OPT_SPOKE_RING=5
+EXTRA="--streams 4" run "48Kx2, 4 in flight"  RB_OPT_SPOKE_RING=6
+EXTRA="--streams 6" run "64Kx2, 6 in flight"  RB_OPT_SPOKE_RING=3
