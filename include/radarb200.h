@@ -281,6 +281,33 @@ int rb_detect_block(rb_ctx* ctx, const float* echo, const float* cos_tab, const 
                     const int32_t* sweep_gain, const float* frame_ids, const rb_detect_params* prm,
                     const rb_detect_buffers* buf, rb_detect_result* res, void* stream);
 
+/* ---- a8: per-frame cluster records on the device (SURVEY section 8 f, rank 1) -----------------------------------
+ * What st_dbscan builds after the labels are known (T4:511-534) and what ObjectTracker.update (T4:553) and
+ * save_tracking_results (T4:873-886) read: for every (frame, cluster id) that occurs - a SEGMENT - the number of points,
+ * centroid = np.mean(points, axis=0) and mean intensity = np.mean(intensities), bit for bit in numpy's float32 arithmetic
+ * (rows added in order per column; numpy's pairwise sum for the 1-D intensities; float32 division), plus the points grouped
+ * by segment in their original order (a stable partition), so the host's per-cluster arrays are slices instead of masks.
+ *   x, y, inten float32[n], labels int32[n] (-1 = noise, ids < n_clusters), frame_off int64[n_frames + 1]: device.
+ *   Table columns (device, capacity cap_segments), segments ordered by frame, then label (-1 first):
+ *     frame  int32  index of the frame in the block          label  int32  cluster id, -1 = the frame's noise entry
+ *     first  int32  index INSIDE the frame of the segment's first point (the order of first occurrences is what decides
+ *                   the iteration order of `set(frame_labels)`, T4:518-521: the host replays it)
+ *     count  int32  points                                   start  int64  offset in gx / gy / gi (-1 for noise)
+ *     cx, cy, mean_intensity float32 (0 for noise)
+ *   gx, gy, gi float32[n]: grouped points (noise points are not copied).
+ *   n_segments, n_grouped: host int64 out. RB_ERR_CAPACITY (with *n_segments set) when cap_segments is too small, or when
+ *   n_frames * (n_clusters + 1) exceeds the slot table (2^27): pass fewer frames per call - frames are independent.
+ * Syncs once. */
+typedef struct rb_cluster_table {
+    int32_t *frame, *label, *first, *count;
+    int64_t* start;
+    float *cx, *cy, *mean_intensity;
+} rb_cluster_table;
+int rb_cluster_records(rb_ctx* ctx, const float* x, const float* y, const float* inten, const int32_t* labels, int64_t n,
+                       const int64_t* frame_off, int64_t n_frames, int64_t n_clusters, const rb_cluster_table* table,
+                       int64_t cap_segments, float* gx, float* gy, float* gi, int64_t* n_segments, int64_t* n_grouped,
+                       void* stream);
+
 /* np.arange(lo, fl32(hi + step), step) as build_occupancy_grid computes its edges (T4:372-373: float32 scalar
  * bounds, float64 result): out[0] = lo, out[1] = lo + step, out[i] = lo + i*(out[1] - lo). Host function.
  * Returns the number of edges (> cap: nothing written beyond cap). */

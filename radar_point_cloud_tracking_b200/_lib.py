@@ -43,6 +43,11 @@ class DetectBuffers(C.Structure):
                 ("x_edges", c_vp), ("y_edges", c_vp), ("max_edges", c_i32)]
 
 
+class ClusterTable(C.Structure):
+    _fields_ = [("frame", c_vp), ("label", c_vp), ("first", c_vp), ("count", c_vp), ("start", c_vp),
+                ("cx", c_vp), ("cy", c_vp), ("mean_intensity", c_vp)]
+
+
 class DetectResult(C.Structure):
     _fields_ = [("n_raw", c_i64), ("n_points", c_i64), ("n_clusters", c_i64),
                 ("frames_built", c_i32), ("land_applied", c_i32), ("filtered_is_raw", c_i32),
@@ -84,6 +89,8 @@ SIGNATURES = {
     "rb_relabel": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "rb_detect_block": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.POINTER(DetectParams), C.POINTER(DetectBuffers),
                                 C.POINTER(DetectResult), c_vp]),
+    "rb_cluster_records": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, C.POINTER(ClusterTable), c_i64,
+                                   c_vp, c_vp, c_vp, C.POINTER(c_i64), C.POINTER(c_i64), c_vp]),
     "rb_arange_edges": (c_i64, [c_f32, c_f32, c_f64, c_vp, c_i64]),
     "rb_stitch_components": (c_i64, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
     "rb_csv_parse_sweep": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),

@@ -44,6 +44,7 @@ enum rb_slot {
     RB_S_PIPE, RB_S_PIPE_EDGES, RB_S_PIPE_TIMES,   // rb_detect_block: sweep bases + bounds, device edges, times
     RB_S_B_NCORE, RB_S_B_PARENT, RB_S_B_LABEL, RB_S_B_MINKEY, RB_S_CORE_START, RB_S_CB_LIST,   // dbscan, tight: per-bucket arrays
     RB_S_CSV,               // csv ingest: newline counts per chunk, their scan, newline offsets
+    RB_S_CLUSTERS,          // cluster records: (frame, label) slot tables, tile lists, segment scans
     RB_S_COUNT
 };
 

@@ -184,6 +184,9 @@ struct __align__(128) MtSmem {
     MtMeta<TILES> meta[STAGES];
 };
 template <typename T, int STAGE_BYTES> __host__ __device__ constexpr int mt_tiles() { return STAGE_BYTES / (SK_TILE * (int)sizeof(T)); }
+template <int STAGE_BYTES> __host__ __device__ constexpr int mt_chunk_stages() {      // stages per work chunk (~256 KiB)
+    return (256 * 1024) / STAGE_BYTES > 0 ? (256 * 1024) / STAGE_BYTES : 1;
+}
 template <typename T, int STAGE_BYTES, int STAGES> constexpr int mt_smem_bytes() {
     return (int)sizeof(MtSmem<mt_tiles<T, STAGE_BYTES>(), STAGE_BYTES, STAGES>) + 128;
 }
@@ -233,6 +236,7 @@ spoke_mask_tma_kernel(const T* __restrict__ echo, const SpokeGeom g, const ThrAr
     constexpr int MT_TILES = mt_tiles<T, MT_STAGE_BYTES>();
     constexpr int MT_WARPS = Elem<T>::WARPS;
     constexpr int MT_STAGE_BATCHES = MT_TILES * SK_BATCHES;
+    constexpr int MT_CHUNK = mt_chunk_stages<MT_STAGE_BYTES>();
     static_assert(MT_TILES >= 1 && MT_TILES * SK_TILE * sizeof(T) == MT_STAGE_BYTES, "a stage is a whole number of tiles");
     using Smem = MtSmem<MT_TILES, MT_STAGE_BYTES, MT_STAGES>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -265,49 +269,62 @@ spoke_mask_tma_kernel(const T* __restrict__ echo, const SpokeGeom g, const ThrAr
             __syncwarp();
         };
         const unsigned long long policy = l2_hint ? l2_evict_first_policy() : 0ull;
-        long long st = blockIdx.x;
+        // Work is handed out in CHUNKS of MT_CHUNK stages (256 KiB), the first one statically (chunk = blockIdx.x), the
+        // following ones by an atomic ticket. A ticket per STAGE serialises on the counter's address at ~3.4 ns each:
+        // with 32 KiB stages that alone is 2.7 ms per 25.8 GB block (measured: 5.5 instead of 7.0 TB/s); per chunk it
+        // is 0.3 ms spread over the whole kernel, whatever the stage size.
+        long long chunk = blockIdx.x;
         int it = 0;
-        while (true) {
-            // the ticket of the NEXT stage goes out first: its round trip hides behind this stage's work
-            unsigned tk = 0;
-            if (lane == 0) tk = atomicAdd(ticket, 1u);
-            const int s = it % MT_STAGES;
+        auto recycle = [&](int s) {                                        // slot s must be empty again before it is refilled
             if (it >= MT_STAGES) {
                 mbar_wait(&sm.empty[s], (uint32_t)(it / MT_STAGES - 1) & 1u);
                 flush(s);
             }
-            MtMeta<MT_TILES>& m = sm.meta[s];
-            if (st >= n_stages) {                                          // end marker for the consumers
+        };
+        while (true) {
+            // the ticket of the NEXT chunk goes out first: its round trip hides behind this chunk's work
+            unsigned tk = 0;
+            if (lane == 0) tk = atomicAdd(ticket, 1u);
+            const long long st0 = chunk * MT_CHUNK;
+            if (st0 >= n_stages) {                                         // end marker for the consumers
+                const int s = it % MT_STAGES;
+                recycle(s);
                 if (lane == 0) {
-                    m.first_tile = -1;
-                    m.n_tiles = 0;
+                    sm.meta[s].first_tile = -1;
+                    sm.meta[s].n_tiles = 0;
                     mbar_arrive(&sm.full[s]);
                 }
                 break;
             }
-            const long long t0 = st * MT_TILES;
-            const int nt = (int)min((long long)MT_TILES, g.total_tiles - t0);
-            int v = 0;
-            const T* src = nullptr;
-            if ((int)lane < nt) {
-                const TileRef<T> tr = tile_ref<T>(echo, g, t0 + lane);
-                v = tr.valid;
-                src = tr.src;
+            const long long st1 = min(st0 + (long long)MT_CHUNK, n_stages);
+            for (long long st = st0; st < st1; ++st) {
+                const int s = it % MT_STAGES;
+                recycle(s);
+                MtMeta<MT_TILES>& m = sm.meta[s];
+                const long long t0 = st * MT_TILES;
+                const int nt = (int)min((long long)MT_TILES, g.total_tiles - t0);
+                int v = 0;
+                const T* src = nullptr;
+                if ((int)lane < nt) {
+                    const TileRef<T> tr = tile_ref<T>(echo, g, t0 + lane);
+                    v = tr.valid;
+                    src = tr.src;
+                }
+                if ((int)lane < MT_TILES) m.valid[lane] = v;
+                if (lane == 0) { m.first_tile = t0; m.n_tiles = nt; }
+                const uint32_t bytes = __reduce_add_sync(0xffffffffu, (uint32_t)v * (uint32_t)sizeof(T));
+                // full tiles are contiguous in memory (also across a sweep boundary) and in the ring
+                const bool all_full = __all_sync(0xffffffffu, (int)lane >= nt || v == SK_TILE);
+                if (lane == 0) mbar_expect_tx(&sm.full[s], bytes);         // releases the meta data to the consumers
+                __syncwarp();
+                if (all_full) {                                            // the common case: ONE bulk copy per stage
+                    if (lane == 0) bulk_g2s(&sm.ring[s][0], src, bytes, &sm.full[s], policy);
+                } else if (v > 0) {                                        // ragged stage: every lane copies its own tile
+                    bulk_g2s(&sm.ring[s][(size_t)lane * SK_TILE * sizeof(T)], src, (uint32_t)v * (uint32_t)sizeof(T), &sm.full[s], policy);
+                }
+                ++it;
             }
-            if ((int)lane < MT_TILES) m.valid[lane] = v;
-            if (lane == 0) { m.first_tile = t0; m.n_tiles = nt; }
-            const uint32_t bytes = __reduce_add_sync(0xffffffffu, (uint32_t)v * (uint32_t)sizeof(T));
-            // full tiles are contiguous in memory (also across a sweep boundary) and in the ring
-            const bool all_full = __all_sync(0xffffffffu, (int)lane >= nt || v == SK_TILE);
-            if (lane == 0) mbar_expect_tx(&sm.full[s], bytes);             // releases the meta data to the consumers
-            __syncwarp();
-            if (all_full) {                                                // the common case: ONE 64 KiB copy per stage
-                if (lane == 0) bulk_g2s(&sm.ring[s][0], src, bytes, &sm.full[s], policy);
-            } else if (v > 0) {                                            // ragged stage: every lane copies its own tile
-                bulk_g2s(&sm.ring[s][(size_t)lane * SK_TILE * sizeof(T)], src, (uint32_t)v * (uint32_t)sizeof(T), &sm.full[s], policy);
-            }
-            st = (long long)gridDim.x + (long long)__shfl_sync(0xffffffffu, tk, 0);
-            ++it;
+            chunk = (long long)gridDim.x + (long long)__shfl_sync(0xffffffffu, tk, 0);
         }
         // stages still in flight: fills it-1 .. it-(MT_STAGES-1)
         for (int j = max(0, it - (MT_STAGES - 1)); j < it; ++j) {
@@ -669,14 +686,14 @@ int launch_mask_tma(rb_ctx* ctx, const T* echo, const SpokeGeom& g, const ThrArg
                     unsigned* ticket, cudaStream_t stream) {
     constexpr int smem = mt_smem_bytes<T, STAGE_BYTES, STAGES>();
     constexpr int ring_id = STAGE_BYTES == 64 * 1024 ? (STAGES == 3 ? 0 : 3) : STAGE_BYTES == 32 * 1024 ? (STAGES == 4 ? 1 : 2) :
-                            STAGE_BYTES == 48 * 1024 ? (STAGES == 3 ? 5 : 6) : STAGE_BYTES == 80 * 1024 ? 7 : 4;
+                            STAGE_BYTES == 48 * 1024 ? (STAGES == 3 ? 5 : 6) : STAGE_BYTES == 80 * 1024 ? 7 : (STAGES == 4 ? 4 : 8);
     const unsigned bit = 1u << (ring_id * 2 + (sizeof(T) == 1 ? 1 : 0));
     auto kernel = spoke_mask_tma_kernel<T, STAGE_BYTES, STAGES>;
     if (!(ctx->attr_spoke_mask & bit)) {
         RB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         ctx->attr_spoke_mask |= bit;
     }
-    const int64_t want_blocks = rb_div_up(g.total_tiles, mt_tiles<T, STAGE_BYTES>());
+    const int64_t want_blocks = rb_div_up(g.total_tiles, (int64_t)mt_tiles<T, STAGE_BYTES>() * mt_chunk_stages<STAGE_BYTES>());
     const unsigned blocks = (unsigned)(want_blocks < ctx->sm_count ? want_blocks : ctx->sm_count);
     RB_CUDA(rb_launch(ctx, kernel, dim3(blocks), dim3(mt_threads<T>()), (size_t)smem, stream, echo, g, thr, mask, tile_count, ticket,
                       ctx->opt_spoke_l2_hint));
@@ -749,6 +766,7 @@ int spoke_to_points_impl(rb_ctx* ctx, const T* echo, const float* cos_tab, const
             case 5: RB_TRY((launch_mask_tma<T, 48 * 1024, 3>(ctx, echo, g, thr, mask, tile_count, ticket, stream))); break;
             case 6: RB_TRY((launch_mask_tma<T, 48 * 1024, 2>(ctx, echo, g, thr, mask, tile_count, ticket, stream))); break;
             case 7: RB_TRY((launch_mask_tma<T, 80 * 1024, 2>(ctx, echo, g, thr, mask, tile_count, ticket, stream))); break;
+            case 8: RB_TRY((launch_mask_tma<T, 16 * 1024, 6>(ctx, echo, g, thr, mask, tile_count, ticket, stream))); break;
             default: RB_TRY((launch_mask_tma<T, 64 * 1024, 3>(ctx, echo, g, thr, mask, tile_count, ticket, stream))); break;
         }
         ctx->spoke_last_variant = 2;

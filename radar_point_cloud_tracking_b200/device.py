@@ -350,6 +350,103 @@ def stdbscan_stats(device: Optional[int] = None) -> dict:
     return d
 
 
+# --------------------------------------------------------------------------------------- a8: cluster records
+def cluster_records(batch: PointBatch, labels: torch.Tensor, n_clusters: int) -> dict:
+    """Per-frame cluster records of a labelled batch computed on the device (``rb_cluster_records``; T4:511-534) and
+    read back with ONE packed device->host copy into pinned memory. Returns host arrays: the segment table
+    ``frame, label, first, count, start, cx, cy, mean_intensity`` (segments ordered by frame, then label; label -1 = the
+    frame's noise entry) and the grouped points ``gx, gy, gi`` (each cluster's points contiguous, original order)."""
+    ctx = context(batch.x.device.index)
+    d = batch.x.device
+    n = int(batch.n)
+    F = batch.frame_off.numel() - 1
+    empty = dict(frame=np.zeros(0, np.int32), label=np.zeros(0, np.int32), first=np.zeros(0, np.int32), count=np.zeros(0, np.int32),
+                 start=np.zeros(0, np.int64), cx=np.zeros(0, np.float32), cy=np.zeros(0, np.float32),
+                 mean_intensity=np.zeros(0, np.float32), gx=np.zeros(0, np.float32), gy=np.zeros(0, np.float32), gi=np.zeros(0, np.float32))
+    if n == 0 or F == 0:
+        return empty
+    width = int(n_clusters) + 1
+    if F * width > (1 << 27):                         # frames are independent: split the call
+        half = F // 2
+        if half == 0:
+            raise RadarB200Error("cluster_records: too many clusters for the slot table")
+        off = batch.frame_off
+        cut = int(off[half].item())
+        a = cluster_records(PointBatch(batch.x[:cut], batch.y[:cut], batch.inten[:cut], batch.gain[:cut], off[:half + 1], cut),
+                            labels[:cut], n_clusters)
+        b = cluster_records(PointBatch(batch.x[cut:n], batch.y[cut:n], batch.inten[cut:n], batch.gain[cut:n], off[half:] - cut, n - cut),
+                            labels[cut:n], n_clusters)
+        b["frame"] = b["frame"] + half
+        b["start"] = np.where(b["start"] >= 0, b["start"] + len(a["gx"]), -1)
+        return {k: np.concatenate([a[k], b[k]]) for k in a}
+    labels = _dev(labels, torch.int32, "labels")
+    cap = min(n + F, F * width)
+    guess = getattr(cluster_records, "_cap_hint", 0) or min(cap, max(4096, 64 * F))
+    while True:
+        cap_s = min(cap, guess)
+        # one packed buffer: 4 int32 columns | start (int64) | 3 float32 columns | 3 grouped float32 arrays
+        i32 = torch.empty(4 * cap_s, dtype=torch.int32, device=d)
+        i64 = torch.empty(cap_s, dtype=torch.int64, device=d)
+        f32 = torch.empty(3 * cap_s + 3 * n, dtype=torch.float32, device=d)
+        tab = _lib.ClusterTable(*(ptr(i32[k * cap_s:]) for k in range(4)), ptr(i64), *(ptr(f32[k * cap_s:]) for k in range(3)))
+        g = f32[3 * cap_s:]
+        n_seg, n_grp = C.c_int64(0), C.c_int64(0)
+        rc = ctx.lib.rb_cluster_records(ctx.handle, ptr(batch.x), ptr(batch.y), ptr(batch.inten), ptr(labels), n, ptr(batch.frame_off), F,
+                                        int(n_clusters), C.byref(tab), cap_s, ptr(g), ptr(g[n:]), ptr(g[2 * n:]), C.byref(n_seg),
+                                        C.byref(n_grp), stream_ptr())
+        if rc == RB_ERR_CAPACITY and n_seg.value > cap_s:
+            guess = int(n_seg.value * 1.25) + 64
+            continue
+        check(rc, "rb_cluster_records")
+        break
+    cluster_records._cap_hint = max(getattr(cluster_records, "_cap_hint", 0), int(n_seg.value * 1.25) + 64)
+    S, M = int(n_seg.value), int(n_grp.value)
+    hi32, hi64, hf32 = i32.cpu().numpy(), i64[:S].cpu().numpy(), f32.cpu().numpy()
+    out = {k: hi32[j * cap_s:j * cap_s + S] for j, k in enumerate(("frame", "label", "first", "count"))}
+    out["start"] = hi64
+    out.update({k: hf32[j * cap_s:j * cap_s + S] for j, k in enumerate(("cx", "cy", "mean_intensity"))})
+    base = 3 * cap_s
+    out.update(gx=hf32[base:base + M], gy=hf32[base + n:base + n + M], gi=hf32[base + 2 * n:base + 2 * n + M])
+    return out
+
+
+def clusters_from_records(rec: dict, frame_ids, cluster_cls, frame_id_type=int) -> dict:
+    """``{frame_id: [Cluster]}`` from the device-computed records, in the reference's order: per frame the clusters come
+    out in the iteration order of ``set(frame_labels)`` (T4:518-521), which depends on the order in which the labels
+    FIRST OCCUR in the frame (hash collisions, table growth) - replayed here with a real Python set fed in that order.
+    ``points`` / ``intensities`` of a cluster are views of the grouped arrays; ``centroid`` rows of one ``[S, 2]`` array."""
+    out = {}
+    S = len(rec["frame"])
+    if S == 0:
+        return out
+    gxy = np.stack([rec["gx"], rec["gy"]], axis=1)
+    gi = rec["gi"]
+    cent = np.stack([rec["cx"], rec["cy"]], axis=1)
+    frame, label, first = rec["frame"], rec["label"], rec["first"]
+    start, count = rec["start"].tolist(), rec["count"].tolist()
+    order = np.lexsort((first, frame))                                    # per frame: segments by first occurrence
+    lab_l, fr_l = label.tolist(), frame.tolist()
+    bounds = np.flatnonzero(np.diff(frame[order], prepend=-1, append=-2))  # starts of the frames' runs in `order`
+    order_l = order.tolist()
+    ids = [frame_id_type(v) for v in np.asarray(frame_ids).tolist()]
+    for a, b in zip(bounds[:-1].tolist(), bounds[1:].tolist()):
+        segs = order_l[a:b]
+        seg_of = {lab_l[k]: k for k in segs}
+        seen = set(lab_l[k] for k in segs)                                 # same insertion order as set(frame_labels)
+        seen.discard(-1)
+        if not seen:
+            continue
+        fid = ids[fr_l[segs[0]]]
+        lst = []
+        for c in seen:
+            k = seg_of[c]
+            s0 = start[k]
+            lst.append(cluster_cls(cluster_id=c, frame_id=fid, points=gxy[s0:s0 + count[k]], intensities=gi[s0:s0 + count[k]],
+                                   centroid=cent[k]))
+        out[fid] = lst
+    return out
+
+
 # --------------------------------------------------------------------------------------- whole block, one call
 RB_ERR_CAPACITY = -3
 

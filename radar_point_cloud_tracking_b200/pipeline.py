@@ -86,7 +86,15 @@ class DetectionResult:
         return out
 
     def clusters_by_frame(self, host: Optional[dict] = None, cluster_cls=None) -> Dict[int, list]:
-        """``{frame_id: [Cluster]}`` exactly as T4:511-534 builds it (host numpy, ``np.mean`` centroids)."""
+        """``{frame_id: [Cluster]}`` exactly as T4:511-534 builds it. The records (member points grouped per cluster,
+        ``np.mean`` centroids bit for bit) come from the device (``rb_cluster_records``) in one packed read-back; the host
+        wraps them into ``Cluster`` objects in the reference's order."""
+        rec = dev.cluster_records(self.points, self.labels, self.n_clusters)
+        return dev.clusters_from_records(rec, self.frame_ids, cluster_cls or trk.Cluster)
+
+    def clusters_by_frame_host(self, host: Optional[dict] = None, cluster_cls=None) -> Dict[int, list]:
+        """The same through the reference's own host loop (boolean masks + ``np.mean`` per cluster): the cross-check of the
+        device records and the "before" of their timing."""
         h = host or self.to_host()
         cls = cluster_cls or trk.Cluster
         off, labels, pts = h["frame_off"], h["labels"], h["points"]

@@ -332,15 +332,13 @@ def st_dbscan_labels(frames: Sequence[RadarFrame], eps_space: float, eps_time: f
     return labels.cpu().numpy(), offs
 
 
-def st_dbscan(frames: List[RadarFrame], eps_space: float, eps_time: float, min_samples: int,
-              _cluster_cls=None) -> Dict[int, List[Cluster]]:
-    """ST-DBSCAN across all frames; returns ``{frame_id: [Cluster]}`` (T4:443-536)."""
-    cluster_cls = _cluster_cls or Cluster
-    if not frames:                                            # T4:463-464
-        return {}
-    labels, offs = st_dbscan_labels(frames, eps_space, eps_time, min_samples)
+def clusters_host(frames: Sequence[RadarFrame], labels: np.ndarray, offs: np.ndarray, cluster_cls=None) -> Dict[int, List[Cluster]]:
+    """The reference's own loop (T4:511-534) in host numpy: boolean masks and ``np.mean`` per cluster. Kept as the
+    cross-check of :func:`device.cluster_records` (the tests compare the two record for record); the product path below
+    does not call it."""
+    cluster_cls = cluster_cls or Cluster
     by_frame: Dict[int, List[Cluster]] = defaultdict(list)
-    for i, frame in enumerate(frames):                        # T4:511-534, host numpy (centroid = np.mean)
+    for i, frame in enumerate(frames):
         lab = labels[offs[i]:offs[i + 1]]
         xy = frame.points[:, :2]
         inten = frame.points[:, 2]
@@ -352,6 +350,25 @@ def st_dbscan(frames: List[RadarFrame], eps_space: float, eps_time: float, min_s
             by_frame[frame.frame_id].append(cluster_cls(cluster_id=int(c), frame_id=frame.frame_id, points=pts,
                                                         intensities=inten[m], centroid=np.mean(pts, axis=0)))
     return dict(by_frame)
+
+
+def st_dbscan(frames: List[RadarFrame], eps_space: float, eps_time: float, min_samples: int,
+              _cluster_cls=None) -> Dict[int, List[Cluster]]:
+    """ST-DBSCAN across all frames; returns ``{frame_id: [Cluster]}`` (T4:443-536). Labels AND the per-frame cluster
+    records (T4:511-534: member points, ``np.mean`` centroid) are computed on the device; the host only wraps the
+    records into ``Cluster`` objects, in the reference's order."""
+    cluster_cls = _cluster_cls or Cluster
+    if not frames:                                            # T4:463-464
+        return {}
+    batch, offs = _to_device_points(frames)
+    if batch.n == 0:
+        return {}
+    d = batch.x.device
+    ids = np.array([f.frame_id for f in frames])
+    times = dev.expand_frame_times(batch.frame_off, torch.from_numpy(ids.astype(np.float32)).to(d), batch.n)      # T4:460,467
+    labels, n_clusters = dev.stdbscan(batch.x, batch.y, None, times, eps_space, eps_time, min_samples, stride=1, n=batch.n)
+    rec = dev.cluster_records(batch, labels, n_clusters)
+    return dev.clusters_from_records(rec, [f.frame_id for f in frames], cluster_cls, frame_id_type=lambda v: v)
 
 
 # ---- drop-in installation ----------------------------------------------------------------------------

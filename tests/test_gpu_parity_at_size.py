@@ -109,10 +109,10 @@ def test_config4_dense_clutter_at_real_density_vs_c_oracle(gpu):
 
 def test_config2_3d_single_gain_vs_c_oracle(gpu):
     """3_stdbscan_point_clouds.py's shape of problem (T3:177-182): coords = (x, y, z = intensity), one gain, frames
-    stacked with time = frame index, eps 5 / 1 / 10 - > 500 k points of 100 full-size sweeps, both algorithms (the tight
+    stacked with time = frame index, eps 5 / 1 / 10 - > 500 k points of 144 full-size sweeps, both algorithms (the tight
     3-D bucket table does not fit the budget at this extent, so 'auto' runs the general algorithm too: asserted)."""
     from radar_point_cloud_tracking_b200.pipeline import DetectionConfig
-    F = 100
+    F = 144
     spec = syn.SweepSpec(seed=222, frames=F, gains=(50,), clutter_p=0.003)
     cfg = DetectionConfig(gains=(50,), land_filter=False)
     res = _run_block(gpu, spec, cfg, cluster=False)

@@ -19,15 +19,15 @@ except Exception as e:
 PY
 }
 run "64Kx3 (197 KB), 3 in flight"   RB_OPT_SPOKE_RING=0
-run "80Kx2 (164 KB), 3 in flight"   RB_OPT_SPOKE_RING=7
 run "48Kx3 (148 KB), 3 in flight"   RB_OPT_SPOKE_RING=5
 run "64Kx2 (131 KB), 3 in flight"   RB_OPT_SPOKE_RING=3
 run "48Kx2 ( 98 KB), 3 in flight"   RB_OPT_SPOKE_RING=6
 run "32Kx3 ( 98 KB), 3 in flight"   RB_OPT_SPOKE_RING=2
-run "64Kx2 + l2 hint, 3 in flight"  RB_OPT_SPOKE_RING=3 RB_OPT_SPOKE_L2_HINT=1
-run "48Kx3 + l2 hint, 3 in flight"  RB_OPT_SPOKE_RING=5 RB_OPT_SPOKE_L2_HINT=1
-EXTRA="--streams 2" run "64Kx2, 2 in flight"  RB_OPT_SPOKE_RING=3
-EXTRA="--streams 4" run "64Kx2, 4 in flight"  RB_OPT_SPOKE_RING=3
-EXTRA="--streams 4" run "48Kx3, 4 in flight"  RB_OPT_SPOKE_RING=5
+run "16Kx6 ( 98 KB), 3 in flight"   RB_OPT_SPOKE_RING=8
+run "16Kx4 ( 66 KB), 3 in flight"   RB_OPT_SPOKE_RING=4
+run "32Kx4 (131 KB), 3 in flight"   RB_OPT_SPOKE_RING=1
+EXTRA="--streams 2" run "32Kx3, 2 in flight"  RB_OPT_SPOKE_RING=2
+EXTRA="--streams 4" run "32Kx3, 4 in flight"  RB_OPT_SPOKE_RING=2
+EXTRA="--streams 4" run "16Kx6, 4 in flight"  RB_OPT_SPOKE_RING=8
 EXTRA="--streams 4" run "48Kx2, 4 in flight"  RB_OPT_SPOKE_RING=6
-EXTRA="--streams 6" run "64Kx2, 6 in flight"  RB_OPT_SPOKE_RING=3
+run "32Kx3 + l2 hint, 3 in flight"  RB_OPT_SPOKE_RING=2 RB_OPT_SPOKE_L2_HINT=1
