@@ -125,10 +125,25 @@ int rb_bounds_counted(rb_ctx* ctx, const float* x, const float* y, const int64_t
  *   ix = clip(searchsorted_right(x_edges, (double)x) - 1, 0, n_x_edges - 2)      (T4:384)
  *   count[ix][iy] += 1 (int32);  isum[ix][iy] += intensity (float64)            (T4:388-389)
  * x_edges / y_edges are the float64 np.arange edges computed on the host (T4:372-373) and copied
- * to the device. count/isum must be zeroed by the caller; the call accumulates. No sync. */
+ * to the device. count/isum must be zeroed by the caller; the call accumulates. No sync. Exact for integer-valued
+ * intensities, checked on the device - see rb_land_accumulate_status below. */
 int rb_land_accumulate(rb_ctx* ctx, const float* x, const float* y, const float* inten, int64_t n,
                        const double* x_edges, int n_x_edges, const double* y_edges, int n_y_edges,
                        int32_t* count, double* isum, void* stream);
+
+/* rb_land_accumulate's float64 sums equal np.add.at's for INTEGER-valued intensities in [0, 65535] (a radar's echoes are
+ * 0..255): integer addition is exact in any order, and the kernel checks that every intensity is one. Otherwise a flag is
+ * raised on the device and the grids of that call must not be used: zero them again and call
+ * rb_land_accumulate_ordered, which adds every cell's points one after the other in the reference's order (slower; a
+ * stable partition by cell first). rb_land_accumulate_status: host int32 out, 1 = some call since the last query saw
+ * such an intensity; syncs and clears the flag. _status_async: the same into `dst` (device or pinned host memory) as a
+ * copy enqueued on the stream, for callers that read several things back with one sync. rb_detect_block does all of
+ * this by itself. */
+int rb_land_accumulate_status(rb_ctx* ctx, int32_t* inexact, void* stream);
+int rb_land_accumulate_status_async(rb_ctx* ctx, int32_t* dst, void* stream);
+int rb_land_accumulate_ordered(rb_ctx* ctx, const float* x, const float* y, const float* inten, int64_t n,
+                               const double* x_edges, int n_x_edges, const double* y_edges, int n_y_edges,
+                               int32_t* count, double* isum, void* stream);
 
 /* identify_land_cells (T4:394-410) in float64 on the device:
  *   land = (count / max(num_frames,1) >= persistence) & ((count>0 ? isum/count : 0) >= min_intensity)
@@ -275,6 +290,7 @@ typedef struct rb_detect_result {                            /* host */
     int32_t frames_built, land_applied, filtered_is_raw;
     int32_t n_x_edges, n_y_edges;
     float bounds[4];                                          /* x_min, x_max, y_min, y_max of the raw points */
+    int32_t land_ordered;                                     /* 1 = non-integer intensities: the ordered accumulation ran */
 } rb_detect_result;
 
 int rb_detect_block(rb_ctx* ctx, const float* echo, const float* cos_tab, const float* sin_tab, const float* range_res,

@@ -51,7 +51,7 @@ class ClusterTable(C.Structure):
 class DetectResult(C.Structure):
     _fields_ = [("n_raw", c_i64), ("n_points", c_i64), ("n_clusters", c_i64),
                 ("frames_built", c_i32), ("land_applied", c_i32), ("filtered_is_raw", c_i32),
-                ("n_x_edges", c_i32), ("n_y_edges", c_i32), ("bounds", c_f32 * 4)]
+                ("n_x_edges", c_i32), ("n_y_edges", c_i32), ("bounds", c_f32 * 4), ("land_ordered", c_i32)]
 
 
 #: name -> (restype, argtypes); must list every symbol of include/radarb200.h
@@ -73,6 +73,9 @@ SIGNATURES = {
     "rb_bounds": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "rb_bounds_counted": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "rb_land_accumulate": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp]),
+    "rb_land_accumulate_status": (c_i32, [c_vp, C.POINTER(c_i32), c_vp]),
+    "rb_land_accumulate_status_async": (c_i32, [c_vp, c_vp, c_vp]),
+    "rb_land_accumulate_ordered": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp]),
     "rb_land_cells": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_f64, c_f64, c_vp, c_vp]),
     "rb_land_filter": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i32, c_vp, c_i32,
                                c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

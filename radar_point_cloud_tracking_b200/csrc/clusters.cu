@@ -72,9 +72,9 @@ __global__ void __launch_bounds__(CL_THREADS) cl_compact_kernel(const int32_t* _
     const int64_t k = rank[s];
     if (k >= cap) return;
     const int label = (int)(s % width) - 1;
-    seg_frame[k] = (int)(s / width);
+    if (seg_frame) seg_frame[k] = (int)(s / width);
     seg_label[k] = label;
-    seg_first[k] = first[s];
+    if (seg_first) seg_first[k] = first[s];
     seg_count[k] = cnt[s];
     seg_grouped[k] = label >= 0 ? cnt[s] : 0;
 }
@@ -190,7 +190,9 @@ __global__ void __launch_bounds__(CL_WARPS * 32) cl_partition_kernel(const float
                 const int p = hash_find(h, key);
                 const int base = h[p].val;
                 const int64_t dst = (int64_t)slot_start[(int64_t)f * width + key] + base + __popc(same & rb_lanemask_lt());
-                gx[dst] = x[p0 + j]; gy[dst] = y[p0 + j]; gi[dst] = inten[p0 + j];
+                if (gx) gx[dst] = x[p0 + j];
+                if (gy) gy[dst] = y[p0 + j];
+                gi[dst] = inten[p0 + j];
                 __syncwarp(same);
                 if ((int)lane == __ffs(same) - 1) h[p].val = base + __popc(same);
             }
@@ -278,24 +280,17 @@ __global__ void __launch_bounds__(128) cl_reduce_kernel(const float* __restrict_
 
 }  // namespace
 
-extern "C" int rb_cluster_records(rb_ctx* ctx, const float* x, const float* y, const float* inten, const int32_t* labels, int64_t n,
-                                  const int64_t* frame_off, int64_t n_frames, int64_t n_clusters, const rb_cluster_table* tab,
-                                  int64_t cap_segments, float* gx, float* gy, float* gi, int64_t* n_segments, int64_t* n_grouped,
-                                  void* stream_) {
-    RB_REQUIRE(ctx && tab && n_segments && n_grouped, "NULL argument");
-    RB_REQUIRE(n >= 0 && n < ((int64_t)1 << 31) && n_frames >= 0 && n_frames < ((int64_t)1 << 30) && n_clusters >= 0 && cap_segments >= 0,
-               "bad sizes");
-    cudaStream_t stream = (cudaStream_t)stream_;
-    *n_segments = 0;
-    *n_grouped = 0;
-    if (n == 0 || n_frames == 0) return RB_OK;
-    RB_REQUIRE(x && y && inten && labels && frame_off && gx && gy && gi, "NULL buffers");
-    RB_REQUIRE(tab->frame && tab->label && tab->first && tab->count && tab->start && tab->cx && tab->cy && tab->mean_intensity,
-               "NULL table columns");
-    const int64_t width = n_clusters + 1;                            // labels -1 .. n_clusters-1
+// The grouping itself (steps 1-3), shared by rb_cluster_records and by the ordered land accumulation (land.cu, cells as
+// labels, one "frame"): segment table + the values grouped by (frame, label) in their original order. Optional outputs
+// may be NULL. Syncs once (segment count / capacity check). *n_seg_dev_out: device copy of the segment count.
+static int group_core(rb_ctx* ctx, const float* x, const float* y, const float* inten, const int32_t* labels, int64_t n,
+                      const int64_t* frame_off, int64_t n_frames, int64_t n_labels, int32_t* seg_frame, int32_t* seg_label,
+                      int32_t* seg_first, int32_t* seg_count, int64_t* seg_start, int64_t cap_segments, float* gx, float* gy, float* gi,
+                      int64_t* n_segments, int64_t* n_grouped, const int32_t** n_seg_dev_out, cudaStream_t stream) {
+    const int64_t width = n_labels + 1;                              // labels -1 .. n_labels-1
     const int64_t m = n_frames * width;
     if (m > ((int64_t)1 << 27)) {
-        rb_set_error("rb_cluster_records: %lld frames x %lld labels exceed the slot table; pass fewer frames per call (frames are independent)",
+        rb_set_error("cluster records: %lld frames x %lld labels exceed the slot table; pass fewer frames per call (frames are independent)",
                      (long long)n_frames, (long long)width);
         return RB_ERR_CAPACITY;
     }
@@ -313,7 +308,7 @@ extern "C" int rb_cluster_records(rb_ctx* ctx, const float* x, const float* y, c
     int32_t* turn = tile_base + F1;
     int32_t* seg_grouped = turn + F1;
     int32_t* seg_start32 = seg_grouped + S1;
-    int32_t* misc = seg_start32 + S1;                                // [0] = bad label flag, [1] = ticket, [2] = grouped total
+    int32_t* misc = seg_start32 + S1;                                // [0] = bad label flag, [1] = ticket, [2] = grouped total, [3] = segments
     RB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * M1, stream));
     RB_CUDA(cudaMemsetAsync(first, 0x7f, sizeof(int32_t) * M1, stream));
     RB_CUDA(cudaMemsetAsync(fill, 0, sizeof(int32_t) * M1, stream));
@@ -328,21 +323,21 @@ extern "C" int rb_cluster_records(rb_ctx* ctx, const float* x, const float* y, c
     int32_t* n_seg_dev = misc + 3;
     RB_TRY(rb_exclusive_scan_i32(ctx, rank, rank, m + 1, n_seg_dev, stream));
     RB_CUDA(rb_launch(ctx, cl_compact_kernel, dim3(mblocks), dim3(CL_THREADS), 0, stream, (const int32_t*)cnt, (const int32_t*)first,
-                      (const int32_t*)rank, m, (int)width, cap_segments, tab->frame, tab->label, tab->first, tab->count, seg_grouped));
+                      (const int32_t*)rank, m, (int)width, cap_segments, seg_frame, seg_label, seg_first, seg_count, seg_grouped));
     RB_LAUNCH_CHECK(ctx);
     if (cap_segments > 0) RB_TRY(rb_exclusive_scan_i32(ctx, seg_grouped, seg_start32, cap_segments, misc + 2, stream));
     RB_CUDA(rb_launch(ctx, cl_slot_start_kernel, dim3(mblocks), dim3(CL_THREADS), 0, stream, (const int32_t*)cnt, (const int32_t*)rank,
-                      (const int32_t*)seg_start32, m, (int)width, cap_segments, slot_start, tab->start));
+                      (const int32_t*)seg_start32, m, (int)width, cap_segments, slot_start, seg_start));
     RB_LAUNCH_CHECK(ctx);
     // read-back: number of segments (capacity check before anything is scattered), grouped points, bad-label flag
     int32_t* h = (int32_t*)ctx->pinned;
     RB_CUDA(cudaMemcpyAsync(h, misc, sizeof(int32_t) * 4, cudaMemcpyDeviceToHost, stream));
     RB_CUDA(cudaStreamSynchronize(stream));
-    if (h[0]) { rb_set_error("rb_cluster_records: a label outside [-1, n_clusters)"); return RB_ERR_ARG; }
+    if (h[0]) { rb_set_error("cluster records: a label outside [-1, n_labels)"); return RB_ERR_ARG; }
     *n_segments = h[3];
     *n_grouped = h[2];
     if (h[3] > cap_segments) {
-        rb_set_error("rb_cluster_records: %d segments need a table of at least that size (cap = %lld)", h[3], (long long)cap_segments);
+        rb_set_error("cluster records: %d segments need a table of at least that size (cap = %lld)", h[3], (long long)cap_segments);
         return RB_ERR_CAPACITY;
     }
     RB_CUDA(rb_launch(ctx, cl_tiles_kernel, dim3((unsigned)rb_div_up(n_frames + 1, CL_THREADS)), dim3(CL_THREADS), 0, stream, frame_off, (int)n_frames, tiles));
@@ -354,11 +349,46 @@ extern "C" int rb_cluster_records(rb_ctx* ctx, const float* x, const float* y, c
     RB_CUDA(rb_launch(ctx, cl_partition_kernel, dim3(blocks), dim3(CL_WARPS * 32), 0, stream, x, y, inten, labels, frame_off, (int)n_frames, (int)width,
                       (const int32_t*)tile_base, (const int32_t*)slot_start, fill, turn, (unsigned*)(misc + 1), gx, gy, gi));
     RB_LAUNCH_CHECK(ctx);
-    if (h[3] > 0) {
-        RB_CUDA(rb_launch(ctx, cl_reduce_kernel, dim3((unsigned)rb_div_up(h[3], 128)), dim3(128), 0, stream, (const float*)gx, (const float*)gy,
-                          (const float*)gi, (const int32_t*)tab->label, (const int32_t*)tab->count, (const int64_t*)tab->start,
-                          (const int32_t*)n_seg_dev, cap_segments, tab->cx, tab->cy, tab->mean_intensity));
+    if (n_seg_dev_out) *n_seg_dev_out = n_seg_dev;
+    return RB_OK;
+}
+
+extern "C" int rb_cluster_records(rb_ctx* ctx, const float* x, const float* y, const float* inten, const int32_t* labels, int64_t n,
+                                  const int64_t* frame_off, int64_t n_frames, int64_t n_clusters, const rb_cluster_table* tab,
+                                  int64_t cap_segments, float* gx, float* gy, float* gi, int64_t* n_segments, int64_t* n_grouped,
+                                  void* stream_) {
+    RB_REQUIRE(ctx && tab && n_segments && n_grouped, "NULL argument");
+    RB_REQUIRE(n >= 0 && n < ((int64_t)1 << 31) && n_frames >= 0 && n_frames < ((int64_t)1 << 30) && n_clusters >= 0 && cap_segments >= 0,
+               "bad sizes");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    *n_segments = 0;
+    *n_grouped = 0;
+    if (n == 0 || n_frames == 0) return RB_OK;
+    RB_REQUIRE(x && y && inten && labels && frame_off && gx && gy && gi, "NULL buffers");
+    RB_REQUIRE(tab->frame && tab->label && tab->first && tab->count && tab->start && tab->cx && tab->cy && tab->mean_intensity,
+               "NULL table columns");
+    const int32_t* n_seg_dev = nullptr;
+    RB_TRY(group_core(ctx, x, y, inten, labels, n, frame_off, n_frames, n_clusters, tab->frame, tab->label, tab->first, tab->count, tab->start,
+                      cap_segments, gx, gy, gi, n_segments, n_grouped, &n_seg_dev, stream));
+    if (*n_segments > 0) {
+        RB_CUDA(rb_launch(ctx, cl_reduce_kernel, dim3((unsigned)rb_div_up(*n_segments, 128)), dim3(128), 0, stream, (const float*)gx, (const float*)gy,
+                          (const float*)gi, (const int32_t*)tab->label, (const int32_t*)tab->count, (const int64_t*)tab->start, n_seg_dev,
+                          cap_segments, tab->cx, tab->cy, tab->mean_intensity));
         RB_LAUNCH_CHECK(ctx);
     }
     return RB_OK;
+}
+
+// values[n] grouped by labels[n] (0 .. n_labels-1) in their original order: one segment per label that occurs
+// (ascending), seg_start = its offset in `grouped`. Used by the ordered land accumulation (land.cu). Syncs once.
+int rb_stable_group(rb_ctx* ctx, const float* values, const int32_t* labels, int64_t n, int64_t n_labels, int32_t* seg_label,
+                    int32_t* seg_count, int64_t* seg_start, int64_t cap_segments, float* grouped, int64_t* n_segments, cudaStream_t stream) {
+    void* fo;
+    RB_TRY(rb_scratch_get(ctx, RB_S_GROUP_TMP, 64, &fo));
+    int64_t* h = (int64_t*)((unsigned char*)ctx->pinned + 256);      // (the first bytes of the staging buffer take the read-back)
+    h[0] = 0; h[1] = n;
+    RB_CUDA(cudaMemcpyAsync(fo, h, sizeof(int64_t) * 2, cudaMemcpyHostToDevice, stream));
+    int64_t n_grouped = 0;
+    return group_core(ctx, nullptr, nullptr, values, labels, n, (const int64_t*)fo, 1, n_labels, nullptr, seg_label, nullptr, seg_count, seg_start,
+                      cap_segments, nullptr, nullptr, grouped, n_segments, &n_grouped, nullptr, stream);
 }

@@ -45,6 +45,9 @@ enum rb_slot {
     RB_S_B_NCORE, RB_S_B_PARENT, RB_S_B_LABEL, RB_S_B_MINKEY, RB_S_CORE_START, RB_S_CB_LIST,   // dbscan, tight: per-bucket arrays
     RB_S_CSV,               // csv ingest: newline counts per chunk, their scan, newline offsets
     RB_S_CLUSTERS,          // cluster records: (frame, label) slot tables, tile lists, segment scans
+    RB_S_LAND_FLAG,         // land accumulate: "an intensity is not a small integer" flag
+    RB_S_GROUP_TMP,         // rb_stable_group: frame offsets of its single frame
+    RB_S_LAND_ORDERED,      // land accumulate, ordered path: cell ids, grouped intensities, segment table
     RB_S_COUNT
 };
 
@@ -68,6 +71,9 @@ struct rb_ctx {
     int opt_spoke_profile = 0;       // 1: record events around the three spoke-to-point kernels
     int opt_spoke_ring = 0;          // TMA ring of the mask kernel: 0 = 64 KiB x 3, 1 = 32 KiB x 4, 2 = 32 KiB x 3, 3 = 64 KiB x 2, 4 = 16 KiB x 4
     int opt_spoke_l2_hint = 0;       // 1: the mask kernel's bulk loads carry an L2 evict-first policy
+    int opt_mask_priority = 1;       // 1: the mask kernel is launched with the device's highest launch priority
+    int prio_high = 0;               // that priority (cudaDeviceGetStreamPriorityRange)
+    int opt_mask_gate = 1;           // 1: the mask kernels of all contexts of a device run one after the other (see spoke.cu)
     int opt_carveout = -1;           // >= 0: every launch asks for this shared-memory carve-out (percent), see rb_launch
     unsigned attr_spoke_mask = 0;    // per-context "function attribute set" flags (a context = one device)
     bool attr_land = false;
@@ -119,22 +125,35 @@ static inline int64_t rb_div_up(int64_t a, int64_t b) { return (a + b - 1) / b; 
 // the HBM-bound mask kernel of the next (blocks in flight on different streams).
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
-inline cudaError_t rb_launch(rb_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                             Args&&... args) {
+inline cudaError_t rb_launch_prio(rb_ctx* ctx, bool high_priority, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                  cudaStream_t stream, Args&&... args) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
+    unsigned na = 0;
     if (ctx->opt_carveout >= 0) {
-        attr[0].id = cudaLaunchAttributePreferredSharedMemoryCarveout;
-        attr[0].val.sharedMemCarveout = (unsigned)ctx->opt_carveout;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        attr[na].id = cudaLaunchAttributePreferredSharedMemoryCarveout;
+        attr[na].val.sharedMemCarveout = (unsigned)ctx->opt_carveout;
+        ++na;
     }
+    if (high_priority && ctx->opt_mask_priority) {
+        // CTAs of a higher-priority launch are dispatched before the waiting CTAs of the other grids: the 148 persistent
+        // CTAs of the HBM-bound mask kernel must not queue behind the thousands of CTAs of another block's kernels
+        attr[na].id = cudaLaunchAttributePriority;
+        attr[na].val.priority = ctx->prio_high;
+        ++na;
+    }
+    if (na) { cfg.attrs = attr; cfg.numAttrs = na; }
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t rb_launch(rb_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                             Args&&... args) {
+    return rb_launch_prio(ctx, false, kernel, grid, block, smem, stream, std::forward<Args>(args)...);
 }
 #endif
 
@@ -186,5 +205,7 @@ int rb_stdbscan_enqueue(rb_ctx* ctx, const float* x, const float* y, const float
                         int64_t n, double eps_space, float eps_time, int min_samples, int32_t* labels, uint8_t* core,
                         const rb_stdbscan_hint* hint, void* stream);
 int rb_stdbscan_fetch_stats(rb_ctx* ctx, int64_t* n_clusters, void* stream);
+// device flag "rb_land_accumulate saw an intensity that is not a small integer" of this context (land.cu)
+int rb_land_inexact_flag(rb_ctx* ctx, int32_t** flag, cudaStream_t stream);
 // bounds of the first *n_dev points (n_dev on the device, at most n_max): no host knowledge of n needed (land.cu)
 int rb_bounds_devn(rb_ctx* ctx, const float* x, const float* y, const int64_t* n_dev, int64_t n_max, float* out4, cudaStream_t stream);

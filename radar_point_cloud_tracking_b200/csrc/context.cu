@@ -45,6 +45,8 @@ extern "C" int rb_create(int device, rb_ctx** out) {
     ctx->cc_major = prop.major;
     ctx->cc_minor = prop.minor;
     ctx->l2_bytes = prop.l2CacheSize;
+    int prio_low = 0, prio_high = 0;
+    if (cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high) == cudaSuccess) ctx->prio_high = prio_high;
     memset(&ctx->last_stats, 0, sizeof ctx->last_stats);
     ctx->pinned_cap = 1 << 20;                     // 1 MiB: frame offsets of 130k frames fit without a re-allocation
     e = cudaMallocHost(&ctx->pinned, ctx->pinned_cap);
@@ -55,7 +57,7 @@ extern "C" int rb_create(int device, rb_ctx** out) {
     }
     // diagnostic defaults from the environment (experiments that must reach every context of a process, worker threads'
     // included): RB_OPT_<NAME>=<integer> is rb_set_option(ctx, "<name>", value)
-    static const char* const env_opts[] = {"carveout", "spoke_ring", "spoke_l2_hint", "dbscan_mode", "spoke_mask_variant"};
+    static const char* const env_opts[] = {"carveout", "spoke_ring", "spoke_l2_hint", "dbscan_mode", "spoke_mask_variant", "mask_gate", "mask_priority"};
     for (const char* name : env_opts) {
         char var[64] = "RB_OPT_";
         size_t k = strlen(var);
@@ -109,6 +111,8 @@ extern "C" int rb_set_option(rb_ctx* ctx, const char* name, int64_t value) {
         return RB_OK;
     }
     if (!strcmp(name, "spoke_l2_hint")) { ctx->opt_spoke_l2_hint = value != 0; return RB_OK; }
+    if (!strcmp(name, "mask_gate")) { ctx->opt_mask_gate = value != 0; return RB_OK; }
+    if (!strcmp(name, "mask_priority")) { ctx->opt_mask_priority = value != 0; return RB_OK; }
     if (!strcmp(name, "carveout")) {
         RB_REQUIRE(value >= -1 && value <= 100, "carveout: -1 = the driver's choice per kernel, 0..100 = percent of the SM's shared memory");
         ctx->opt_carveout = (int)value;
@@ -127,6 +131,8 @@ extern "C" int64_t rb_get_info(rb_ctx* ctx, const char* name) {
     if (!strcmp(name, "spoke_last_variant")) return ctx->spoke_last_variant;
     if (!strcmp(name, "spoke_ring")) return ctx->opt_spoke_ring;
     if (!strcmp(name, "spoke_l2_hint")) return ctx->opt_spoke_l2_hint;
+    if (!strcmp(name, "mask_gate")) return ctx->opt_mask_gate;
+    if (!strcmp(name, "mask_priority")) return ctx->opt_mask_priority;
     if (!strcmp(name, "carveout")) return ctx->opt_carveout;
     // device time of the last profiled rb_spoke_to_points, per kernel, in nanoseconds (syncs on its last event)
     int k = !strcmp(name, "spoke_mask_ns") ? 0 : !strcmp(name, "spoke_offsets_ns") ? 1 : !strcmp(name, "spoke_emit_ns") ? 2 : -1;

@@ -384,36 +384,34 @@ __global__ void __launch_bounds__(DB_THREADS) dbg_keyout_kernel(int n, const uin
 // cluster of a core neighbour q may be joined only if it started before the border point was looked at (its start
 // point = smallest core index = comp_key < the border point's index) or q IS the start point.
 template <int DIM, bool WF>
-__global__ void __launch_bounds__(DB_THREADS) dbg_border_kernel(Sorted s, DbGrid g, int n, double eps2, float eps_t,
+__global__ void __launch_bounds__(DB_THREADS) dbg_border_kernel(Sorted s, DbGrid g, double eps2, float eps_t,
                                                                const uint8_t* __restrict__ core, const int* __restrict__ slabel,
                                                                const int* __restrict__ sidx, const long long* __restrict__ comp_key,
-                                                               int32_t* __restrict__ labels,
-                                                               unsigned long long* __restrict__ ctr) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
+                                                               const int* __restrict__ open_list, const int* __restrict__ n_open,
+                                                               int32_t* __restrict__ labels, unsigned long long* __restrict__ ctr) {
+    // one thread per LISTED point (core == 0: not core, not alone); everything else got its label from the gather kernel
+    const int total = *n_open;
     unsigned long long tests = 0;
-    if (p < n) {
-        int out = core[p] == 1 ? slabel[p] : -1;
-        if (core[p] == 0) {
-            Pt<DIM> a = load_pt<DIM>(s, p);
-            int best = INT_MAX;
-            for_each_candidate<DIM>(g, s.cell_start, s.cell[p], [&](int q) {
-                if (core[q] == 1) {
-                    int lq = slabel[q];
-                    if (lq < best) {                          // only a smaller id can change the answer
-                        if (WF) {
-                            const int oq = sidx[q];
-                            const long long start = comp_key[oq];
-                            if (!(start < (long long)sidx[p] || start == (long long)oq)) return true;
-                        }
-                        ++tests;
-                        if (is_neighbour<DIM>(a, load_pt<DIM>(s, q), eps2, eps_t)) best = lq;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int p = open_list[i];
+        Pt<DIM> a = load_pt<DIM>(s, p);
+        int best = INT_MAX;
+        for_each_candidate<DIM>(g, s.cell_start, s.cell[p], [&](int q) {
+            if (core[q] == 1) {
+                int lq = slabel[q];
+                if (lq < best) {                          // only a smaller id can change the answer
+                    if (WF) {
+                        const int oq = sidx[q];
+                        const long long start = comp_key[oq];
+                        if (!(start < (long long)sidx[p] || start == (long long)oq)) return true;
                     }
+                    ++tests;
+                    if (is_neighbour<DIM>(a, load_pt<DIM>(s, q), eps2, eps_t)) best = lq;
                 }
-                return best != 0;                             // id 0 cannot be beaten
-            });
-            if (best != INT_MAX) out = best;
-        }
-        labels[sidx[p]] = out;
+            }
+            return best != 0;                             // id 0 cannot be beaten
+        });
+        if (best != INT_MAX) labels[sidx[p]] = best;
     }
     add_counter(ctr, tests);
 }
@@ -480,6 +478,10 @@ __global__ void __launch_bounds__(DB_THREADS) dbt_count_kernel(Sorted s, DbGrid 
     add_counter(ctr, tests);
 }
 
+// (Round 2 tried the count in two passes - bucket sizes first, the undecided points compacted and then counted by EIGHT
+// lanes per point with a group reduction after every row: 0.94 ms instead of 0.48 ms per 1024-frame block. The kernel is
+// bound by the number of instructions per point, not by idle lanes: spreading a point over lanes adds index arithmetic and
+// shuffles and loses part of the early exit (151 M instead of 124 M tests). Not kept; profiles/r02_tail_kernels.txt.)
 __global__ void __launch_bounds__(DB_THREADS) dbt_bucket_init_kernel(int64_t n_cells, int* __restrict__ b_ncore, int* __restrict__ b_parent,
                                                                     long long* __restrict__ b_minkey, int* __restrict__ n_cb) {
     int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -860,75 +862,99 @@ __global__ void __launch_bounds__(DB_THREADS) dbt_keyout_kernel(int n, const uin
     comp_key[sidx[p]] = k;
 }
 
-// sorted copy of the core labels + the label of every bucket that holds cores (all its cores share it)
+// sorted copy of the core labels + the label of every bucket that holds cores (all its cores share it); final label of
+// every core point (its id) and of every point that is certainly noise (-1); the points that may be border points
+// (core == 0: not core, but not alone) are LISTED - one warp-aggregated atomic per warp - so that the border search runs
+// over a dense list instead of one busy lane in a hundred.
 __global__ void __launch_bounds__(DB_THREADS) db_gather_labels_kernel(int n, const uint8_t* __restrict__ core, const int* __restrict__ sidx,
-                                                                     const int* __restrict__ scell, const int32_t* __restrict__ core_label,
-                                                                     int* __restrict__ slabel, int* __restrict__ b_label) {
+                                                                     const int* __restrict__ scell, const int32_t* core_label,
+                                                                     int* __restrict__ slabel, int* __restrict__ b_label, int32_t* labels,
+                                                                     int* __restrict__ open_list, int* __restrict__ n_open) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    int lab = -1;
-    if (core[p] == 1) { lab = core_label[sidx[p]]; if (b_label) b_label[scell[p]] = lab; }
-    slabel[p] = lab;
+    bool open = false;
+    if (p < n) {
+        const int orig = sidx[p];
+        int lab = -1;
+        if (core[p] == 1) { lab = core_label[orig]; if (b_label) b_label[scell[p]] = lab; }     // (core_label may alias labels:
+        slabel[p] = lab;                                                                         //  element orig belongs to this thread)
+        labels[orig] = lab;
+        open = core[p] == 0;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, open);
+    if (m) {
+        int base = 0;
+        if (rb_lane() == (unsigned)(__ffs(m) - 1)) base = atomicAdd(n_open, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (open) open_list[base + __popc(m & rb_lanemask_lt())] = p;
+    }
 }
 
+// One WARP per listed point (core == 0). Step 1, lanes over the time bins of the own spatial cell: cores there are
+// neighbours by construction, their bucket labels count without a test. Step 2, lanes over the ROWS of the window (a row =
+// the buckets with the same dt, dz, dy): only buckets whose label can lower the lane's best id are searched for ONE core
+// point within eps. The warp's answer is the minimum over the lanes.
+// (Round 1 ran this search with one thread per point over ALL points: the ~1 % that are border candidates sat alone in
+// their warps - 1.2-1.9 active lanes per warp, 0.30 ms per 1024-frame block.)
 template <int DIM, bool WF>
-__global__ void __launch_bounds__(DB_THREADS) dbt_border_kernel(Sorted s, DbGrid g, int n, double eps2, const uint8_t* __restrict__ core,
-                                                               const int* __restrict__ slabel, const int* __restrict__ sidx,
-                                                               const int* __restrict__ b_ncore, const int* __restrict__ core_start,
-                                                               const int* __restrict__ b_label, const int* __restrict__ b_parent,
-                                                               const long long* __restrict__ b_minkey, int32_t* __restrict__ labels,
-                                                               unsigned long long* __restrict__ ctr) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(DB_THREADS) dbt_border_kernel(Sorted s, DbGrid g, double eps2, const uint8_t* __restrict__ core,
+                                                               const int* __restrict__ sidx, const int* __restrict__ open_list,
+                                                               const int* __restrict__ n_open, const int* __restrict__ b_ncore,
+                                                               const int* __restrict__ core_start, const int* __restrict__ b_label,
+                                                               const int* __restrict__ b_parent, const long long* __restrict__ b_minkey,
+                                                               int32_t* __restrict__ labels, unsigned long long* __restrict__ ctr) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const unsigned lane = rb_lane();
+    const int total = *n_open;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int per_t = g.n[0] * g.n[1] * g.n[2];
     unsigned long long tests = 0;
-    if (p < n) {
-        int out = core[p] == 1 ? slabel[p] : -1;
-        if (core[p] == 0) {
-            const int cell = s.cell[p];
-            const CellPos c = decode_cell(g, cell);
-            const Window w = window_of<DIM>(g, c);
-            const int per_t = g.n[0] * g.n[1] * g.n[2];
-            const int sp = cell - c.tb * per_t;
-            int best = INT_MAX;
-            // cores of the own spatial cell inside the time window are neighbours
-            const long long me = sidx[p];
-            for (int tt = w.t0; tt <= w.t1; ++tt) {
-                const int b = tt * per_t + sp;
-                if (b_ncore[b] <= 0) continue;
-                if (WF) {
-                    // WF border rule: the bucket's cluster must have started before this point was looked at, or its
-                    // start point itself (the core whose index is the component key) must be among the neighbours
-                    const long long start = b_minkey[b_parent[b]];
-                    bool ok = start < me;
-                    for (int q = s.cell_start[b]; !ok && q < s.cell_start[b + 1]; ++q) ok = core[q] == 1 && (long long)sidx[q] == start;
-                    if (!ok) continue;
-                }
-                best = min(best, b_label[b]);
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += n_warps) {
+        const int p = open_list[w];
+        const int cell = s.cell[p];
+        const CellPos c = decode_cell(g, cell);
+        const Window win = window_of<DIM>(g, c);
+        const int sp = cell - c.tb * per_t;
+        const long long me = sidx[p];
+        int best = INT_MAX;
+        for (int tt = win.t0 + (int)lane; tt <= win.t1; tt += 32) {
+            const int b = tt * per_t + sp;
+            if (b_ncore[b] <= 0) continue;
+            if (WF) {
+                // WF border rule: the bucket's cluster must have started before this point was looked at, or its start
+                // point itself (the core whose index is the component key) must be among the neighbours
+                const long long start = b_minkey[b_parent[b]];
+                bool ok = start < me;
+                for (int q = s.cell_start[b]; !ok && q < s.cell_start[b + 1]; ++q) ok = core[q] == 1 && (long long)sidx[q] == start;
+                if (!ok) continue;
             }
-            if (best != 0) {
-                const Pt<DIM> a = load_pt<DIM>(s, p);
-                for (int tt = w.t0; tt <= w.t1 && best != 0; ++tt)
-                    for (int zz = w.z0; zz <= w.z1 && best != 0; ++zz)
-                        for (int yy = w.y0; yy <= w.y1 && best != 0; ++yy) {
-                            const int row = ((tt * g.n[2] + zz) * g.n[1] + yy) * g.n[0];
-                            if (core_start[row + w.x1 + 1] == core_start[row + w.x0]) continue;      // no core in this row
-                            for (int xx = w.x0; xx <= w.x1; ++xx) {
-                                const int b = row + xx;
-                                if (b_ncore[b] == 0 || (xx == c.cx && yy == c.cy && zz == c.cz)) continue;
-                                const int lb = b_label[b];
-                                if (lb >= best) continue;                 // only a smaller id can change the answer
-                                const long long start = WF ? b_minkey[b_parent[b]] : 0;
-                                const bool any_core = !WF || start < me;   // WF: else only the start point itself counts
-                                for (int q = s.cell_start[b]; q < s.cell_start[b + 1]; ++q) {
-                                    if (core[q] != 1 || (!any_core && (long long)sidx[q] != start)) continue;
-                                    ++tests;
-                                    if (near_enough<DIM>(a, load_pt<DIM>(s, q), eps2)) { best = lb; break; }
-                                }
-                            }
-                        }
-            }
-            if (best != INT_MAX) out = best;
+            best = min(best, b_label[b]);
         }
-        labels[sidx[p]] = out;
+        best = __reduce_min_sync(FULL, best);
+        if (best != 0) {
+            const Pt<DIM> a = load_pt<DIM>(s, p);
+            const int ny = win.y1 - win.y0 + 1, nz = win.z1 - win.z0 + 1, nt = win.t1 - win.t0 + 1;
+            const int rows = ny * nz * nt;
+            for (int r = (int)lane; r < rows; r += 32) {
+                const int yy = win.y0 + r % ny, zz = win.z0 + (r / ny) % nz, tt = win.t0 + r / (ny * nz);
+                const int row = ((tt * g.n[2] + zz) * g.n[1] + yy) * g.n[0];
+                if (core_start[row + win.x1 + 1] == core_start[row + win.x0]) continue;          // no core in this row
+                for (int xx = win.x0; xx <= win.x1 && best != 0; ++xx) {
+                    const int b = row + xx;
+                    if (b_ncore[b] == 0 || (xx == c.cx && yy == c.cy && zz == c.cz)) continue;
+                    const int lb = b_label[b];
+                    if (lb >= best) continue;                 // only a smaller id can change the answer
+                    const long long start = WF ? b_minkey[b_parent[b]] : 0;
+                    const bool any_core = !WF || start < me;   // WF: else only the start point itself counts
+                    for (int q = s.cell_start[b]; q < s.cell_start[b + 1]; ++q) {
+                        if (core[q] != 1 || (!any_core && (long long)sidx[q] != start)) continue;
+                        ++tests;
+                        if (near_enough<DIM>(a, load_pt<DIM>(s, q), eps2)) { best = lb; break; }
+                    }
+                }
+            }
+            best = __reduce_min_sync(FULL, best);
+        }
+        if (lane == 0 && best != INT_MAX) labels[me] = best;
     }
     add_counter(ctr, tests);
 }
@@ -1252,22 +1278,27 @@ int phase_assign(rb_ctx* ctx, rb_db_plan& P, const int32_t* core_label, int32_t*
     const int n = P.n;
     const unsigned blocks = (unsigned)rb_div_up(n, DB_THREADS);
     const Sorted s = sorted_view(P);
+    // labels of the core points and of the certain noise, bucket labels, list of the border candidates (P.rank is free here)
+    int* open_list = P.rank;
+    int* n_open = P.d_misc + 34;
+    RB_CUDA(cudaMemsetAsync(n_open, 0, sizeof(int), stream));
     RB_CUDA(rb_launch(ctx, db_gather_labels_kernel, dim3(blocks), dim3(DB_THREADS), 0, stream, n, P.core, P.sidx, P.scell, core_label, P.slabel,
-                                                              P.g.tight ? P.b_label : nullptr));
+                      P.g.tight ? P.b_label : nullptr, labels, open_list, n_open));
     RB_LAUNCH_CHECK(ctx);
     const bool wf = P.min_frames > 0;
+    const unsigned wblocks = (unsigned)(blocks < (unsigned)ctx->sm_count * 8 ? blocks : (unsigned)ctx->sm_count * 8);
     if (P.g.tight && wf)
-        RB_CUDA(rb_launch(ctx, dbt_border_kernel<DIM, true>, dim3(blocks), dim3(DB_THREADS), 0, stream, s, P.g, n, P.eps2, P.core, P.slabel, P.sidx, P.b_ncore, P.core_start,
-                                                                        P.b_label, P.b_parent, P.b_minkey, labels, P.d_ctr + 2));
+        RB_CUDA(rb_launch(ctx, dbt_border_kernel<DIM, true>, dim3(wblocks), dim3(DB_THREADS), 0, stream, s, P.g, P.eps2, P.core, P.sidx, open_list, n_open,
+                          P.b_ncore, P.core_start, P.b_label, P.b_parent, P.b_minkey, labels, P.d_ctr + 2));
     else if (P.g.tight)
-        RB_CUDA(rb_launch(ctx, dbt_border_kernel<DIM, false>, dim3(blocks), dim3(DB_THREADS), 0, stream, s, P.g, n, P.eps2, P.core, P.slabel, P.sidx, P.b_ncore, P.core_start,
-                                                                         P.b_label, P.b_parent, P.b_minkey, labels, P.d_ctr + 2));
+        RB_CUDA(rb_launch(ctx, dbt_border_kernel<DIM, false>, dim3(wblocks), dim3(DB_THREADS), 0, stream, s, P.g, P.eps2, P.core, P.sidx, open_list, n_open,
+                          P.b_ncore, P.core_start, P.b_label, P.b_parent, P.b_minkey, labels, P.d_ctr + 2));
     else if (wf)
-        RB_CUDA(rb_launch(ctx, dbg_border_kernel<DIM, true>, dim3(blocks), dim3(DB_THREADS), 0, stream, s, P.g, n, P.eps2, P.eps_t, P.core, P.slabel, P.sidx, P.comp_key, labels,
-                                                                        P.d_ctr + 2));
+        RB_CUDA(rb_launch(ctx, dbg_border_kernel<DIM, true>, dim3(wblocks), dim3(DB_THREADS), 0, stream, s, P.g, P.eps2, P.eps_t, P.core, P.slabel, P.sidx,
+                          P.comp_key, open_list, n_open, labels, P.d_ctr + 2));
     else
-        RB_CUDA(rb_launch(ctx, dbg_border_kernel<DIM, false>, dim3(blocks), dim3(DB_THREADS), 0, stream, s, P.g, n, P.eps2, P.eps_t, P.core, P.slabel, P.sidx, P.comp_key, labels,
-                                                                         P.d_ctr + 2));
+        RB_CUDA(rb_launch(ctx, dbg_border_kernel<DIM, false>, dim3(wblocks), dim3(DB_THREADS), 0, stream, s, P.g, P.eps2, P.eps_t, P.core, P.slabel, P.sidx,
+                          P.comp_key, open_list, n_open, labels, P.d_ctr + 2));
     RB_LAUNCH_CHECK(ctx);
     return RB_OK;
 }

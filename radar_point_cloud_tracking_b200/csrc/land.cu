@@ -103,66 +103,129 @@ __device__ __forceinline__ AxisGuess axis_guess(const double* __restrict__ edges
 }
 
 // ---- accumulate -------------------------------------------------------------------------------------
-// Privatised histogram in shared memory (int32 count + float64 sum per cell), flushed with one
-// global atomic per touched cell and block.
+// np.add.at(count, (ix, iy), 1) and np.add.at(isum, (ix, iy), intensity) (T4:388-389) add one point after the other; a
+// parallel float64 sum is order dependent - unless every addend is an integer. Radar echoes ARE integers (0..255,
+// PIPELINE_DOCUMENTATION.txt:47), so the fast path works in integer arithmetic, which is exact in any order, and CHECKS
+// that assumption on the device: an intensity that is not an integer in [0, 65535] raises a flag (*inexact); the caller
+// then repeats the accumulation with rb_land_accumulate_ordered, which adds in the reference's order for any input.
+//
+// Privatised histogram in shared memory (int32 count + uint32 sum per cell, 8 bytes: the whole ~93 x 93 grid of a
+// 231 m sweep takes 69 KB, so two CTAs fit beside the mask kernel's ring), flushed to the global grids every 65536 points
+// per block (65536 x 65535 < 2^32) with one atomic pair per touched cell. A thread takes ACC_ITEMS CONSECUTIVE points -
+// neighbouring range bins of one spoke, a run of which falls into one cell - and the lanes of a warp that close a run in
+// the same cell (land: most points sit in a few dozen cells) combine them with __match_any_sync / __reduce_add_sync
+// before ONE lane touches shared memory: the shared atomics, serialised per address, were the kernel's limit.
 constexpr int ACC_ITEMS = 8;
+constexpr int ACC_FLUSH_POINTS = 65536;
 __global__ void __launch_bounds__(LD_THREADS) land_accumulate_smem(const float* __restrict__ x, const float* __restrict__ y,
                                                                   const float* __restrict__ inten, int64_t n,
                                                                   GridArgs g, int32_t* __restrict__ count,
-                                                                  double* __restrict__ isum) {
+                                                                  double* __restrict__ isum, int32_t* __restrict__ inexact) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int cells = g.nx * g.ny;
-    double* s_sum = reinterpret_cast<double*>(smem);
-    int* s_cnt = reinterpret_cast<int*>(s_sum + cells);
-    double* s_xe = reinterpret_cast<double*>(s_cnt + ((cells + 1) & ~1));
+    double* s_xe = reinterpret_cast<double*>(smem);
     double* s_ye = s_xe + g.nxe;
-    for (int i = threadIdx.x; i < cells; i += blockDim.x) { s_sum[i] = 0.0; s_cnt[i] = 0; }
+    int* s_cnt = reinterpret_cast<int*>(s_ye + g.nye);
+    unsigned* s_sum = reinterpret_cast<unsigned*>(s_cnt + cells);
+    for (int i = threadIdx.x; i < cells; i += blockDim.x) { s_sum[i] = 0u; s_cnt[i] = 0; }
     for (int i = threadIdx.x; i < g.nxe; i += blockDim.x) s_xe[i] = g.xe[i];
     for (int i = threadIdx.x; i < g.nye; i += blockDim.x) s_ye[i] = g.ye[i];
     __syncthreads();
     const AxisGuess gx = axis_guess(s_xe, g.nxe), gy = axis_guess(s_ye, g.nye);
-    // A thread takes ACC_ITEMS CONSECUTIVE points: neighbours in the batch are neighbouring range bins of one spoke, so
-    // over land (where most points are, and where the atomics on a few hot cells collide) several in a row fall into
-    // the same cell and are added with one pair of atomics instead of one pair each.
-    const int64_t chunk = (int64_t)gridDim.x * blockDim.x * ACC_ITEMS;
-    for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * ACC_ITEMS; base < n; base += chunk) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const unsigned lane = rb_lane();
+    bool bad = false;
+    const int64_t step = (int64_t)blockDim.x * ACC_ITEMS;                       // points per block and iteration
+    const int64_t chunk = (int64_t)gridDim.x * step;
+    int since_flush = 0;
+    // every thread of the block runs the same number of iterations (the flush below is a block-wide barrier)
+    for (int64_t base0 = (int64_t)blockIdx.x * step; base0 < n; base0 += chunk) {
+        const int64_t base = base0 + (int64_t)threadIdx.x * ACC_ITEMS;
         int cur = -1, cnt = 0;
-        double sum = 0.0;
+        unsigned sum = 0;
 #pragma unroll
-        for (int j = 0; j < ACC_ITEMS; ++j) {
+        for (int j = 0; j <= ACC_ITEMS; ++j) {
             const int64_t i = base + j;
-            if (i >= n) break;
-            const int ix = cell_of((double)x[i], s_xe, g.nxe, g.nx, gx.e0, gx.inv_step);
-            const int iy = cell_of((double)y[i], s_ye, g.nye, g.ny, gy.e0, gy.inv_step);
-            const int c = ix * g.ny + iy;
-            if (c != cur) {
-                if (cnt) { atomicAdd(&s_cnt[cur], cnt); atomicAdd(&s_sum[cur], sum); }
-                cur = c; cnt = 0; sum = 0.0;
+            int c = -1;
+            unsigned v = 0;
+            if (j < ACC_ITEMS && i < n) {
+                const int ix = cell_of((double)x[i], s_xe, g.nxe, g.nx, gx.e0, gx.inv_step);
+                const int iy = cell_of((double)y[i], s_ye, g.nye, g.ny, gy.e0, gy.inv_step);
+                c = ix * g.ny + iy;
+                const float f = inten[i];
+                const int iv = (int)f;
+                bad |= !(f == (float)iv && iv >= 0 && iv <= 65535);
+                v = (unsigned)iv & 0xffffu;
             }
-            ++cnt;
-            sum += (double)inten[i];
+            // a run ends where the cell changes (and after the last point): lanes that close a run in the same cell pool it
+            const bool close = cnt > 0 && c != cur;
+            const unsigned closing = __ballot_sync(FULL, close);
+            if (close) {
+                const unsigned same = __match_any_sync(closing, cur);
+                const int tc = __reduce_add_sync(same, cnt);
+                const unsigned ts = __reduce_add_sync(same, sum);
+                if (lane == (unsigned)(__ffs(same) - 1)) { atomicAdd(&s_cnt[cur], tc); atomicAdd(&s_sum[cur], ts); }
+                cnt = 0; sum = 0;
+            }
+            if (c >= 0) { cur = c; ++cnt; sum += v; }
         }
-        if (cnt) { atomicAdd(&s_cnt[cur], cnt); atomicAdd(&s_sum[cur], sum); }
+        since_flush += (int)step;
+        if (since_flush + (int)step > ACC_FLUSH_POINTS || base0 + chunk >= n) {   // block-uniform condition
+            __syncthreads();
+            for (int i = threadIdx.x; i < cells; i += blockDim.x) {
+                const int c = s_cnt[i];
+                if (c) { atomicAdd(&count[i], c); atomicAdd(&isum[i], (double)s_sum[i]); s_cnt[i] = 0; s_sum[i] = 0u; }
+            }
+            __syncthreads();
+            since_flush = 0;
+        }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < cells; i += blockDim.x) {
-        int c = s_cnt[i];
-        if (c) { atomicAdd(&count[i], c); atomicAdd(&isum[i], s_sum[i]); }
-    }
+    if (__any_sync(FULL, bad) && lane == 0) atomicOr(inexact, 1);
 }
 
+// grids too large for shared memory: global atomics (float64 adds of integers are exact in any order; same check)
 __global__ void __launch_bounds__(LD_THREADS) land_accumulate_global(const float* __restrict__ x, const float* __restrict__ y,
                                                                     const float* __restrict__ inten, int64_t n,
                                                                     GridArgs g, int32_t* __restrict__ count,
-                                                                    double* __restrict__ isum) {
+                                                                    double* __restrict__ isum, int32_t* __restrict__ inexact) {
     const AxisGuess gx = axis_guess(g.xe, g.nxe), gy = axis_guess(g.ye, g.nye);
+    bool bad = false;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int ix = cell_of((double)x[i], g.xe, g.nxe, g.nx, gx.e0, gx.inv_step);
         int iy = cell_of((double)y[i], g.ye, g.nye, g.ny, gy.e0, gy.inv_step);
         int c = ix * g.ny + iy;
+        const float f = inten[i];
+        bad |= !(f == rintf(f) && fabsf(f) <= 16777216.f);
         atomicAdd(&count[c], 1);
-        atomicAdd(&isum[c], (double)inten[i]);
+        atomicAdd(&isum[c], (double)f);
     }
+    if (bad) atomicOr(inexact, 1);
+}
+
+// ---- the ordered accumulation (any intensities): cell id per point, then the points of every cell in their original
+// order (the stable partition of clusters.cu), then one thread per cell adds them one after the other in float64 -
+// exactly np.add.at's order
+__global__ void __launch_bounds__(LD_THREADS) land_cell_id_kernel(const float* __restrict__ x, const float* __restrict__ y, int64_t n,
+                                                                 GridArgs g, int32_t* __restrict__ cell) {
+    const AxisGuess gx = axis_guess(g.xe, g.nxe), gy = axis_guess(g.ye, g.nye);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        cell[i] = cell_of((double)x[i], g.xe, g.nxe, g.nx, gx.e0, gx.inv_step) * g.ny + cell_of((double)y[i], g.ye, g.nye, g.ny, gy.e0, gy.inv_step);
+}
+
+__global__ void __launch_bounds__(128) land_ordered_sum_kernel(const int32_t* __restrict__ seg_label, const int32_t* __restrict__ seg_count,
+                                                              const int64_t* __restrict__ seg_start, int64_t n_seg,
+                                                              const float* __restrict__ grouped, int32_t* __restrict__ count,
+                                                              double* __restrict__ isum) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_seg) return;
+    const int c = seg_label[k];
+    if (c < 0) return;
+    const int m = seg_count[k];
+    const float* __restrict__ v = grouped + seg_start[k];
+    double acc = isum[c];
+    for (int i = 0; i < m; ++i) acc = __dadd_rn(acc, (double)v[i]);
+    isum[c] = acc;
+    count[c] += m;
 }
 
 __global__ void land_cells_kernel(const int32_t* __restrict__ count, const double* __restrict__ isum, int64_t n_cells,
@@ -309,6 +372,16 @@ extern "C" int rb_bounds_counted(rb_ctx* ctx, const float* x, const float* y, co
     return rb_bounds_devn(ctx, x, y, n_dev, n_max, out4, (cudaStream_t)stream);
 }
 
+int rb_land_inexact_flag(rb_ctx* ctx, int32_t** flag, cudaStream_t stream) {
+    rb_scratch& slot = ctx->slots[RB_S_LAND_FLAG];
+    const void* before = slot.ptr;
+    void* p;
+    RB_TRY(rb_scratch_get(ctx, RB_S_LAND_FLAG, 64, &p));
+    if (slot.ptr != before) RB_CUDA(cudaMemsetAsync(p, 0, 64, stream));
+    *flag = (int32_t*)p;
+    return RB_OK;
+}
+
 extern "C" int rb_land_accumulate(rb_ctx* ctx, const float* x, const float* y, const float* inten, int64_t n,
                                   const double* x_edges, int n_x_edges, const double* y_edges, int n_y_edges,
                                   int32_t* count, double* isum, void* stream_) {
@@ -318,23 +391,84 @@ extern "C" int rb_land_accumulate(rb_ctx* ctx, const float* x, const float* y, c
     RB_REQUIRE(x && y && inten, "NULL points");
     cudaStream_t stream = (cudaStream_t)stream_;
     GridArgs g = make_grid_args(x_edges, n_x_edges, y_edges, n_y_edges);
+    int32_t* inexact;
+    RB_TRY(rb_land_inexact_flag(ctx, &inexact, stream));
     int64_t cells = (int64_t)g.nx * g.ny;
-    size_t smem = (size_t)cells * 8 + (size_t)((cells + 1) & ~1) * 4 + (size_t)(n_x_edges + n_y_edges) * 8;
-    int per_sm = smem <= 110 * 1024 ? 2 : 1;
-    int blocks = (int)(rb_div_up(n, LD_THREADS * 4) < (int64_t)ctx->sm_count * per_sm ? rb_div_up(n, LD_THREADS * 4)
-                                                                                      : (int64_t)ctx->sm_count * per_sm);
+    size_t smem = (size_t)cells * 8 + (size_t)(n_x_edges + n_y_edges) * 8;
+    const int per_sm = smem <= 72 * 1024 ? 3 : (smem <= 110 * 1024 ? 2 : 1);
+    int blocks = (int)(rb_div_up(n, LD_THREADS * ACC_ITEMS) < (int64_t)ctx->sm_count * per_sm ? rb_div_up(n, LD_THREADS * ACC_ITEMS)
+                                                                                              : (int64_t)ctx->sm_count * per_sm);
     if (smem <= 220 * 1024) {
         if (!ctx->attr_land) {                          // once per context (= per device): allow the largest grid that fits
             RB_CUDA(cudaFuncSetAttribute(land_accumulate_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             ctx->attr_land = true;
         }
-        RB_CUDA(rb_launch(ctx, land_accumulate_smem, dim3(blocks), dim3(LD_THREADS), smem, stream, x, y, inten, n, g, count, isum));
+        RB_CUDA(rb_launch(ctx, land_accumulate_smem, dim3(blocks), dim3(LD_THREADS), smem, stream, x, y, inten, n, g, count, isum, inexact));
     } else {
         blocks = (int)(rb_div_up(n, LD_THREADS) < (int64_t)ctx->sm_count * 8 ? rb_div_up(n, LD_THREADS)
                                                                            : (int64_t)ctx->sm_count * 8);
-        RB_CUDA(rb_launch(ctx, land_accumulate_global, dim3(blocks), dim3(LD_THREADS), 0, stream, x, y, inten, n, g, count, isum));
+        RB_CUDA(rb_launch(ctx, land_accumulate_global, dim3(blocks), dim3(LD_THREADS), 0, stream, x, y, inten, n, g, count, isum, inexact));
     }
     RB_LAUNCH_CHECK(ctx);
+    return RB_OK;
+}
+
+extern "C" int rb_land_accumulate_status(rb_ctx* ctx, int32_t* inexact_out, void* stream_) {
+    RB_REQUIRE(ctx && inexact_out, "NULL argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int32_t* flag;
+    RB_TRY(rb_land_inexact_flag(ctx, &flag, stream));
+    int32_t* h = (int32_t*)ctx->pinned;
+    RB_CUDA(cudaMemcpyAsync(h, flag, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    RB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t), stream));
+    RB_CUDA(cudaStreamSynchronize(stream));
+    *inexact_out = h[0];
+    return RB_OK;
+}
+
+extern "C" int rb_land_accumulate_status_async(rb_ctx* ctx, int32_t* dst, void* stream_) {
+    RB_REQUIRE(ctx && dst, "NULL argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int32_t* flag;
+    RB_TRY(rb_land_inexact_flag(ctx, &flag, stream));
+    RB_CUDA(cudaMemcpyAsync(dst, flag, sizeof(int32_t), cudaMemcpyDefault, stream));
+    RB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t), stream));
+    return RB_OK;
+}
+
+int rb_stable_group(rb_ctx* ctx, const float* values, const int32_t* labels, int64_t n, int64_t n_labels, int32_t* seg_label,
+                    int32_t* seg_count, int64_t* seg_start, int64_t cap_segments, float* grouped, int64_t* n_segments, cudaStream_t stream);
+
+extern "C" int rb_land_accumulate_ordered(rb_ctx* ctx, const float* x, const float* y, const float* inten, int64_t n,
+                                          const double* x_edges, int n_x_edges, const double* y_edges, int n_y_edges,
+                                          int32_t* count, double* isum, void* stream_) {
+    RB_REQUIRE(ctx && x_edges && y_edges && count && isum, "NULL argument");
+    RB_REQUIRE(n_x_edges >= 2 && n_y_edges >= 2, "need at least two edges per axis");
+    RB_REQUIRE(n < ((int64_t)1 << 31), "too many points");
+    if (n <= 0) return RB_OK;
+    RB_REQUIRE(x && y && inten, "NULL points");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GridArgs g = make_grid_args(x_edges, n_x_edges, y_edges, n_y_edges);
+    const int64_t cells = (int64_t)g.nx * g.ny;
+    // scratch: cell id per point, grouped intensities, segment table (one segment per occupied cell)
+    void* raw;
+    const size_t seg_cap = (size_t)cells + 1;
+    RB_TRY(rb_scratch_get(ctx, RB_S_LAND_ORDERED, sizeof(int32_t) * (size_t)n + sizeof(float) * (size_t)n + seg_cap * 16 + 64, &raw));
+    int64_t* seg_start = (int64_t*)raw;
+    int32_t* seg_label = (int32_t*)(seg_start + seg_cap);
+    int32_t* seg_count = seg_label + seg_cap;
+    int32_t* cell = seg_count + seg_cap;
+    float* grouped = (float*)(cell + n);
+    const int blocks = (int)(rb_div_up(n, LD_THREADS) < (int64_t)ctx->sm_count * 8 ? rb_div_up(n, LD_THREADS) : (int64_t)ctx->sm_count * 8);
+    RB_CUDA(rb_launch(ctx, land_cell_id_kernel, dim3(blocks), dim3(LD_THREADS), 0, stream, x, y, n, g, cell));
+    RB_LAUNCH_CHECK(ctx);
+    int64_t n_seg = 0;
+    RB_TRY(rb_stable_group(ctx, inten, cell, n, cells, seg_label, seg_count, seg_start, (int64_t)seg_cap, grouped, &n_seg, stream));
+    if (n_seg > 0) {
+        RB_CUDA(rb_launch(ctx, land_ordered_sum_kernel, dim3((unsigned)rb_div_up(n_seg, 128)), dim3(128), 0, stream, (const int32_t*)seg_label,
+                          (const int32_t*)seg_count, (const int64_t*)seg_start, n_seg, (const float*)grouped, count, isum));
+        RB_LAUNCH_CHECK(ctx);
+    }
     return RB_OK;
 }
 

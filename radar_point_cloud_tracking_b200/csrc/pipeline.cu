@@ -185,15 +185,28 @@ extern "C" int rb_detect_block(rb_ctx* ctx, const float* echo, const float* cos_
         double* d_ye = d_xe + nxe;
         RB_CUDA(cudaMemcpyAsync(d_xe, h_xe, sizeof(double) * (size_t)nxe, cudaMemcpyHostToDevice, stream));
         RB_CUDA(cudaMemcpyAsync(d_ye, h_ye, sizeof(double) * (size_t)nye, cudaMemcpyHostToDevice, stream));
-        RB_CUDA(cudaMemsetAsync(buf->count, 0, sizeof(int32_t) * (size_t)cells, stream));
-        RB_CUDA(cudaMemsetAsync(buf->isum, 0, sizeof(double) * (size_t)cells, stream));
-        RB_TRY(rb_land_accumulate(ctx, buf->x, buf->y, buf->inten, n_raw, d_xe, (int)nxe, d_ye, (int)nye, buf->count, buf->isum, stream_));
-        RB_TRY(rb_land_cells(ctx, buf->count, buf->isum, cells, built, prm->land_persistence, prm->land_min_intensity, buf->land, stream_));
-        RB_TRY(rb_land_filter(ctx, buf->x, buf->y, buf->inten, buf->gain, n_raw, buf->frame_off, F, d_xe, (int)nxe, d_ye, (int)nye,
-                              buf->land, buf->fx, buf->fy, buf->finten, buf->fgain, buf->f_frame_off, nullptr, stream_));
-        // read-back 2: how many points are left
-        RB_CUDA(cudaMemcpyAsync(h_off, buf->f_frame_off + F, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
-        RB_CUDA(cudaStreamSynchronize(stream));
+        // the fast accumulation is exact for integer-valued intensities (what a radar delivers) and says so itself; if
+        // the flag comes back with read-back 2, the land stage is repeated with the ordered accumulation (any input)
+        int32_t* d_inexact;
+        RB_TRY(rb_land_inexact_flag(ctx, &d_inexact, stream));
+        for (int pass = 0; pass < 2; ++pass) {
+            RB_CUDA(cudaMemsetAsync(buf->count, 0, sizeof(int32_t) * (size_t)cells, stream));
+            RB_CUDA(cudaMemsetAsync(buf->isum, 0, sizeof(double) * (size_t)cells, stream));
+            if (pass == 0)
+                RB_TRY(rb_land_accumulate(ctx, buf->x, buf->y, buf->inten, n_raw, d_xe, (int)nxe, d_ye, (int)nye, buf->count, buf->isum, stream_));
+            else
+                RB_TRY(rb_land_accumulate_ordered(ctx, buf->x, buf->y, buf->inten, n_raw, d_xe, (int)nxe, d_ye, (int)nye, buf->count, buf->isum, stream_));
+            RB_TRY(rb_land_cells(ctx, buf->count, buf->isum, cells, built, prm->land_persistence, prm->land_min_intensity, buf->land, stream_));
+            RB_TRY(rb_land_filter(ctx, buf->x, buf->y, buf->inten, buf->gain, n_raw, buf->frame_off, F, d_xe, (int)nxe, d_ye, (int)nye,
+                                  buf->land, buf->fx, buf->fy, buf->finten, buf->fgain, buf->f_frame_off, nullptr, stream_));
+            // read-back 2: how many points are left (+ the "inexact" flag of the fast accumulation)
+            RB_CUDA(cudaMemcpyAsync(h_off, buf->f_frame_off + F, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+            RB_CUDA(cudaMemcpyAsync(h_off + 1, d_inexact, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+            RB_CUDA(cudaMemsetAsync(d_inexact, 0, sizeof(int32_t), stream));
+            RB_CUDA(cudaStreamSynchronize(stream));
+            if (pass == 1 || *(const int32_t*)(h_off + 1) == 0) break;
+            res->land_ordered = 1;
+        }
         n_pts = h_off[0];
         res->land_applied = 1;
         res->filtered_is_raw = 0;

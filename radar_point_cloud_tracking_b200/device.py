@@ -16,6 +16,8 @@ import torch
 from . import _lib
 from ._lib import RadarB200Error, check, context, ptr, stream_ptr
 
+check_rc = check
+
 
 def _dev(t: torch.Tensor, dtype: torch.dtype, name: str) -> torch.Tensor:
     if not t.is_cuda:
@@ -194,19 +196,44 @@ def bounds_counted(x: torch.Tensor, y: torch.Tensor, n_dev: torch.Tensor) -> tor
 
 
 def land_accumulate(x, y, inten, x_edges: torch.Tensor, y_edges: torch.Tensor,
-                    count: Optional[torch.Tensor] = None, isum: Optional[torch.Tensor] = None):
-    """Accumulate per-cell point counts (int32) and intensity sums (float64) — T4:378-389."""
+                    count: Optional[torch.Tensor] = None, isum: Optional[torch.Tensor] = None, check: bool = True):
+    """Accumulate per-cell point counts (int32) and intensity sums (float64) — T4:378-389.
+
+    The fast kernel is exact for integer-valued intensities (radar echoes) and checks that on the device. With
+    ``check=True`` (one stream sync) a batch with other intensities is accumulated again by the ordered kernel, which adds
+    in ``np.add.at``'s order; ``check=False`` leaves the flag to the caller (``land_accumulate_flag``)."""
     ctx = context(x.device.index)
     x_edges = _dev(x_edges, torch.float64, "x_edges")
     y_edges = _dev(y_edges, torch.float64, "y_edges")
     nx, ny = x_edges.numel() - 1, y_edges.numel() - 1
-    if count is None:
+    fresh = count is None
+    if fresh:
         count = torch.zeros((nx, ny), dtype=torch.int32, device=x.device)
         isum = torch.zeros((nx, ny), dtype=torch.float64, device=x.device)
-    check(ctx.lib.rb_land_accumulate(ctx.handle, ptr(_dev(x, torch.float32, "x")), ptr(_dev(y, torch.float32, "y")),
-                                     ptr(_dev(inten, torch.float32, "inten")), x.numel(), ptr(x_edges), nx + 1,
-                                     ptr(y_edges), ny + 1, ptr(count), ptr(isum), stream_ptr()), "rb_land_accumulate")
+    elif check:
+        count0, isum0 = count.clone(), isum.clone()
+    args = (ctx.handle, ptr(_dev(x, torch.float32, "x")), ptr(_dev(y, torch.float32, "y")), ptr(_dev(inten, torch.float32, "inten")),
+            x.numel(), ptr(x_edges), nx + 1, ptr(y_edges), ny + 1, ptr(count), ptr(isum), stream_ptr())
+    check_rc(ctx.lib.rb_land_accumulate(*args), "rb_land_accumulate")
+    if check:
+        flag = C.c_int32(0)
+        check_rc(ctx.lib.rb_land_accumulate_status(ctx.handle, C.byref(flag), stream_ptr()), "rb_land_accumulate_status")
+        if flag.value:
+            if fresh:
+                count.zero_(), isum.zero_()
+            else:
+                count.copy_(count0), isum.copy_(isum0)
+            check_rc(ctx.lib.rb_land_accumulate_ordered(*args), "rb_land_accumulate_ordered")
     return count, isum
+
+
+def land_accumulate_flag(device_index: Optional[int] = None) -> torch.Tensor:
+    """Device int32[1]: 1 if a ``land_accumulate(check=False)`` call since the last query saw a non-integer intensity
+    (copy enqueued on the current stream, no sync; the library's flag is cleared)."""
+    ctx = context(device_index)
+    out = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", ctx.device))
+    check_rc(ctx.lib.rb_land_accumulate_status_async(ctx.handle, ptr(out), stream_ptr()), "rb_land_accumulate_status_async")
+    return out
 
 
 def land_cells(count: torch.Tensor, isum: torch.Tensor, num_frames: int, persistence: float,

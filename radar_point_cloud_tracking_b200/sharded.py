@@ -127,7 +127,11 @@ class CudaEngine:
         if n == 0:
             return (torch.zeros((len(xe) - 1, len(ye) - 1), dtype=torch.int32, device=self.device),
                     torch.zeros((len(xe) - 1, len(ye) - 1), dtype=torch.float64, device=self.device))
-        return self.dev.land_accumulate(batch.x[:n], batch.y[:n], batch.inten[:n], d_xe, d_ye)
+        return self.dev.land_accumulate(batch.x[:n], batch.y[:n], batch.inten[:n], d_xe, d_ye, check=False)
+
+    def land_flag(self):
+        """Device int32[1]: a non-integer intensity was seen by land_accumulate (read with the block's next read-back)."""
+        return self.dev.land_accumulate_flag(self.device.index)
 
     def land_cells(self, count, isum, built, persistence, min_intensity):
         return self.dev.land_cells(count, isum, built, persistence, min_intensity)
@@ -388,13 +392,14 @@ class ShardedDetection:
         self._tick("spoke+stats")
 
         # ---- land / stationary persistence filter over ALL ranks' frames --------------------------
-        pts, land, edges, b4 = raw, None, None, None
+        pts, land, edges, b4, inexact_d = raw, None, None, None, None
         built, n_all = int(allv[:, 0].sum()), int(allv[:, 1].sum())
         if cfg.land_filter and n_all > 0 and built > cfg.land_min_frames:
             have = allv[allv[:, 1] > 0]
             b4 = np.array([have[:, 2].min(), have[:, 3].max(), have[:, 4].min(), have[:, 5].max()], dtype=np.float32)
             xe, ye = trk.grid_edges_from_bounds(b4, cfg.land_resolution)
             count, isum = eng.land_accumulate(raw, xe, ye)
+            inexact_d = eng.land_flag() if hasattr(eng, "land_flag") else None
             if self.world > 1:
                 # collective 2: counts and sums in ONE float64 all-reduce (counts < 2^53 stay exact)
                 grids = torch.stack([count.to(f64), isum])
@@ -419,6 +424,11 @@ class ShardedDetection:
                                                      ids_d[F - hh:], per[F - hh:]]))
         yield 0
         meta = g_meta.cpu().numpy() if cluster else None       # read-back B
+        if inexact_d is not None and int(inexact_d.item()):
+            # the per-cell float64 sums of non-integer intensities depend on the order of addition; across ranks the
+            # reference's order (all points of all frames, one after the other) cannot be reproduced by a sum of partial sums
+            raise RadarB200Error("time-sharded land filter: intensities must be integer valued (radar echoes are 0..255); "
+                                 "use the single-GPU path for other data")
         off = off_d.cpu().numpy().astype(np.int64)
         pts.n = int(off[-1])
         self._tick("land+layout")

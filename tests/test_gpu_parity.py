@@ -510,6 +510,68 @@ def test_land_filter_full_size_vs_torch_float64(gpu):
     assert torch.equal(pts.frame_off, want_off)
 
 
+def test_land_accumulate_non_integer_intensities_take_the_ordered_path(gpu):
+    """np.add.at adds the points of a cell one after the other (T4:388-389). The fast kernel is exact for integer-valued
+    intensities and raises a flag otherwise; the ordered kernel then reproduces the sequential float64 sums bit for bit -
+    through device.land_accumulate and through the block driver (rb_detect_block, res.land_ordered)."""
+    import ctypes as C
+    from radar_point_cloud_tracking_b200 import _lib
+    rng = np.random.default_rng(61)
+    n = 400_000
+    x = rng.normal(0, 60, n).astype(np.float32)
+    y = rng.normal(0, 60, n).astype(np.float32)
+    x[: n // 2] = rng.normal(35, 1.5, n // 2).astype(np.float32)        # half of the points in a handful of cells
+    y[: n // 2] = rng.normal(-20, 1.5, n // 2).astype(np.float32)
+    inten = (rng.random(n) * 255 + rng.random(n) * 1e-3).astype(np.float32)
+    xe, ye = O.grid_edges(x.min(), x.max(), 5.0), O.grid_edges(y.min(), y.max(), 5.0)
+    ix, iy = O.cell_index(x, xe, len(xe) - 1), O.cell_index(y, ye, len(ye) - 1)
+    count = np.zeros((len(xe) - 1, len(ye) - 1), np.int32)
+    isum = np.zeros(count.shape, np.float64)
+    np.add.at(count, (ix, iy), 1)
+    np.add.at(isum, (ix, iy), inten)
+    d = torch.device("cuda:0")
+    tx, ty, ti, txe, tye = (torch.from_numpy(a).to(d) for a in (x, y, inten, xe, ye))
+    c1, s1 = gpu.land_accumulate(tx, ty, ti, txe, tye)
+    assert np.array_equal(c1.cpu().numpy(), count) and np.array_equal(s1.cpu().numpy(), isum)
+    # the flag really was what sent it there: check=False leaves the (order dependent) fast result and the raised flag
+    c2, s2 = gpu.land_accumulate(tx, ty, ti, txe, tye, check=False)
+    assert int(gpu.land_accumulate_flag(0).item()) == 1 and np.array_equal(c2.cpu().numpy(), count)
+    assert int(gpu.land_accumulate_flag(0).item()) == 0                    # reading clears it
+    # integer-valued intensities: fast path, exact, no flag
+    ti_int = torch.from_numpy(np.rint(inten)).to(d)
+    c3, s3 = gpu.land_accumulate(tx, ty, ti_int, txe, tye, check=False)
+    want = np.zeros(count.shape, np.float64)
+    np.add.at(want, (ix, iy), np.rint(inten))
+    assert int(gpu.land_accumulate_flag(0).item()) == 0 and np.array_equal(s3.cpu().numpy(), want)
+
+
+def test_block_driver_with_non_integer_echoes_matches_the_oracle(gpu):
+    """A recording whose echoes are not integers through rb_detect_block: the land stage repeats itself with the ordered
+    accumulation (res.land_ordered) and grids, mask and filtered points equal the numpy oracle's."""
+    from radar_point_cloud_tracking_b200 import _lib
+    from radar_point_cloud_tracking_b200.pipeline import DetectionConfig, DetectionPipeline
+    spec = syn.SweepSpec(seed=71, frames=14, spokes=128, bins=512, clutter_p=0.01, land_blobs=2, buoys=2, boats=2)
+    echo = syn.synth_echo(spec)
+    rng = np.random.default_rng(5)
+    echo = (echo * np.float32(0.731) + rng.random(echo.shape).astype(np.float32) * np.float32(0.01)).astype(np.float32)
+    cfg = DetectionConfig(intensity_threshold=7.0, land_min_intensity=60.0)
+    pipe = DetectionPipeline(cfg, 0)
+    c, s, r = pipe.spoke_tables(spec.angle_units(), spec.scale(), spec.frames, spec.bins)
+    res = pipe.run_device(torch.from_numpy(echo).cuda(), *(torch.from_numpy(t).cuda() for t in (c, s, r)), cluster=False)
+    frames = []
+    for f in range(spec.frames):
+        per_gain = {g: O.sweep_to_points(echo[f, gi], spec.angle_units(), spec.scale(), 7.0, 4) for gi, g in enumerate(spec.gains)}
+        frames.append(O.fuse_concat(per_gain)[0])
+    count, isum, edges = O.occupancy_grid(frames)
+    land = O.land_cells(count, isum, len(frames), min_intensity=60.0)
+    assert land.any() and not np.array_equal(isum, np.rint(isum))
+    assert np.array_equal(res.count.cpu().numpy(), count) and np.array_equal(res.isum.cpu().numpy(), isum)
+    assert np.array_equal(res.land.cpu().numpy().astype(bool), land)
+    want = np.concatenate([p[O.land_keep_mask(p, land, edges)] for p in frames])
+    p = res.points
+    assert np.array_equal(torch.stack([p.x[:p.n], p.y[:p.n], p.inten[:p.n]], 1).cpu().numpy(), want)
+
+
 def test_pipeline_is_deterministic_at_scale(gpu):
     """Atomics decide only WHICH thread links two components first, never the result: two runs over 48
     full-size frames give identical points and labels; labels are canonical (ids appear in index order)."""

@@ -120,12 +120,29 @@ def test_config2_3d_single_gain_vs_c_oracle(gpu):
     assert raw.n > 500_000
     t = _times(gpu, raw, F)
     _check_vs_oracle(gpu, raw.x[:raw.n], raw.y[:raw.n], raw.inten[:raw.n], t, 5.0, 1.0, 10, modes=(0,))
-    # a crop small enough for the tight 3-D table: the bucket algorithm in three dimensions at size
-    x, y, z = raw.x[:raw.n], raw.y[:raw.n], raw.inten[:raw.n]
-    keep = (x.abs() < 60) & (y.abs() < 60) & (t < 40)
-    xs, ys, zs, ts = (v[keep].contiguous() for v in (x, y, z, t))
-    assert ts.numel() > 30_000
-    _check_vs_oracle(gpu, xs, ys, zs, ts, 5.0, 1.0, 10, modes=(0, 1), want_tight=1)
+    assert gpu.stdbscan_stats()["tight"] == 0
+
+
+def test_tight_3d_buckets_at_size_vs_c_oracle(gpu):
+    """The bucket algorithm in THREE dimensions at size (200 k points in a 100 x 100 x 60 box over 16 integer times,
+    eps 5 / 1 / 10: 35 x 35 x 21 x 16 buckets fit the budget): dense blobs, thin noise, both algorithms."""
+    rng = np.random.default_rng(33)
+    n, B = 200_000, 200
+    pts = np.column_stack([rng.random(n) * 100, rng.random(n) * 100, rng.random(n) * 60]).astype(np.float32)
+    times = rng.integers(0, 16, n).astype(np.float32)
+    centres = np.column_stack([rng.random(B) * 100, rng.random(B) * 100, rng.random(B) * 60])
+    tcen = rng.integers(0, 16, B)
+    k = n * 17 // 20                                             # 85 % in blobs that live for three time steps, 15 % noise
+    which = rng.integers(0, B, k)
+    pts[:k] = (centres[which] + rng.normal(0, 1.2, (k, 3))).astype(np.float32)
+    times[:k] = np.clip(tcen[which] + rng.integers(-1, 2, k), 0, 15).astype(np.float32)
+    perm = rng.permutation(n)
+    pts, times = pts[perm], times[perm]
+    d = torch.device("cuda:0")
+    cols = [torch.from_numpy(np.ascontiguousarray(pts[:, j])).to(d) for j in range(3)]
+    _, want, want_core = _check_vs_oracle(gpu, cols[0], cols[1], cols[2], torch.from_numpy(times).to(d), 5.0, 1.0, 10, modes=(0, 1),
+                                          want_tight=1)
+    assert 0.5 < want_core.mean() < 0.95 and want.max() > 100 and (want < 0).mean() > 0.03
 
 
 @pytest.mark.parametrize("eps_t", [5.0, 7.5])

@@ -5,6 +5,7 @@ kernel concurrency across the worker streams.
 """
 import collections
 import json
+import re
 import sys
 from pathlib import Path
 
@@ -58,5 +59,30 @@ print(f"{n_blocks} blocks of {frames} frames, {workers} in flight: span {(t1 - t
       f"GPU busy {100 * busy / (t1 - t0):.1f} %; kernel time {tot / 1e3 / n_blocks:.3f} ms/block of which mask {mask_t / 1e3 / n_blocks:.3f}; "
       f"non-mask kernel time overlapping a mask kernel {ovl / 1e3 / n_blocks:.3f} ms/block")
 agg = collections.defaultdict(float)
-for e in ev: agg[e["name"].split("(")[0][-44:]] += e["dur"]
-for k, v in sorted(agg.items(), key=lambda x: -x[1])[:8]: print(f"  {v / 1e3 / n_blocks:7.3f} ms/block  {k}")
+def kname(e):
+    m = re.search(r"(\w+)(<[^(]*>)?\(", e["name"])
+    return m.group(1) if m else e["name"][:40]
+
+
+for e in ev: agg[kname(e)] += e["dur"]
+for k, v in sorted(agg.items(), key=lambda x: -x[1])[:40]: print(f"  {v / 1e3 / n_blocks:7.3f} ms/block  {k}")
+# where the time goes when NO mask kernel is running: the exposed tail
+gaps = []
+ms = sorted(mask)
+cur_end = t0
+for a, b in ms:
+    if a > cur_end: gaps.append((cur_end, a))
+    cur_end = max(cur_end, b)
+if cur_end < t1: gaps.append((cur_end, t1))
+exposed = sum(b - a for a, b in gaps)
+agg2 = collections.defaultdict(float)
+for e in ev:
+    if "spoke_mask" in e["name"]: continue
+    a, b = e["ts"], e["ts"] + e["dur"]
+    for ga, gb in gaps:
+        lo, hi = max(a, ga), min(b, gb)
+        if hi > lo: agg2[kname(e)] += hi - lo
+print(f"time with no mask kernel running: {exposed / 1e3 / n_blocks:.3f} ms/block; kernels running then (ms/block):")
+for k, v in sorted(agg2.items(), key=lambda x: -x[1])[:10]: print(f"  {v / 1e3 / n_blocks:7.3f}  {k}")
+conc = sum(min(b, mb) - max(a, ma) for i, (a, b) in enumerate(ms) for (ma, mb) in ms[i + 1:] if min(b, mb) > max(a, ma))
+print(f"two mask kernels running at once: {conc / 1e3 / n_blocks:.3f} ms/block")
