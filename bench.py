@@ -72,7 +72,7 @@ def parse_args():
     ap.add_argument("--clutter-p", type=float, default=0.003)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--streams", type=int, default=3, help="N=1: blocks in flight (host threads x CUDA streams x library contexts) "
+    ap.add_argument("--streams", type=int, default=4, help="N=1: blocks in flight (host threads x CUDA streams x library contexts) "
                     "for `value`; the time-sharded path (N>1) always has one block in flight per rank")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames per CPU worker in the reference/cpu_baseline sample; 0 = the workload's default")
     ap.add_argument("--shard-profile", action="store_true", help="N>1: print per-stage wall-clock of the sharded driver to stderr")

@@ -112,9 +112,9 @@ __device__ __forceinline__ AxisGuess axis_guess(const double* __restrict__ edges
 // Privatised histogram in shared memory (int32 count + uint32 sum per cell, 8 bytes: the whole ~93 x 93 grid of a
 // 231 m sweep takes 69 KB, so two CTAs fit beside the mask kernel's ring), flushed to the global grids every 65536 points
 // per block (65536 x 65535 < 2^32) with one atomic pair per touched cell. A thread takes ACC_ITEMS CONSECUTIVE points -
-// neighbouring range bins of one spoke, a run of which falls into one cell - and the lanes of a warp that close a run in
-// the same cell (land: most points sit in a few dozen cells) combine them with __match_any_sync / __reduce_add_sync
-// before ONE lane touches shared memory: the shared atomics, serialised per address, were the kernel's limit.
+// neighbouring range bins of one spoke, a run of which falls into one cell - and adds each run with one pair of native
+// integer shared-memory atomics (round 1 used float64 shared atomics, a compare-and-swap loop each: 0.22 ms per 1024-frame
+// block; pooling the runs of a warp with __match_any_sync first was measured too and is slower, 0.46 ms).
 constexpr int ACC_ITEMS = 8;
 constexpr int ACC_FLUSH_POINTS = 65536;
 __global__ void __launch_bounds__(LD_THREADS) land_accumulate_smem(const float* __restrict__ x, const float* __restrict__ y,
@@ -144,31 +144,23 @@ __global__ void __launch_bounds__(LD_THREADS) land_accumulate_smem(const float* 
         int cur = -1, cnt = 0;
         unsigned sum = 0;
 #pragma unroll
-        for (int j = 0; j <= ACC_ITEMS; ++j) {
+        for (int j = 0; j < ACC_ITEMS; ++j) {
             const int64_t i = base + j;
-            int c = -1;
-            unsigned v = 0;
-            if (j < ACC_ITEMS && i < n) {
-                const int ix = cell_of((double)x[i], s_xe, g.nxe, g.nx, gx.e0, gx.inv_step);
-                const int iy = cell_of((double)y[i], s_ye, g.nye, g.ny, gy.e0, gy.inv_step);
-                c = ix * g.ny + iy;
-                const float f = inten[i];
-                const int iv = (int)f;
-                bad |= !(f == (float)iv && iv >= 0 && iv <= 65535);
-                v = (unsigned)iv & 0xffffu;
+            if (i >= n) break;
+            const int ix = cell_of((double)x[i], s_xe, g.nxe, g.nx, gx.e0, gx.inv_step);
+            const int iy = cell_of((double)y[i], s_ye, g.nye, g.ny, gy.e0, gy.inv_step);
+            const int c = ix * g.ny + iy;
+            const float f = inten[i];
+            const int iv = (int)f;
+            bad |= !(f == (float)iv && iv >= 0 && iv <= 65535);
+            if (c != cur) {                                                     // a run ends where the cell changes
+                if (cnt) { atomicAdd(&s_cnt[cur], cnt); atomicAdd(&s_sum[cur], sum); }
+                cur = c; cnt = 0; sum = 0;
             }
-            // a run ends where the cell changes (and after the last point): lanes that close a run in the same cell pool it
-            const bool close = cnt > 0 && c != cur;
-            const unsigned closing = __ballot_sync(FULL, close);
-            if (close) {
-                const unsigned same = __match_any_sync(closing, cur);
-                const int tc = __reduce_add_sync(same, cnt);
-                const unsigned ts = __reduce_add_sync(same, sum);
-                if (lane == (unsigned)(__ffs(same) - 1)) { atomicAdd(&s_cnt[cur], tc); atomicAdd(&s_sum[cur], ts); }
-                cnt = 0; sum = 0;
-            }
-            if (c >= 0) { cur = c; ++cnt; sum += v; }
+            ++cnt;
+            sum += (unsigned)iv & 0xffffu;
         }
+        if (cnt) { atomicAdd(&s_cnt[cur], cnt); atomicAdd(&s_sum[cur], sum); }
         since_flush += (int)step;
         if (since_flush + (int)step > ACC_FLUSH_POINTS || base0 + chunk >= n) {   // block-uniform condition
             __syncthreads();

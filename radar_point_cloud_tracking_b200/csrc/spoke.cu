@@ -297,6 +297,11 @@ spoke_mask_tma_kernel(const T* __restrict__ echo, const SpokeGeom g, const ThrAr
                 break;
             }
             const long long st1 = min(st0 + (long long)MT_CHUNK, n_stages);
+            // lane t follows tile t of the stage through the chunk: sweep and tile-in-sweep by ONE division per chunk, then
+            // increments (a 64-bit division per stage on the producer's critical path costs more than the copy's issue)
+            long long my_tile = st0 * MT_TILES + lane;
+            int my_w = (int)(my_tile / g.tiles_per_sweep);
+            int my_tis = (int)(my_tile - (long long)my_w * g.tiles_per_sweep);
             for (long long st = st0; st < st1; ++st) {
                 const int s = it % MT_STAGES;
                 recycle(s);
@@ -306,10 +311,13 @@ spoke_mask_tma_kernel(const T* __restrict__ echo, const SpokeGeom g, const ThrAr
                 int v = 0;
                 const T* src = nullptr;
                 if ((int)lane < nt) {
-                    const TileRef<T> tr = tile_ref<T>(echo, g, t0 + lane);
-                    v = tr.valid;
-                    src = tr.src;
+                    const int cell0 = my_tis * SK_TILE;
+                    v = min(SK_TILE, g.sweep_cells - cell0);
+                    src = echo + (int64_t)my_w * g.sweep_cells + cell0;
                 }
+                my_tile += MT_TILES;
+                my_tis += MT_TILES;
+                while (my_tis >= g.tiles_per_sweep) { my_tis -= g.tiles_per_sweep; ++my_w; }
                 if ((int)lane < MT_TILES) m.valid[lane] = v;
                 if (lane == 0) { m.first_tile = t0; m.n_tiles = nt; }
                 const uint32_t bytes = __reduce_add_sync(0xffffffffu, (uint32_t)v * (uint32_t)sizeof(T));
