@@ -36,7 +36,7 @@ extern "C" {
 #define RB_ERR_ARG (-2)         /* bad argument                                   */
 #define RB_ERR_CAPACITY (-3)    /* caller-provided output capacity too small      */
 #define RB_ERR_NOMEM (-4)       /* scratch allocation failed                      */
-#define RB_ERR_NCCL (-5)        /* collective layer failure (reserved)            */
+#define RB_ERR_NCCL (-5)        /* collective layer (NCCL) failure                */
 
 typedef struct rb_ctx rb_ctx;
 
@@ -338,6 +338,55 @@ int64_t rb_arange_edges(float lo, float hi, double step, double* out, int64_t ca
  * SURVEY.md N4). Returns the table size (<= cap) or a negative RB_ERR_*; *n_clusters = number of clusters. */
 int64_t rb_stitch_components(const int64_t* keys, int64_t n_keys, const int64_t* pair_a, const int64_t* pair_b,
                              int64_t n_pairs, int64_t* table_keys, int32_t* table_ids, int64_t cap, int64_t* n_clusters);
+
+/* ---- multi-GPU: time sharding (SURVEY section 8 e) -----------------------------------------------------------------
+ * One process per GPU; rank r owns a contiguous block of frames and clusters it together with a floor(eps_time)-frame
+ * halo from each neighbour (radar_point_cloud_tracking_b200/sharded.py drives the protocol). The
+ * collectives are NCCL calls made BY THE LIBRARY on the caller's stream; the library binds to the NCCL the process already
+ * holds (the one PyTorch loaded; RB_NCCL_LIBRARY names another). A context owns one communicator; a rank that keeps
+ * several blocks in flight uses one context - hence one communicator - per block slot.
+ *   rb_comm_unique_id   HOST: a fresh NCCL unique id (128 bytes), to be created on one rank and handed to all others
+ *                       by whatever means the application has (torch.distributed broadcast, MPI, a file)
+ *   rb_comm_init        collective over all ranks: joins the communicator `unique_id` as `rank` of `world`
+ *   rb_comm_all_gather  send[bytes_per_rank] of every rank -> recv[world * bytes_per_rank] on every rank
+ *   rb_comm_all_reduce_sum / _grids   in-place sums (dtype 0 = int32, 1 = float64); _grids: the land filter's count and
+ *                       intensity grids in one NCCL group (sums of integers: exact in any order)
+ *   rb_comm_exchange    neighbour exchange in one NCCL group: part k of to_left goes to rank - 1, of to_right to rank + 1,
+ *                       from_left / from_right receive the neighbours' parts; sizes in bytes, 0 = nothing; device pointers
+ * None of these sync the stream. */
+int rb_comm_unique_id(uint8_t* out128);
+int rb_comm_init(rb_ctx* ctx, const uint8_t* unique_id128, int rank, int world);
+int rb_comm_destroy(rb_ctx* ctx);
+int rb_comm_info(rb_ctx* ctx, int* rank, int* world);
+int rb_comm_all_gather(rb_ctx* ctx, const void* send, void* recv, int64_t bytes_per_rank, void* stream);
+int rb_comm_all_reduce_sum(rb_ctx* ctx, void* buf, int64_t count, int dtype, void* stream);
+int rb_comm_all_reduce_grids(rb_ctx* ctx, int32_t* count, double* isum, int64_t cells, void* stream);
+int rb_comm_exchange(rb_ctx* ctx, int n_parts, const void* const* to_left, const int64_t* to_left_bytes,
+                     const void* const* to_right, const int64_t* to_right_bytes, void* const* from_left,
+                     const int64_t* from_left_bytes, void* const* from_right, const int64_t* from_right_bytes, void* stream);
+
+/* What the collectives of a block carry, assembled on the device (no sync, a few small launches each):
+ *   rb_shard_pack_stats   out7 float64 = [frames with points, points, x_min, x_max, y_min, y_max, capacity] from the raw
+ *                         frame offsets (int64[F+1]) and rb_bounds_counted's output
+ *   rb_shard_pack_layout  out int64[2 + 4 hh] = [points owned, first point of the last hh frames, ids and point counts of
+ *                         the first hh frames, ids and point counts of the last hh frames]; frame_ids: HOST int64[F]
+ *   rb_shard_local_index  times float32[n_loc] and global point index int64[n_loc] of the local problem
+ *                         [left halo (nl) | owned (n_own) | right halo (nr)]; head / ids: HOST arrays describing its
+ *                         frames (head[f] = first local point of frame f, head[n_local_frames] = n_loc); the three parts
+ *                         start at the global indices lbase / gbase / rbase
+ *   rb_shard_pack_keys    vec int64[5 + cap_keys]: the component keys (rb_stdbscan_components) of the core points of four
+ *                         zones [a, b) of the local problem (zones8: HOST int64[8]) followed by the keys that are their
+ *                         own global index (one per local component), compacted in order; vec[0..5) = number of keys up to
+ *                         the end of each of the five groups (they exceed cap_keys when the vector was too small) */
+int rb_shard_pack_stats(rb_ctx* ctx, const int64_t* frame_off, int64_t n_frames, const float* bounds4, int64_t cap, double* out7,
+                        void* stream);
+int rb_shard_pack_layout(rb_ctx* ctx, const int64_t* frame_off, int64_t n_frames, const int64_t* frame_ids_host, int hh, int64_t* out,
+                         void* stream);
+int rb_shard_local_index(rb_ctx* ctx, const int64_t* head_host, const float* ids_host, int64_t n_local_frames, int64_t nl,
+                         int64_t n_own, int64_t nr, int64_t lbase, int64_t gbase, int64_t rbase, float* times, int64_t* gidx,
+                         void* stream);
+int rb_shard_pack_keys(rb_ctx* ctx, const int64_t* key, const int64_t* gidx, int64_t n_loc, const int64_t* zones8_host, int64_t cap_keys,
+                       int64_t* vec, void* stream);
 
 /* ---- ingest (SURVEY section 8 f, rank 2) --------------------------------------------------------------------------
  * One radar sweep CSV parsed on the device; replaces the numeric part of pd.read_csv in load_radar_csv

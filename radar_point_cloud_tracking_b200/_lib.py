@@ -96,6 +96,18 @@ SIGNATURES = {
                                    c_vp, c_vp, c_vp, C.POINTER(c_i64), C.POINTER(c_i64), c_vp]),
     "rb_arange_edges": (c_i64, [c_f32, c_f32, c_f64, c_vp, c_i64]),
     "rb_stitch_components": (c_i64, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
+    "rb_comm_unique_id": (c_i32, [c_vp]),
+    "rb_comm_init": (c_i32, [c_vp, c_vp, c_i32, c_i32]),
+    "rb_comm_destroy": (c_i32, [c_vp]),
+    "rb_comm_info": (c_i32, [c_vp, C.POINTER(c_i32), C.POINTER(c_i32)]),
+    "rb_comm_all_gather": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "rb_comm_all_reduce_sum": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp]),
+    "rb_comm_all_reduce_grids": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "rb_comm_exchange": (c_i32, [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "rb_shard_pack_stats": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
+    "rb_shard_pack_layout": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_i32, c_vp, c_vp]),
+    "rb_shard_local_index": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "rb_shard_pack_keys": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
     "rb_csv_parse_sweep": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "rb_ply_append_ascii": (c_i32, [C.c_char_p, c_vp, c_vp, c_vp, c_vp, c_i64]),
     "rb_synth_echo": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),

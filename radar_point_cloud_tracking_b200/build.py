@@ -10,7 +10,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 INCLUDE = PKG.parent / "include"
 LIB = PKG / "libradarb200.so"
-SOURCES = ["context.cu", "spoke.cu", "land.cu", "dbscan.cu", "fuse.cu", "synth.cu", "pipeline.cu", "csv.cu", "plyfmt.cu", "clusters.cu"]
+SOURCES = ["context.cu", "spoke.cu", "land.cu", "dbscan.cu", "fuse.cu", "synth.cu", "pipeline.cu", "csv.cu", "plyfmt.cu", "clusters.cu", "comm.cu", "shard.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -62,7 +62,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     log = "".join(r[2] for r in results)
     failed = [r[0] for r in results if r[1] != 0]
     if not failed:
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *[str(obj_dir / (s + ".o")) for s in SOURCES]]
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *[str(obj_dir / (s + ".o")) for s in SOURCES], "-ldl"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         log += " ".join(cmd) + "\n" + res.stdout + res.stderr
         if res.returncode != 0:

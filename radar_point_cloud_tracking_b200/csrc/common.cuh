@@ -46,12 +46,14 @@ enum rb_slot {
     RB_S_CSV,               // csv ingest: newline counts per chunk, their scan, newline offsets
     RB_S_CLUSTERS,          // cluster records: (frame, label) slot tables, tile lists, segment scans
     RB_S_LAND_FLAG,         // land accumulate: "an intensity is not a small integer" flag
+    RB_S_SHARD_IDS, RB_S_SHARD_LOCAL, RB_S_SHARD_KEYS,   // time-sharded driver: staged frame ids, local frame list, key flags / ranks
     RB_S_GROUP_TMP,         // rb_stable_group: frame offsets of its single frame
     RB_S_LAND_ORDERED,      // land accumulate, ordered path: cell ids, grouped intensities, segment table
     RB_S_COUNT
 };
 
 struct rb_db_plan;
+struct rb_comm;
 
 struct rb_ctx {
     int device = 0;
@@ -65,6 +67,7 @@ struct rb_ctx {
     size_t pinned_cap = 0;
     rb_dbscan_stats last_stats;
     rb_db_plan* db_plan = nullptr;   // state shared by the rb_stdbscan_* phases (dbscan.cu)
+    rb_comm* comm = nullptr;         // NCCL communicator of this context (comm.cu, rb_comm_init)
     int opt_dbscan_mode = 0;         // 0 = auto, 1 = always the general algorithm, 2 = require the tight one
     int opt_spoke_mask_variant = 0;  // 0 = auto, 1 = register-staged mask kernel, 2 = require the TMA-staged one
     int spoke_last_variant = 0;      // mask kernel the last rb_spoke_to_points launched (1 / 2)
@@ -82,6 +85,7 @@ struct rb_ctx {
 
 void rb_set_error(const char* fmt, ...);
 void rb_db_plan_free(rb_ctx* ctx);
+void rb_comm_free(rb_ctx* ctx);
 int rb_scratch_get(rb_ctx* ctx, rb_slot slot, size_t bytes, void** out);
 
 #define RB_CUDA(call)                                                                      \

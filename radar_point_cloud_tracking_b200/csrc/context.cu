@@ -80,6 +80,7 @@ extern "C" void rb_destroy(rb_ctx* ctx) {
     for (int i = 0; i < 4; ++i)
         if (ctx->spoke_ev[i]) cudaEventDestroy(ctx->spoke_ev[i]);
     rb_db_plan_free(ctx);
+    rb_comm_free(ctx);
     delete ctx;
 }
 

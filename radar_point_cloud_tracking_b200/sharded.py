@@ -23,9 +23,12 @@ communicator (:meth:`ShardedDetection.run_blocks`).
 
 The result equals the single-GPU labels of the concatenated recording, id for id.
 
-The collectives and the stitching are host logic and device-agnostic torch plumbing; every numeric
-stage goes through an *engine* (:class:`CudaEngine` = the C ABI). The CPU tests drive the same logic
-over gloo with an oracle-backed engine.
+The protocol (what is exchanged when, the halo layout, the stitching) is host logic in this file; everything that
+touches data goes through an *engine*. :class:`CudaEngine` is the product: every numeric stage, the packing of what the
+collectives carry AND the collectives themselves (NCCL, ``rb_comm_*``) are calls into ``libradarb200.so`` on the block's
+own stream - no tensor arithmetic happens in Python. :class:`TorchEngineBase` implements the same bookkeeping and
+collectives with plain torch ops over ``torch.distributed``; the CPU tests derive an oracle-backed engine from it and
+drive this file's protocol over gloo.
 """
 from __future__ import annotations
 
@@ -81,8 +84,127 @@ def stitch_components(seg_keys: Sequence[Sequence[np.ndarray]], keys: Sequence[n
 
 
 # ------------------------------------------------------------------------------------------ engines
-class CudaEngine:
-    """Numeric stages on the current CUDA device through ``libradarb200.so``."""
+class TorchEngineBase:
+    """Bookkeeping and collectives of the protocol with torch ops over ``torch.distributed`` (any backend, any device).
+    The CPU test engine derives from this (numeric stages from the oracle, gloo underneath); :class:`CudaEngine`
+    overrides every method with library calls."""
+
+    #: collectives of all blocks share the backend's one stream: issue them only after the block's GPU work is done
+    wait_before_collective = True
+    rank, world, group = 0, 1, None
+
+    def attach(self, rank: int, world: int, group) -> None:
+        self.rank, self.world, self.group = rank, world, group
+
+    def prepare_slots(self, n_slots: int, slot_ctx) -> None:
+        """Called (collectively) before blocks run in ``n_slots`` block slots."""
+
+    def upload(self, arr, dtype=None) -> torch.Tensor:
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+        if dtype is not None and t.dtype != dtype:
+            t = t.to(dtype)
+        return t.to(self.device)
+
+    # -- what the collectives carry
+    def pack_stats(self, raw_off_d, b4_d, cap: int) -> torch.Tensor:
+        f64 = torch.float64
+        return torch.cat([torch.count_nonzero(torch.diff(raw_off_d))[None].to(f64), raw_off_d[-1:].to(f64), b4_d.to(f64),
+                          self.upload(np.array([cap], dtype=np.float64))])
+
+    def pack_layout(self, off_d, ids: np.ndarray, F: int, hh: int) -> torch.Tensor:
+        ids_d, per = self.upload(ids), torch.diff(off_d)
+        return torch.cat([off_d[F:F + 1], off_d[F - hh:F - hh + 1], ids_d[:hh], per[:hh], ids_d[F - hh:], per[F - hh:]])
+
+    def pack_keys(self, key, gidx, zones, n_loc: int, cap_k: int) -> torch.Tensor:
+        if n_loc == 0:
+            return torch.zeros(5 + cap_k, dtype=torch.int64, device=self.device)
+        seg_end = np.cumsum([b - a for a, b in zones] + [n_loc])        # ends of the five segments in the candidate vector
+        is_core, is_root = key >= 0, key == gidx
+        cand = torch.cat([key[a:b] for a, b in zones] + [key])
+        take = torch.cat([is_core[a:b] for a, b in zones] + [is_root])
+        pos = torch.cumsum(take, 0) - 1
+        buf = torch.zeros(5 + cap_k + 1, dtype=torch.int64, device=self.device)
+        # head of the vector: how many keys were taken up to the end of each segment (0 for a leading empty one)
+        buf[:5] = torch.where(self.upload(seg_end > 0), pos[self.upload(np.maximum(seg_end - 1, 0))] + 1, 0)
+        buf[torch.where(take & (pos < cap_k), pos + 5, 5 + cap_k)] = cand          # the last slot takes the rest
+        return buf[:5 + cap_k]
+
+    # -- collectives
+    def all_gather(self, mine: torch.Tensor) -> torch.Tensor:
+        """One fixed-length device vector per rank -> ``[world, len]`` (no sync; the caller yields before reading it)."""
+        if self.world == 1:
+            return mine[None]
+        out = torch.empty((self.world, mine.numel()), dtype=mine.dtype, device=self.device)
+        dist.all_gather_into_tensor(out, mine.contiguous()[None], group=self.group)
+        return out
+
+    def all_reduce_grids(self, count, isum):
+        if self.world == 1:
+            return count, isum
+        grids = torch.stack([count.to(torch.float64), isum])            # counts < 2^53 stay exact
+        dist.all_reduce(grids, op=dist.ReduceOp.SUM, group=self.group)
+        return grids[0].to(torch.int32), grids[1].contiguous()
+
+    def exchange(self, to_left, to_right, from_left, from_right) -> None:
+        """Lists of 1-D tensors: part k of ``to_left`` goes to rank - 1, of ``to_right`` to rank + 1; ``from_*`` are
+        preallocated views that receive the neighbours' parts (empty tensors are skipped)."""
+        ops, keep = [], []
+        if self.rank > 0:
+            for t in to_left:
+                if t.numel():
+                    keep.append(t.contiguous()); ops.append(dist.P2POp(dist.isend, keep[-1], self.rank - 1, group=self.group))
+            for t in from_left:
+                if t.numel():
+                    tmp = torch.empty_like(t); keep.append((t, tmp)); ops.append(dist.P2POp(dist.irecv, tmp, self.rank - 1, group=self.group))
+        if self.rank < self.world - 1:
+            for t in to_right:
+                if t.numel():
+                    keep.append(t.contiguous()); ops.append(dist.P2POp(dist.isend, keep[-1], self.rank + 1, group=self.group))
+            for t in from_right:
+                if t.numel():
+                    tmp = torch.empty_like(t); keep.append((t, tmp)); ops.append(dist.P2POp(dist.irecv, tmp, self.rank + 1, group=self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        for item in keep:
+            if isinstance(item, tuple):
+                item[0].copy_(item[1])
+
+    # -- the local problem [left halo | owned | right halo]
+    def local_problem(self, pts: PointBatch, n_own: int, lo_end: int, hi_start: int, nl: int, nr: int, head: np.ndarray,
+                      all_ids: np.ndarray, lbase: int, gbase: int, rbase: int):
+        n_loc = nl + n_own + nr
+        X = torch.empty(n_loc, dtype=torch.float32, device=self.device)
+        Y = torch.empty(n_loc, dtype=torch.float32, device=self.device)
+        X[nl:nl + n_own].copy_(pts.x[:n_own])
+        Y[nl:nl + n_own].copy_(pts.y[:n_own])
+        self.exchange([pts.x[:lo_end], pts.y[:lo_end]], [pts.x[hi_start:n_own], pts.y[hi_start:n_own]],
+                      [X[:nl], Y[:nl]], [X[nl + n_own:], Y[nl + n_own:]])
+        times, gidx = self.local_index(head, all_ids, nl, n_own, nr, lbase, gbase, rbase)
+        return X, Y, times, gidx
+
+    def local_index(self, head, all_ids, nl, n_own, nr, lbase, gbase, rbase):
+        n_loc = nl + n_own + nr
+        if n_loc == 0:
+            return (torch.zeros(0, dtype=torch.float32, device=self.device), torch.zeros(0, dtype=torch.int64, device=self.device))
+        times = self.expand_frame_times(self.upload(head), self.upload(all_ids.astype(np.float32)), n_loc)
+        gidx = torch.arange(n_loc, dtype=torch.int64, device=self.device)
+        gidx[:nl] += lbase
+        gidx[nl:nl + n_own] += gbase - nl
+        gidx[nl + n_own:] += rbase - nl - n_own
+        return times, gidx
+
+    def exchange_cores(self, core, nl: int, n_own: int, nr: int, lo_end: int, hi_start: int) -> None:
+        """Halo points take their OWNER's core flags (in place)."""
+        own = core[nl:nl + n_own]
+        self.exchange([own[:lo_end]], [own[hi_start:]], [core[:nl]], [core[nl + n_own:]])
+
+
+class CudaEngine(TorchEngineBase):
+    """The product engine: numeric stages, packing and collectives through ``libradarb200.so`` on the current CUDA device
+    and stream (torch allocates the buffers and provides the stream, nothing else)."""
+
+    wait_before_collective = False          # every block slot has its own communicator and issues on its own stream
 
     def __init__(self, device_index: Optional[int] = None):
         from . import device as dev
@@ -91,6 +213,46 @@ class CudaEngine:
             raise RadarB200Error("no CUDA device: the sharded detection path is GPU only (no CPU fallback)")
         self.dev = dev
         self.device = torch.device("cuda", torch.cuda.current_device() if device_index is None else device_index)
+        self._comm_slots = set()
+
+    # -- communicators: one per block slot (library context), created collectively
+    def prepare_slots(self, n_slots: int, slot_ctx) -> None:
+        import ctypes as C
+
+        from . import _lib
+
+        if self.world == 1:
+            return
+        for k in range(n_slots):
+            if k in self._comm_slots:
+                continue
+            with slot_ctx(k):
+                ctx = _lib.context(self.device.index)
+                uid = torch.zeros(128, dtype=torch.uint8)
+                if self.rank == 0:
+                    buf = (C.c_uint8 * 128)()
+                    _lib.check(ctx.lib.rb_comm_unique_id(buf), "rb_comm_unique_id")
+                    uid = torch.tensor(list(buf), dtype=torch.uint8)
+                if dist.get_backend(self.group) == "nccl":
+                    uid = uid.to(self.device)
+                dist.broadcast(uid, src=0, group=self.group)         # bootstrap only: the id travels over the caller's group
+                raw = bytes(uid.cpu().tolist())
+                _lib.check(ctx.lib.rb_comm_init(ctx.handle, raw, self.rank, self.world), "rb_comm_init")
+            self._comm_slots.add(k)
+
+    def _ctx(self):
+        from . import _lib
+        return _lib.context(self.device.index)
+
+    def upload(self, arr, dtype=None) -> torch.Tensor:
+        """Host array -> device tensor WITHOUT a stream sync: staged in pinned memory (torch's caching host allocator
+        recycles the block only after the copy has run) and copied asynchronously."""
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+        if dtype is not None and t.dtype != dtype:
+            t = t.to(dtype)
+        pinned = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        pinned.copy_(t)
+        return pinned.to(self.device, non_blocking=True)
 
     def spoke_to_points(self, echo, cos_tab, sin_tab, range_res, sweep_gain, thr, stride, gpf, cap=None) -> PointBatch:
         return self.dev.spoke_to_points(echo, cos_tab, sin_tab, range_res, sweep_gain, thr, stride, gains_per_frame=gpf, cap=cap)
@@ -117,7 +279,7 @@ class CudaEngine:
         cache = self.__dict__.setdefault("_edge_cache", {})       # one upload per distinct grid and block slot (stream)
         hit = cache.get(_lib.get_slot())
         if hit is None or hit[0] != key:
-            both = torch.from_numpy(np.concatenate([xe, ye])).to(self.device)
+            both = self.upload(np.concatenate([xe, ye]))
             hit = cache[_lib.get_slot()] = (key, (both[:len(xe)], both[len(xe):]))
         return hit[1]
 
@@ -149,6 +311,80 @@ class CudaEngine:
 
     def relabel(self, keys, table_keys, table_ids):
         return self.dev.relabel(keys, table_keys, table_ids)
+
+    # -- packing and collectives: library calls (kernels of csrc/shard.cu, NCCL through csrc/comm.cu)
+    def pack_stats(self, raw_off_d, b4_d, cap: int) -> torch.Tensor:
+        from ._lib import check, ptr, stream_ptr
+        ctx = self._ctx()
+        out = torch.empty(7, dtype=torch.float64, device=self.device)
+        check(ctx.lib.rb_shard_pack_stats(ctx.handle, ptr(raw_off_d), raw_off_d.numel() - 1, ptr(b4_d), int(cap), ptr(out), stream_ptr()),
+              "rb_shard_pack_stats")
+        return out
+
+    def pack_layout(self, off_d, ids: np.ndarray, F: int, hh: int) -> torch.Tensor:
+        from ._lib import check, ptr, stream_ptr
+        ctx = self._ctx()
+        out = torch.empty(2 + 4 * hh, dtype=torch.int64, device=self.device)
+        ids64 = np.ascontiguousarray(ids, dtype=np.int64)
+        check(ctx.lib.rb_shard_pack_layout(ctx.handle, ptr(off_d), int(F), ids64.ctypes.data, int(hh), ptr(out), stream_ptr()),
+              "rb_shard_pack_layout")
+        return out
+
+    def pack_keys(self, key, gidx, zones, n_loc: int, cap_k: int) -> torch.Tensor:
+        from ._lib import check, ptr, stream_ptr
+        ctx = self._ctx()
+        vec = torch.empty(5 + cap_k, dtype=torch.int64, device=self.device)
+        z = np.ascontiguousarray(np.array(zones, dtype=np.int64).reshape(-1))
+        check(ctx.lib.rb_shard_pack_keys(ctx.handle, ptr(key) if n_loc else None, ptr(gidx) if n_loc else None, int(n_loc), z.ctypes.data,
+                                         int(cap_k), ptr(vec), stream_ptr()), "rb_shard_pack_keys")
+        return vec
+
+    def all_gather(self, mine: torch.Tensor) -> torch.Tensor:
+        from ._lib import check, ptr, stream_ptr
+        if self.world == 1:
+            return mine[None]
+        ctx = self._ctx()
+        mine = mine.contiguous()
+        out = torch.empty((self.world, mine.numel()), dtype=mine.dtype, device=self.device)
+        check(ctx.lib.rb_comm_all_gather(ctx.handle, ptr(mine), ptr(out), mine.numel() * mine.element_size(), stream_ptr()),
+              "rb_comm_all_gather")
+        return out
+
+    def all_reduce_grids(self, count, isum):
+        from ._lib import check, ptr, stream_ptr
+        if self.world == 1:
+            return count, isum
+        ctx = self._ctx()
+        check(ctx.lib.rb_comm_all_reduce_grids(ctx.handle, ptr(count), ptr(isum), count.numel(), stream_ptr()), "rb_comm_all_reduce_grids")
+        return count, isum
+
+    def exchange(self, to_left, to_right, from_left, from_right) -> None:
+        import ctypes as C
+
+        from ._lib import check, stream_ptr
+        if self.world == 1:
+            return
+        k = len(to_left)
+        assert len(to_right) == k and len(from_left) == k and len(from_right) == k
+        ctx = self._ctx()
+        vp, i64 = C.c_void_p * k, C.c_int64 * k
+        nbytes = lambda ts: i64(*[t.numel() * t.element_size() for t in ts])
+        ptrs = lambda ts: vp(*[t.data_ptr() if t.numel() else None for t in ts])
+        check(ctx.lib.rb_comm_exchange(ctx.handle, k, ptrs(to_left), nbytes(to_left), ptrs(to_right), nbytes(to_right), ptrs(from_left),
+                                       nbytes(from_left), ptrs(from_right), nbytes(from_right), stream_ptr()), "rb_comm_exchange")
+
+    def local_index(self, head, all_ids, nl, n_own, nr, lbase, gbase, rbase):
+        from ._lib import check, ptr, stream_ptr
+        n_loc = nl + n_own + nr
+        times = torch.empty(max(n_loc, 1), dtype=torch.float32, device=self.device)[:n_loc]
+        gidx = torch.empty(max(n_loc, 1), dtype=torch.int64, device=self.device)[:n_loc]
+        if n_loc:
+            ctx = self._ctx()
+            h = np.ascontiguousarray(head, dtype=np.int64)
+            ids = np.ascontiguousarray(all_ids, dtype=np.float32)
+            check(ctx.lib.rb_shard_local_index(ctx.handle, h.ctypes.data, ids.ctypes.data, len(ids), int(nl), int(n_own), int(nr), int(lbase),
+                                               int(gbase), int(rbase), ptr(times), ptr(gidx), stream_ptr()), "rb_shard_local_index")
+        return times, gidx
 
 
 # a block that has just enqueued its spoke stage (~2 ms of GPU time for 512 frames) sits out this many scheduler
@@ -190,6 +426,7 @@ class ShardedDetection:
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
         self.engine = engine or CudaEngine(device)
+        self.engine.attach(self.rank, self.world, group)
         self.device = self.engine.device
         self.base = None
         if engine is None:
@@ -215,72 +452,24 @@ class ShardedDetection:
             self.timings[name] = self.timings.get(name, 0.0) + (now - self._t_last)
         self._t_last = now
 
-    # ---- small collective helpers (tensors live on the engine's device) -----------------------------
-    def _t(self, values, dtype) -> torch.Tensor:
-        return torch.tensor(values, dtype=dtype, device=self.device)
-
-    def _up(self, arr, dtype=None) -> torch.Tensor:
-        """Host array -> device tensor WITHOUT a stream sync: staged in pinned memory (torch's caching host
-        allocator recycles the block only after the copy has run) and copied asynchronously. A plain ``.to(device)``
-        from pageable memory waits for everything queued on the stream - a hidden sync per call."""
-        t = torch.from_numpy(np.ascontiguousarray(arr))
-        if dtype is not None and t.dtype != dtype:
-            t = t.to(dtype)
-        if self.device.type != "cuda":
-            return t
-        pinned = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-        pinned.copy_(t)
-        return pinned.to(self.device, non_blocking=True)
-
     def _wait_stream(self) -> None:
         if self.device.type == "cuda":
             torch.cuda.current_stream(self.device).synchronize()
 
-    def _all_gather_dev(self, mine: torch.Tensor) -> torch.Tensor:
-        """All-gather one fixed-length device vector per rank -> ``[world, len]``, still on the device (ONE
-        collective, no sync); the caller yields before reading it."""
-        if self.world == 1:
-            return mine[None]
-        out = torch.empty((self.world, mine.numel()), dtype=mine.dtype, device=self.device)
-        dist.all_gather_into_tensor(out, mine.contiguous()[None], group=self.group)
-        return out
-
-    def _exchange(self, to_left: Optional[torch.Tensor], to_right: Optional[torch.Tensor],
-                  n_from_left: int, n_from_right: int, dtype, width: int = 1):
-        """Send 2-D ``[width, n]`` tensors to the neighbours and receive theirs (sizes known)."""
-        ops, left, right = [], None, None
-        if self.rank > 0:
-            if to_left is not None and to_left.numel():
-                ops.append(dist.P2POp(dist.isend, to_left.contiguous(), self.rank - 1, group=self.group))
-            if n_from_left:
-                left = torch.empty((width, n_from_left), dtype=dtype, device=self.device)
-                ops.append(dist.P2POp(dist.irecv, left, self.rank - 1, group=self.group))
-        if self.rank < self.world - 1:
-            if to_right is not None and to_right.numel():
-                ops.append(dist.P2POp(dist.isend, to_right.contiguous(), self.rank + 1, group=self.group))
-            if n_from_right:
-                right = torch.empty((width, n_from_right), dtype=dtype, device=self.device)
-                ops.append(dist.P2POp(dist.irecv, right, self.rank + 1, group=self.group))
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
-        return left, right
-
     # ---- the path -------------------------------------------------------------------------------------
     # The path of one block is a GENERATOR that yields right before every host read-back. Driven alone
     # (run_device) it is a plain sequential pass. run_blocks drives several of them round-robin in ONE host
-    # thread over ONE communicator: while a block waits for the GPU, the other blocks' next phases are enqueued,
-    # so kernels, collectives and host work of different blocks overlap. Every rank follows the same
-    # deterministic schedule (the yields and the collectives of a block do not depend on local data), so the
-    # collectives are issued in the same order everywhere - unlike several communicators used concurrently,
-    # which deadlocked (DESIGN.md section 6).
+    # thread: while a block waits for the GPU, the other blocks' next phases are enqueued, so kernels,
+    # collectives and host work of different blocks overlap. Every rank follows the same deterministic schedule
+    # (the yields and the collectives of a block do not depend on local data), so the collectives of every
+    # communicator are issued in the same order everywhere.
     def _gains(self, n_sweeps: int) -> torch.Tensor:
         if self._gain_cache is None or self._gain_cache.numel() != n_sweeps:
-            self._gain_cache = self._t(list(self.cfg.gains) * (n_sweeps // len(self.cfg.gains)), torch.int32)
+            self._gain_cache = self.engine.upload(np.array(list(self.cfg.gains) * (n_sweeps // len(self.cfg.gains)), dtype=np.int32))
         return self._gain_cache
 
     def _slot(self, k: int):
-        """Context of block slot ``k``: its own CUDA stream and library context (scratch, ST-DBSCAN plan)."""
+        """Context of block slot ``k``: its own CUDA stream and library context (scratch, ST-DBSCAN plan, communicator)."""
         import contextlib
         from . import _lib
 
@@ -307,6 +496,7 @@ class ShardedDetection:
         results = [None] * len(blocks)
         active = []                                           # [index, generator, slot, rounds to skip]
         free = list(range(max(1, in_flight)))[::-1]
+        self.engine.prepare_slots(max(1, in_flight), self._slot)
         nxt = 0
         main = torch.cuda.current_stream(self.device) if self.device.type == "cuda" else None
         while active or nxt < len(blocks):
@@ -342,6 +532,10 @@ class ShardedDetection:
     def run_device(self, echo, cos_tab, sin_tab, range_res, frame_ids: Sequence[int], cluster: bool = True) -> ShardResult:
         """``echo[F,G,S,E]`` = this rank's frames (device tensor of the engine); ``frame_ids`` their ids,
         increasing across ranks (rank r's ids are all smaller than rank r+1's)."""
+        from . import _lib
+
+        slot = _lib.get_slot() if self.device.type == "cuda" else 0
+        self.engine.prepare_slots(slot + 1, self._slot)
         gen = self._run_gen(echo, cos_tab, sin_tab, range_res, frame_ids, cluster)
         while True:
             try:
@@ -352,14 +546,13 @@ class ShardedDetection:
     def _run_gen(self, echo, cos_tab, sin_tab, range_res, frame_ids: Sequence[int], cluster: bool = True):
         """One block = three host read-backs (A: point count + every rank's statistics, B: filtered offsets + every
         rank's halo layout, C: every rank's component keys), each preceded by a ``yield``. What the collectives carry
-        is assembled ON THE DEVICE, so nothing between two read-backs waits for the GPU - except the two places where
-        a long GPU phase is waited for BEFORE its collective is issued (see below)."""
+        is assembled ON THE DEVICE by the engine, so nothing between two read-backs waits for the GPU (an engine whose
+        collectives share one stream waits for its long GPU phases before it issues them, see ``wait_before_collective``)."""
         cfg, eng = self.cfg, self.engine
         F, G, S, E = echo.shape
         ids = np.asarray(frame_ids, dtype=np.int64)
         sweeps = echo.reshape(F * G, S, E)
         launch = getattr(eng, "spoke_launch", None)
-        f64 = torch.float64
         self._tick(None)
         while True:
             if launch is not None:
@@ -371,16 +564,14 @@ class ShardedDetection:
                                         cfg.point_stride, G, cap=None)
                 cap, outs, raw_off_d = r.n, (r.x, r.y, r.inten, r.gain), r.frame_off
                 b4_d = eng.bounds(r.x[:r.n], r.y[:r.n]) if r.n > 0 else torch.zeros(4, dtype=torch.float32, device=self.device)
-            # The spoke stage is the long GPU phase of a block (~2 ms for 512 frames). Its collective is issued only
-            # once it has finished: all blocks' collectives share NCCL's one stream, in issue order, so a collective
-            # queued behind unfinished work holds up every other block's collectives behind it.
-            yield SPOKE_SKIP if launch is not None else 0
-            self._wait_stream()
+            if eng.wait_before_collective:
+                # The spoke stage is the long GPU phase of a block. With ONE stream for all blocks' collectives, a
+                # collective queued behind unfinished work holds up every other block's collectives behind it.
+                yield SPOKE_SKIP if launch is not None else 0
+                self._wait_stream()
             # collective 1: [frames built, points, xmin, xmax, ymin, ymax, capacity] of every rank (exact in float64)
-            stats = torch.cat([torch.count_nonzero(torch.diff(raw_off_d))[None].to(f64), raw_off_d[-1:].to(f64), b4_d.to(f64),
-                               self._up(np.array([cap], dtype=np.float64))])
-            g_stats = self._all_gather_dev(stats)
-            yield 0
+            g_stats = eng.all_gather(eng.pack_stats(raw_off_d, b4_d, cap))
+            yield SPOKE_SKIP if (launch is not None and not eng.wait_before_collective) else 0
             allv = g_stats.cpu().numpy()                       # read-back A
             if (allv[:, 1] <= allv[:, 6]).all():
                 break
@@ -400,11 +591,8 @@ class ShardedDetection:
             xe, ye = trk.grid_edges_from_bounds(b4, cfg.land_resolution)
             count, isum = eng.land_accumulate(raw, xe, ye)
             inexact_d = eng.land_flag() if hasattr(eng, "land_flag") else None
-            if self.world > 1:
-                # collective 2: counts and sums in ONE float64 all-reduce (counts < 2^53 stay exact)
-                grids = torch.stack([count.to(f64), isum])
-                dist.all_reduce(grids, op=dist.ReduceOp.SUM, group=self.group)
-                count, isum = grids[0].to(torch.int32), grids[1].contiguous()
+            # collective 2: counts and intensity sums of all ranks (sums of integers: exact in any order)
+            count, isum = eng.all_reduce_grids(count, isum)
             land = eng.land_cells(count, isum, built, cfg.land_persistence, cfg.land_min_intensity)
             if raw.n > 0:
                 pts = eng.land_filter(raw, xe, ye, land)       # enqueued; its point count comes with read-back B
@@ -417,11 +605,7 @@ class ShardedDetection:
         if cluster and self.world > 1 and h_t > F:
             raise RadarB200Error(f"time shard of {F} frames is shorter than the eps_time halo ({h_t} frames)")
         hh = min(h_t, F)
-        g_meta = None
-        if cluster:
-            ids_d, per = self._up(ids), torch.diff(off_d)
-            g_meta = self._all_gather_dev(torch.cat([off_d[F:F + 1], off_d[F - hh:F - hh + 1], ids_d[:hh], per[:hh],
-                                                     ids_d[F - hh:], per[F - hh:]]))
+        g_meta = eng.all_gather(eng.pack_layout(off_d, ids, F, hh)) if cluster else None
         yield 0
         meta = g_meta.cpu().numpy() if cluster else None       # read-back B
         if inexact_d is not None and int(inexact_d.item()):
@@ -458,23 +642,11 @@ class ShardedDetection:
         if int(meta[:, 0].sum()) == 0:
             return torch.empty(0, dtype=torch.int32, device=self.device), 0, (nl, nr)
 
-        xy = torch.stack([pts.x[:n_own], pts.y[:n_own]]) if n_own else torch.zeros((2, 0), dtype=torch.float32, device=self.device)
-        xl, xr = self._exchange(xy[:, :lo_end], xy[:, hi_start:], nl, nr, torch.float32, width=2)
-
-        # ---- local problem: [left halo | owned | right halo], times = frame ids --------------------------
-        XY = torch.cat([t for t in (xl, xy, xr) if t is not None], dim=1)
-        X, Y = XY[0].contiguous(), XY[1].contiguous()
+        # ---- local problem: [left halo | owned | right halo], times = frame ids, global point indices ------
         all_ids = np.concatenate([lids, ids, rids]).astype(np.float32)
         all_cnt = np.concatenate([lcnt, np.diff(off), rcnt]).astype(np.int64)
         head = np.concatenate([[0], np.cumsum(all_cnt)]).astype(np.int64)
-        aux = self._up(np.concatenate([head, all_ids.astype(np.int64)]))                               # one upload
-        loc_off = aux[:len(head)]
-        times = eng.expand_frame_times(loc_off, aux[len(head):].to(torch.float32), n_loc) if n_loc else \
-            torch.zeros(0, dtype=torch.float32, device=self.device)
-        gidx = torch.arange(n_loc, dtype=torch.int64, device=self.device)
-        gidx[:nl] += lbase
-        gidx[nl:nl + n_own] += gbase - nl
-        gidx[nl + n_own:] += rbase - nl - n_own
+        X, Y, times, gidx = eng.local_problem(pts, n_own, lo_end, hi_start, nl, nr, head, all_ids, lbase, gbase, rbase)
         self._tick("halo+prep")
 
         # every point (own or halo) lies inside the global raw bounds and every time is one of the ids: with that
@@ -485,13 +657,8 @@ class ShardedDetection:
         ph = eng.phases(X, Y, times, cfg.eps_space, cfg.eps_time, cfg.min_samples, hint=hint) if n_loc else None
         core = ph.cores() if n_loc else torch.zeros(0, dtype=torch.uint8, device=self.device)
         # ---- exact core flags of the halo points come from their owners ----------------------------------
-        own_core = core[nl:nl + n_own]
-        cl, cr = self._exchange(own_core[None, :lo_end], own_core[None, hi_start:], nl, nr, torch.uint8)
+        eng.exchange_cores(core, nl, n_own, nr, lo_end, hi_start)
         if n_loc:
-            if cl is not None:
-                core[:nl] = cl[0]
-            if cr is not None:
-                core[nl + n_own:] = cr[0]
             ph.set_cores(core)
             key = ph.components(gidx)
         else:
@@ -500,30 +667,18 @@ class ShardedDetection:
         # ---- stitch (on every rank) -----------------------------------------------------------------------------
         # what the stitch needs from me: the local key of every CORE point of my four boundary zones (left halo, own
         # first frames, own last frames, right halo - they pair up with the neighbours' zones by position) and my
-        # distinct component keys (= keys of the points that ARE their component's smallest core). They are compacted
-        # on the device into a fixed-capacity vector [5 counts | keys ...]; collective 4 all-gathers it.
+        # distinct component keys (= keys of the points that ARE their component's smallest core). The engine compacts
+        # them on the device into a fixed-capacity vector [5 counts | keys ...]; collective 4 all-gathers it.
         zones = ((0, nl), (nl, nl + lo_end), (nl + hi_start, nl + n_own), (nl + n_own, n_loc))
-        seg_end = np.cumsum([b - a for a, b in zones] + [n_loc])        # ends of the five segments in the candidate vector
         while True:
             cap_k = self._key_cap
-            if n_loc:
-                is_core, is_root = key >= 0, key == gidx
-                cand = torch.cat([key[a:b] for a, b in zones] + [key])
-                take = torch.cat([is_core[a:b] for a, b in zones] + [is_root])
-                pos = torch.cumsum(take, 0) - 1
-                buf = torch.zeros(5 + cap_k + 1, dtype=torch.int64, device=self.device)
-                # head of the vector: how many keys were taken up to the end of each segment (0 for a leading empty one);
-                # the receiver turns them into the five counts
-                buf[:5] = torch.where(self._up(seg_end > 0), pos[self._up(np.maximum(seg_end - 1, 0))] + 1, 0)
-                buf[torch.where(take & (pos < cap_k), pos + 5, 5 + cap_k)] = cand          # the last slot takes the rest
-                vec = buf[:5 + cap_k]
-            else:
-                vec = torch.zeros(5 + cap_k, dtype=torch.int64, device=self.device)
+            vec = eng.pack_keys(key, gidx, zones, n_loc, cap_k)
             self._tick("plan..components+pack")
-            yield 1                                            # the clustering kernels (~1 ms): same reasoning as for the spoke stage
-            self._wait_stream()
-            g_keys = self._all_gather_dev(vec)
-            yield 0
+            if eng.wait_before_collective:
+                yield 1                                        # the clustering kernels (~1 ms): same reasoning as for the spoke stage
+                self._wait_stream()
+            g_keys = eng.all_gather(vec)
+            yield 0 if eng.wait_before_collective else 1
             got = g_keys.cpu().numpy()                         # read-back C
             sizes = np.diff(got[:, :5], prepend=0, axis=1)
             need = int(sizes.sum(axis=1).max())
@@ -540,9 +695,9 @@ class ShardedDetection:
         # ---- labels of the owned points -------------------------------------------------------------------------
         if n_loc == 0:
             return torch.empty(0, dtype=torch.int32, device=self.device), int(ncl), (nl, nr)
-        core_label = eng.relabel(key, self._up(tk, torch.int64), self._up(ti, torch.int32))
+        core_label = eng.relabel(key, eng.upload(tk, torch.int64), eng.upload(ti, torch.int32))
         labels = ph.assign(core_label)
-        out = labels[nl:nl + n_own].contiguous()
+        out = labels[nl:nl + n_own]
         self._tick("relabel+assign")
         return out, int(ncl), (nl, nr)
 
@@ -561,10 +716,10 @@ class ShardedDetection:
         c, s, r = self.base.spoke_tables(angle_units, scale, F, E)
         d = self.device
         d_echo = t_echo.to(d, non_blocking=True)
-        res = self.run_device(d_echo, torch.from_numpy(c).to(d), torch.from_numpy(s).to(d), torch.from_numpy(r).to(d), frame_ids)
+        up = self.engine.upload
+        res = self.run_device(d_echo, up(c), up(s), up(r), frame_ids)
         out = res.to_host()
         out["n_clusters"] = res.n_clusters
         out["h2d_bytes"] = t_echo.numel() * t_echo.element_size() + 3 * c.nbytes
         out["d2h_bytes"] = out["points"].nbytes + out["gains"].nbytes + out["labels"].nbytes + out["frame_off"].nbytes
         return out
-

@@ -28,7 +28,7 @@ from oracle.c_oracle import st_dbscan_c                                 # noqa: 
 from radar_point_cloud_tracking_b200 import synthetic as syn           # noqa: E402
 from radar_point_cloud_tracking_b200.device import PointBatch          # noqa: E402
 from radar_point_cloud_tracking_b200.pipeline import DetectionConfig   # noqa: E402
-from radar_point_cloud_tracking_b200.sharded import ShardedDetection, stitch_components  # noqa: E402
+from radar_point_cloud_tracking_b200.sharded import ShardedDetection, TorchEngineBase, stitch_components  # noqa: E402
 
 SPEC = dict(seed=21, frames=12, spokes=96, bins=512, clutter_p=0.01, land_blobs=2, buoys=3, boats=3)
 
@@ -99,7 +99,8 @@ class OraclePhases:
         return torch.from_numpy(out)
 
 
-class OracleEngine:
+class OracleEngine(TorchEngineBase):
+    """Numeric stages from the oracle; packing and collectives inherited (plain torch over gloo)."""
     device = torch.device("cpu")
 
     def __init__(self, spec):

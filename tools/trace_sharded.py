@@ -34,7 +34,37 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     sd.run_blocks([blk] * 8, keep=False, in_flight=K)
     torch.cuda.synchronize()
 if rank == 0:
+    import collections
+    import json
+    import re
     Path("gpurun_out").mkdir(exist_ok=True)
-    prof.export_chrome_trace(f"gpurun_out/shard_trace_k{K}.json")
+    path = f"gpurun_out/shard_trace_k{K}.json"
+    prof.export_chrome_trace(path)
+    n_blocks = 8
+    ev = [e for e in json.load(open(path))["traceEvents"] if e.get("ph") == "X" and e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
+    os.remove(path)
+
+    def kname(e):
+        m = re.search(r"(\w+)(<[^(]*>)?\(", e["name"])
+        return m.group(1) if m else e["name"][:40]
+    t0 = min(e["ts"] for e in ev); t1 = max(e["ts"] + e["dur"] for e in ev)
+    iv = sorted((e["ts"], e["ts"] + e["dur"]) for e in ev)
+    busy = 0; cs, ce = iv[0]
+    for a, b in iv[1:]:
+        if a > ce: busy += ce - cs; cs, ce = a, b
+        else: ce = max(ce, b)
+    busy += ce - cs
+    mask = sorted((e["ts"], e["ts"] + e["dur"]) for e in ev if "spoke_mask" in e["name"])
+    gaps, cur = [], t0
+    for a, b in mask:
+        if a > cur: gaps.append((cur, a))
+        cur = max(cur, b)
+    if cur < t1: gaps.append((cur, t1))
+    print(f"rank 0 of {world}: {n_blocks} blocks of {B} frames, {K} in flight: span {(t1 - t0) / 1e3 / n_blocks:.3f} ms/block; GPU busy {100 * busy / (t1 - t0):.1f} %; "
+          f"kernel time {sum(e['dur'] for e in ev) / 1e3 / n_blocks:.3f} ms/block of which mask {sum(b - a for a, b in mask) / 1e3 / n_blocks:.3f}; "
+          f"no mask kernel running {sum(b - a for a, b in gaps) / 1e3 / n_blocks:.3f} ms/block; {len(ev) / n_blocks:.0f} GPU activities per block")
+    agg = collections.defaultdict(float)
+    for e in ev: agg[kname(e)] += e["dur"]
+    for k, v in sorted(agg.items(), key=lambda x: -x[1])[:16]: print(f"  {v / 1e3 / n_blocks:7.3f} ms/block  {k}")
 dist.barrier()
 dist.destroy_process_group()
