@@ -223,6 +223,37 @@ def get_slot() -> int:
     return getattr(_tls, "slot", 0)
 
 
+def bind_to_gpu_numa(device: Optional[int] = None) -> Optional[list]:
+    """Pin the calling process to the CPU cores next to ``device`` (NVML's ideal CPU affinity of the GPU = the cores of its
+    NUMA node). With one process per GPU this keeps every rank's pinned host buffers and its copy threads on the socket
+    the GPU hangs off; without it the 8 ranks' host-to-device streams cross the inter-socket link at random and the
+    end-to-end rate stops scaling (round 1: 0.43 per-GPU efficiency at 8 GPUs). Call before allocating pinned memory.
+    Returns the CPU list, or ``None`` when NVML / the affinity call is unavailable (nothing is changed then)."""
+    import os
+
+    import torch
+
+    try:
+        import pynvml
+
+        if device is None:
+            device = torch.cuda.current_device()
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(visible.split(",")[device]) if visible else device
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1 and 64 * w + b < n_cpu]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
+
+
 def stream_ptr() -> int:
     import torch
 

@@ -311,6 +311,18 @@ class OverlappedPipeline:
             del res
         return out
 
+    def _run_host(self, args, kwargs):
+        pipe, stream = self._worker_state()
+        with torch.cuda.stream(stream):
+            return pipe.run_host(*args, **kwargs)           # upload, device path and read-back, all on this worker's stream
+
+    def map_host(self, blocks) -> List[dict]:
+        """End-to-end blocks ``(args, kwargs)`` of :meth:`DetectionPipeline.run_host` on the worker streams: the
+        host-to-device copy of one block runs under the kernels and the read-back of another (copy engines and SMs work
+        side by side). Host dictionaries in order."""
+        futs = [self._pool.submit(self._run_host, a, k) for a, k in blocks]
+        return [f.result() for f in futs]
+
     def launch_count(self) -> int:
         """Kernels launched so far by all worker contexts (each worker registers its ctx on first use)."""
         return sum(c.launch_count() for c in self._ctxs)

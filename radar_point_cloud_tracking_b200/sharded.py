@@ -238,6 +238,14 @@ class CudaEngine(TorchEngineBase):
                 dist.broadcast(uid, src=0, group=self.group)         # bootstrap only: the id travels over the caller's group
                 raw = bytes(uid.cpu().tolist())
                 _lib.check(ctx.lib.rb_comm_init(ctx.handle, raw, self.rank, self.world), "rb_comm_init")
+                # one round of every kind of operation, in the same order on all ranks: NCCL sets up its connections
+                # (neighbour send/recv channels above all) on first use, and later the slots run unordered
+                t = torch.zeros(16, dtype=torch.uint8, device=self.device)
+                r = torch.zeros(16, dtype=torch.uint8, device=self.device)
+                self.exchange([t[:4]], [t[4:8]], [r[:4]], [r[4:8]])
+                self.all_gather(t)
+                self.all_reduce_grids(torch.zeros(4, dtype=torch.int32, device=self.device), torch.zeros(4, dtype=torch.float64, device=self.device))
+                torch.cuda.current_stream(self.device).synchronize()
             self._comm_slots.add(k)
 
     def _ctx(self):
@@ -452,9 +460,20 @@ class ShardedDetection:
             self.timings[name] = self.timings.get(name, 0.0) + (now - self._t_last)
         self._t_last = now
 
-    def _wait_stream(self) -> None:
-        if self.device.type == "cuda":
-            torch.cuda.current_stream(self.device).synchronize()
+    def _pause(self, skip: int = 0, *tensors):
+        """What a block's generator yields before it needs the host: ``(event, skip, host tensors)``. The device->host
+        copies of ``tensors`` go into pinned memory and the event marks their completion on the block's stream; the
+        scheduler resumes the block once the event has fired (``skip``: rounds to sit out first in ordered mode)."""
+        if self.device.type != "cuda":
+            return None, skip, [t for t in tensors]
+        host = []
+        for t in tensors:
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t, non_blocking=True)
+            host.append(h)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        return ev, skip, host
 
     # ---- the path -------------------------------------------------------------------------------------
     # The path of one block is a GENERATOR that yields right before every host read-back. Driven alone
@@ -488,13 +507,24 @@ class ShardedDetection:
                 _lib.set_slot(prev)
         return ctx()
 
-    def run_blocks(self, blocks, keep: bool = True, in_flight: int = 2):
+    def run_blocks(self, blocks, keep: bool = True, in_flight: int = 2, ordered: Optional[bool] = None, make_gen=None):
         """Run a sequence of blocks ``(echo, cos_tab, sin_tab, range_res, frame_ids)`` of this rank with up to
         ``in_flight`` of them interleaved (see above). Same results as :meth:`run_device` per block. Returns the
-        results in order (``keep=False``: only the last one; earlier ones are released for buffer reuse)."""
+        results in order (``keep=False``: only the last one; earlier ones are released for buffer reuse).
+
+        ``ordered`` (default: what the engine needs): True = the blocks are stepped round-robin and the host WAITS for
+        each block's pending read-back in turn - every rank issues all collectives in one global order, which engines
+        whose collectives share a communicator need. False = a block is stepped as soon as ITS read-back has arrived
+        (event query), whatever the others do: no head-of-line blocking of the one host thread. The order of a
+        communicator's collectives is still the block's program order; only the interleaving BETWEEN the slots'
+        communicators then differs from rank to rank, which is safe because their kernels can run side by side."""
+        import os
+
         blocks = list(blocks)
         results = [None] * len(blocks)
-        active = []                                           # [index, generator, slot, rounds to skip]
+        if ordered is None:
+            ordered = bool(self.engine.wait_before_collective) or os.environ.get("RB_SHARD_ORDERED", "0") == "1"
+        active = []                                           # [index, generator, slot, rounds to skip, pending event]
         free = list(range(max(1, in_flight)))[::-1]
         self.engine.prepare_slots(max(1, in_flight), self._slot)
         nxt = 0
@@ -505,28 +535,39 @@ class ShardedDetection:
                 if main is not None:
                     with self._slot(k):
                         torch.cuda.current_stream(self.device).wait_stream(main)
-                active.append([nxt, self._run_gen(*blocks[nxt]), k, 0])
+                active.append([nxt, (make_gen or self._run_gen)(*blocks[nxt]), k, 0, None])
                 nxt += 1
-            for entry in list(active):                         # one step of every active block, in order
-                i, gen, k = entry[:3]
-                if entry[3] > 0 and len(active) > 1:           # it asked to be left alone for a few rounds (its GPU
-                    entry[3] -= 1                              # phase is long): the others' steps fill the time
-                    continue
+            progressed = False
+            for entry in list(active):                         # one step of every active block that can take one
+                i, gen, k, _, ev = entry
+                if ordered:
+                    if entry[3] > 0 and len(active) > 1:       # it asked to be left alone for a few rounds (its GPU
+                        entry[3] -= 1                          # phase is long): the others' steps fill the time
+                        continue
+                    if ev is not None:
+                        ev.synchronize()
+                elif ev is not None and not ev.query():
+                    continue                                   # its read-back has not arrived yet: somebody else's turn
+                progressed = True
                 with self._slot(k):
                     try:
-                        entry[3] = next(gen) or 0
+                        entry[4], entry[3], _ = next(gen)
                         continue
                     except StopIteration as fin:
                         res = fin.value
                     if main is not None:
-                        ev = torch.cuda.Event()
-                        ev.record(torch.cuda.current_stream(self.device))
-                        main.wait_event(ev)
+                        done = torch.cuda.Event()
+                        done.record(torch.cuda.current_stream(self.device))
+                        main.wait_event(done)
                 active.remove(entry)
                 free.append(k)
                 if keep or i == len(blocks) - 1:
                     results[i] = res
                 del res
+            if not ordered and not progressed and active:      # nothing was ready: wait for the oldest block's read-back
+                pend = [e[4] for e in active if e[4] is not None]
+                if pend:
+                    pend[0].synchronize()
         return [r for r in results if r is not None]
 
     def run_device(self, echo, cos_tab, sin_tab, range_res, frame_ids: Sequence[int], cluster: bool = True) -> ShardResult:
@@ -539,7 +580,9 @@ class ShardedDetection:
         gen = self._run_gen(echo, cos_tab, sin_tab, range_res, frame_ids, cluster)
         while True:
             try:
-                next(gen)
+                ev, _, _ = next(gen)
+                if ev is not None:
+                    ev.synchronize()
             except StopIteration as fin:
                 return fin.value
 
@@ -567,17 +610,17 @@ class ShardedDetection:
             if eng.wait_before_collective:
                 # The spoke stage is the long GPU phase of a block. With ONE stream for all blocks' collectives, a
                 # collective queued behind unfinished work holds up every other block's collectives behind it.
-                yield SPOKE_SKIP if launch is not None else 0
-                self._wait_stream()
+                yield self._pause(SPOKE_SKIP if launch is not None else 0)
             # collective 1: [frames built, points, xmin, xmax, ymin, ymax, capacity] of every rank (exact in float64)
             g_stats = eng.all_gather(eng.pack_stats(raw_off_d, b4_d, cap))
-            yield SPOKE_SKIP if (launch is not None and not eng.wait_before_collective) else 0
-            allv = g_stats.cpu().numpy()                       # read-back A
+            pause = self._pause(SPOKE_SKIP if (launch is not None and not eng.wait_before_collective) else 0, g_stats, raw_off_d)
+            yield pause
+            allv, raw_off = (t.numpy() for t in pause[2])      # read-back A
             if (allv[:, 1] <= allv[:, 6]).all():
                 break
             # some rank's capacity guess was too small (its points were cut): everybody repeats - all see the same numbers
             self._cap_hint = int(allv[self.rank, 1] * 1.25) + 1024
-        raw_off = raw_off_d.cpu().numpy().astype(np.int64)
+        raw_off = raw_off.astype(np.int64)
         raw = PointBatch(*outs, raw_off_d, int(raw_off[-1]))
         self._cap_hint = max(self._cap_hint, int(raw.n * 1.25) + 1024)
         self._tick("spoke+stats")
@@ -606,14 +649,16 @@ class ShardedDetection:
             raise RadarB200Error(f"time shard of {F} frames is shorter than the eps_time halo ({h_t} frames)")
         hh = min(h_t, F)
         g_meta = eng.all_gather(eng.pack_layout(off_d, ids, F, hh)) if cluster else None
-        yield 0
-        meta = g_meta.cpu().numpy() if cluster else None       # read-back B
-        if inexact_d is not None and int(inexact_d.item()):
+        pause = self._pause(0, off_d, *([g_meta] if cluster else []), *([inexact_d] if inexact_d is not None else []))
+        yield pause
+        back = [t.numpy() for t in pause[2]]                   # read-back B
+        off = back[0].astype(np.int64)
+        meta = back[1] if cluster else None
+        if inexact_d is not None and int(back[-1][0]):
             # the per-cell float64 sums of non-integer intensities depend on the order of addition; across ranks the
             # reference's order (all points of all frames, one after the other) cannot be reproduced by a sum of partial sums
             raise RadarB200Error("time-sharded land filter: intensities must be integer valued (radar echoes are 0..255); "
                                  "use the single-GPU path for other data")
-        off = off_d.cpu().numpy().astype(np.int64)
         pts.n = int(off[-1])
         self._tick("land+layout")
         labels = torch.empty(0, dtype=torch.int32, device=self.device)
@@ -675,11 +720,11 @@ class ShardedDetection:
             vec = eng.pack_keys(key, gidx, zones, n_loc, cap_k)
             self._tick("plan..components+pack")
             if eng.wait_before_collective:
-                yield 1                                        # the clustering kernels (~1 ms): same reasoning as for the spoke stage
-                self._wait_stream()
+                yield self._pause(1)                           # the clustering kernels (~1 ms): same reasoning as for the spoke stage
             g_keys = eng.all_gather(vec)
-            yield 0 if eng.wait_before_collective else 1
-            got = g_keys.cpu().numpy()                         # read-back C
+            pause = self._pause(0 if eng.wait_before_collective else 1, g_keys)
+            yield pause
+            got = pause[2][0].numpy()                          # read-back C
             sizes = np.diff(got[:, :5], prepend=0, axis=1)
             need = int(sizes.sum(axis=1).max())
             if need <= cap_k:
@@ -701,7 +746,34 @@ class ShardedDetection:
         self._tick("relabel+assign")
         return out, int(ncl), (nl, nr)
 
-    # ---- host entry (mirrors DetectionPipeline.run_host for this rank's block) -------------------------------
+    # ---- host entries -----------------------------------------------------------------------------------------------
+    def _run_host_gen(self, t_echo, angle_units, scale, frame_ids):
+        """End-to-end path of one block as a generator: upload on the block's stream, the device path, and the
+        read-back of this rank's result into pinned memory (awaited like every other read-back of the block)."""
+        F, G, S, E = t_echo.shape
+        c, s, r = self.base.spoke_tables(angle_units, scale, F, E)
+        up = self.engine.upload
+        d_echo = t_echo.to(self.device, non_blocking=True)
+        res = yield from self._run_gen(d_echo, up(c), up(s), up(r), frame_ids)
+        n, p = res.points.n, res.points
+        pause = self._pause(0, p.x[:n], p.y[:n], p.inten[:n], p.gain[:n], p.frame_off, res.labels[:n])
+        yield pause
+        x, y, inten, gain, off, labels = (t.numpy() for t in pause[2])
+        out = dict(points=np.stack([x, y, inten], axis=1), gains=gain, frame_off=off, labels=labels, frame_ids=res.frame_ids,
+                   n_clusters=res.n_clusters)
+        out["h2d_bytes"] = t_echo.numel() * t_echo.element_size() + 3 * c.nbytes
+        out["d2h_bytes"] = out["points"].nbytes + gain.nbytes + labels.nbytes + off.nbytes
+        return out
+
+    def run_host_blocks(self, host_blocks, in_flight: int = 2, keep: bool = True):
+        """``host_blocks``: ``(pinned echo tensor [F,G,S,E], angle_units, scale, frame_ids)`` per block. The blocks run
+        interleaved like :meth:`run_blocks`, so the upload of one block overlaps the kernels and the read-back of
+        another. Returns the host dictionaries of :meth:`run_host`."""
+        if self.base is None:
+            raise RadarB200Error("run_host_blocks needs the CUDA engine")
+        return self.run_blocks(host_blocks, keep=keep, in_flight=in_flight, make_gen=self._run_host_gen)
+
+
     def run_host(self, echo, angle_units, scale, frame_ids: Sequence[int], pinned: Optional[torch.Tensor] = None) -> dict:
         """Host buffers in, host buffers out for this rank's frames: uploads ``echo[F,G,S,E]`` (numpy or a
         pinned torch tensor), runs the sharded device path and reads this rank's result back."""

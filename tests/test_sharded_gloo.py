@@ -315,7 +315,7 @@ def test_run_blocks_schedule_is_deterministic_round_robin_with_skips():
         def gen(*_):
             for step, y in enumerate(yields):
                 trace.append((name, step))
-                yield y
+                yield None, y, []                                  # (event, rounds to sit out, host tensors)
             trace.append((name, "done"))
             return name
         return gen
@@ -323,12 +323,18 @@ def test_run_blocks_schedule_is_deterministic_round_robin_with_skips():
     scripts = {"A": [3, 0, 0], "B": [0, 0], "C": [0]}
     order = iter(scripts)
     sd._run_gen = lambda *a: scripted(n := next(order), scripts[n])()
-    out = sd.run_blocks([("A",), ("B",), ("C",)], in_flight=2)
+    out = sd.run_blocks([("A",), ("B",), ("C",)], in_flight=2, ordered=True)
     assert out == ["A", "B", "C"]                                   # results in block order
     # A steps once and sits out 3 rounds while B runs to its end; C takes B's slot; then A and C alternate
     assert trace == [("A", 0), ("B", 0), ("B", 1), ("B", "done"), ("C", 0), ("A", 1), ("C", "done"), ("A", 2), ("A", "done")]
     # a block alone never waits for its own skip count
     trace.clear()
     order = iter(["A"])
-    assert sd.run_blocks([("A",)], in_flight=2) == ["A"]
+    assert sd.run_blocks([("A",)], in_flight=2, ordered=True) == ["A"]
     assert trace == [("A", 0), ("A", 1), ("A", 2), ("A", "done")]
+    # unordered mode (the CUDA engine's default): a block is stepped whenever its read-back has arrived - with no events
+    # pending that is plain round-robin, skip hints ignored; results still come back in block order
+    trace.clear()
+    order = iter(scripts)
+    assert sd.run_blocks([("A",), ("B",), ("C",)], in_flight=2, ordered=False) == ["A", "B", "C"]
+    assert trace == [("A", 0), ("B", 0), ("A", 1), ("B", 1), ("A", 2), ("B", "done"), ("A", "done"), ("C", 0), ("C", "done")]
