@@ -889,12 +889,15 @@ __global__ void __launch_bounds__(DB_THREADS) db_gather_labels_kernel(int n, con
     }
 }
 
-// One WARP per listed point (core == 0). Step 1, lanes over the time bins of the own spatial cell: cores there are
-// neighbours by construction, their bucket labels count without a test. Step 2, lanes over the ROWS of the window (a row =
-// the buckets with the same dt, dz, dy): only buckets whose label can lower the lane's best id are searched for ONE core
-// point within eps. The warp's answer is the minimum over the lanes.
-// (Round 1 ran this search with one thread per point over ALL points: the ~1 % that are border candidates sat alone in
-// their warps - 1.2-1.9 active lanes per warp, 0.30 ms per 1024-frame block.)
+// One THREAD per listed point (core == 0: not core, not alone), the list being dense. Step 1: cores of the own spatial
+// cell inside the time window are neighbours by construction, their bucket labels count without a test. Step 2: the
+// other buckets of the window, row by row; only a bucket whose label can lower the best id so far is searched for ONE
+// core point within eps, and id 0 ends the search.
+// (Round 1 ran the same search with one thread per point over ALL points: the ~10 % that are border candidates sat
+// nearly alone in their warps, 3.3 active lanes per warp. Round 2 first gave every listed point a WARP with the lanes
+// over the window's rows: no faster (0.31 ms per 1024-frame block) - 25 lanes search at once where the serial walk stops
+// at the first bucket of cluster 0, 4.9 M instead of 1.2 M tests. The dense list with the serial early-exit walk keeps
+// both: full warps and few tests.)
 template <int DIM, bool WF>
 __global__ void __launch_bounds__(DB_THREADS) dbt_border_kernel(Sorted s, DbGrid g, double eps2, const uint8_t* __restrict__ core,
                                                                const int* __restrict__ sidx, const int* __restrict__ open_list,
@@ -902,21 +905,18 @@ __global__ void __launch_bounds__(DB_THREADS) dbt_border_kernel(Sorted s, DbGrid
                                                                const int* __restrict__ core_start, const int* __restrict__ b_label,
                                                                const int* __restrict__ b_parent, const long long* __restrict__ b_minkey,
                                                                int32_t* __restrict__ labels, unsigned long long* __restrict__ ctr) {
-    constexpr unsigned FULL = 0xffffffffu;
-    const unsigned lane = rb_lane();
     const int total = *n_open;
-    const int n_warps = (gridDim.x * blockDim.x) >> 5;
     const int per_t = g.n[0] * g.n[1] * g.n[2];
     unsigned long long tests = 0;
-    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += n_warps) {
-        const int p = open_list[w];
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
+        const int p = open_list[k];
         const int cell = s.cell[p];
         const CellPos c = decode_cell(g, cell);
-        const Window win = window_of<DIM>(g, c);
+        const Window w = window_of<DIM>(g, c);
         const int sp = cell - c.tb * per_t;
         const long long me = sidx[p];
         int best = INT_MAX;
-        for (int tt = win.t0 + (int)lane; tt <= win.t1; tt += 32) {
+        for (int tt = w.t0; tt <= w.t1; ++tt) {
             const int b = tt * per_t + sp;
             if (b_ncore[b] <= 0) continue;
             if (WF) {
@@ -929,32 +929,29 @@ __global__ void __launch_bounds__(DB_THREADS) dbt_border_kernel(Sorted s, DbGrid
             }
             best = min(best, b_label[b]);
         }
-        best = __reduce_min_sync(FULL, best);
         if (best != 0) {
             const Pt<DIM> a = load_pt<DIM>(s, p);
-            const int ny = win.y1 - win.y0 + 1, nz = win.z1 - win.z0 + 1, nt = win.t1 - win.t0 + 1;
-            const int rows = ny * nz * nt;
-            for (int r = (int)lane; r < rows; r += 32) {
-                const int yy = win.y0 + r % ny, zz = win.z0 + (r / ny) % nz, tt = win.t0 + r / (ny * nz);
-                const int row = ((tt * g.n[2] + zz) * g.n[1] + yy) * g.n[0];
-                if (core_start[row + win.x1 + 1] == core_start[row + win.x0]) continue;          // no core in this row
-                for (int xx = win.x0; xx <= win.x1 && best != 0; ++xx) {
-                    const int b = row + xx;
-                    if (b_ncore[b] == 0 || (xx == c.cx && yy == c.cy && zz == c.cz)) continue;
-                    const int lb = b_label[b];
-                    if (lb >= best) continue;                 // only a smaller id can change the answer
-                    const long long start = WF ? b_minkey[b_parent[b]] : 0;
-                    const bool any_core = !WF || start < me;   // WF: else only the start point itself counts
-                    for (int q = s.cell_start[b]; q < s.cell_start[b + 1]; ++q) {
-                        if (core[q] != 1 || (!any_core && (long long)sidx[q] != start)) continue;
-                        ++tests;
-                        if (near_enough<DIM>(a, load_pt<DIM>(s, q), eps2)) { best = lb; break; }
+            for (int tt = w.t0; tt <= w.t1 && best != 0; ++tt)
+                for (int zz = w.z0; zz <= w.z1 && best != 0; ++zz)
+                    for (int yy = w.y0; yy <= w.y1 && best != 0; ++yy) {
+                        const int row = ((tt * g.n[2] + zz) * g.n[1] + yy) * g.n[0];
+                        if (core_start[row + w.x1 + 1] == core_start[row + w.x0]) continue;      // no core in this row
+                        for (int xx = w.x0; xx <= w.x1; ++xx) {
+                            const int b = row + xx;
+                            if (b_ncore[b] == 0 || (xx == c.cx && yy == c.cy && zz == c.cz)) continue;
+                            const int lb = b_label[b];
+                            if (lb >= best) continue;                 // only a smaller id can change the answer
+                            const long long start = WF ? b_minkey[b_parent[b]] : 0;
+                            const bool any_core = !WF || start < me;   // WF: else only the start point itself counts
+                            for (int q = s.cell_start[b]; q < s.cell_start[b + 1]; ++q) {
+                                if (core[q] != 1 || (!any_core && (long long)sidx[q] != start)) continue;
+                                ++tests;
+                                if (near_enough<DIM>(a, load_pt<DIM>(s, q), eps2)) { best = lb; break; }
+                            }
+                        }
                     }
-                }
-            }
-            best = __reduce_min_sync(FULL, best);
         }
-        if (lane == 0 && best != INT_MAX) labels[me] = best;
+        if (best != INT_MAX) labels[me] = best;
     }
     add_counter(ctr, tests);
 }
