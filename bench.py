@@ -96,7 +96,7 @@ def workload_config(args) -> dict:
 def load_traffic(frames_per_launch: int):
     """DRAM bytes (read + write) of the mask kernel per launch, from the committed ncu --set full capture,
     scaled from the captured launch size to this run's (the kernel's traffic is proportional to its input)."""
-    cands = [REPO / "profiles" / n for n in ("r01_ncu_spoke_final_traffic.json", "r01_ncu_spoke_v4_traffic.json")]
+    cands = [REPO / "profiles" / n for n in ("r02_ncu_spoke_traffic.json", "r01_ncu_spoke_final_traffic.json")]
     p = next((c for c in cands if c.exists()), None)
     if p is None:
         return None, None
@@ -506,11 +506,29 @@ def run_ours(args):
         host_echo = torch.empty(echo[:Be].shape, dtype=torch.float32, pin_memory=True)
         host_echo.copy_(echo[:Be])
         torch.cuda.synchronize()
+        # what the platform gives: the same pinned buffer copied to the device and nothing else, all ranks at once
+        d_tmp = torch.empty_like(echo[:Be])
+        d_tmp.copy_(host_echo, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            d_tmp.copy_(host_echo, non_blocking=True)
+        torch.cuda.synchronize()
+        copy_s = (time.perf_counter() - t0) / 3
+        if world > 1:
+            t = torch.tensor([copy_s], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            copy_s = float(t.item())
+        del d_tmp
         ms_e, out_f = e2e_run(host_echo)
         e2e = {"value": Be * world * e_steps / (ms_e * 1e-3), "unit": UNIT, "frames_per_step_per_gpu": Be, "steps": e_steps,
                "h2d_bytes_per_step": int(out_f["h2d_bytes"]), "d2h_bytes_per_step": int(out_f["d2h_bytes"]),
                "ms_per_step": ms_e / e_steps, "host_buffers": "float32 echoes (the reference's in-memory type), pinned",
-               "blocks_in_flight": 2, "timing": "wall clock between device synchronisations, max over ranks"}
+               "blocks_in_flight": 2, "timing": "wall clock between device synchronisations, max over ranks",
+               "h2d_copy_only": {"ms_per_step": copy_s * 1e3, "gb_per_s_per_gpu": host_echo.numel() * 4 / copy_s / 1e9,
+                                 "frames_per_s": Be * world / copy_s,
+                                 "note": "the pinned echo buffer copied to the device and nothing else, all ranks at once: the "
+                                         "ceiling the platform's host-to-device path sets for this end-to-end number"}}
         del host_echo
         # the same with the radar's native uint8 echoes in the pinned host buffer (identical results, a quarter of the
         # bytes over PCIe) - the transport the drop-in uses when it parses sweeps itself; reported next to the float32

@@ -107,7 +107,7 @@ extern "C" int rb_set_option(rb_ctx* ctx, const char* name, int64_t value) {
         return RB_OK;
     }
     if (!strcmp(name, "spoke_ring")) {
-        RB_REQUIRE(value >= 0 && value <= 8, "spoke_ring: 0 = 64 KiB x 3, 1 = 32 KiB x 4, 2 = 32 KiB x 3, 3 = 64 KiB x 2, 4 = 16 KiB x 4, 5 = 48 KiB x 3, 6 = 48 KiB x 2, 7 = 80 KiB x 2, 8 = 16 KiB x 6");
+        RB_REQUIRE(value >= 0 && value <= 3, "spoke_ring: 0 = 64 KiB x 3, 1 = 32 KiB x 4, 2 = 32 KiB x 3 (default), 3 = 48 KiB x 2");
         ctx->opt_spoke_ring = (int)value;
         return RB_OK;
     }

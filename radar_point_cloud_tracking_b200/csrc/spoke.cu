@@ -164,9 +164,12 @@ __device__ __forceinline__ TileRef<T> tile_ref(const T* echo, const SpokeGeom& g
 // that the producer flushes to global memory when it recycles the slot. Stages are handed out by one
 // atomic ticket per CTA and stage (a ticket per WARP and tile serialises on the atomic unit: measured
 // 4.8 instead of 7.0 TB/s, tools/mask_bench.cu).
-// The ring is a template parameter pair (stage bytes x stages). 64 KiB x 3 (197 KB) is the default: the most bytes in
-// flight. The smaller rings (rb_set_option "spoke_ring") leave shared memory / L1 to other kernels, so that the
-// latency-bound clustering kernels of the previous block can be RESIDENT next to this HBM-bound one ("carveout" option).
+// The ring is a template parameter pair (stage bytes x stages), chosen with rb_set_option "spoke_ring":
+//   2 (default) 32 KiB x 3 =  98 KB: 6.6 TB/s alone, and small enough for the CTAs of OTHER kernels to be resident on the SM
+//                                    beside it - the latency-bound clustering kernels of the block before run under this
+//                                    HBM-bound one (measured: rings up to ~100 KB co-reside, 131 KB and more do not)
+//   0           64 KiB x 3 = 197 KB: the most bytes in flight, 7.0 TB/s alone, owns the SM (round 1's kernel)
+//   1           32 KiB x 4 = 131 KB, 3: 48 KiB x 2 = 98 KB: the sweep's other useful points (profiles/r02_ring_sweep.txt)
 template <typename T> constexpr int mt_threads() { return Elem<T>::WARPS * 32 + 32; }    // consumer warps + the producer warp
 
 template <int TILES>
@@ -693,8 +696,7 @@ template <typename T, int STAGE_BYTES, int STAGES>
 int launch_mask_tma(rb_ctx* ctx, const T* echo, const SpokeGeom& g, const ThrArg& thr, uint32_t* mask, uint32_t* tile_count,
                     unsigned* ticket, cudaStream_t stream) {
     constexpr int smem = mt_smem_bytes<T, STAGE_BYTES, STAGES>();
-    constexpr int ring_id = STAGE_BYTES == 64 * 1024 ? (STAGES == 3 ? 0 : 3) : STAGE_BYTES == 32 * 1024 ? (STAGES == 4 ? 1 : 2) :
-                            STAGE_BYTES == 48 * 1024 ? (STAGES == 3 ? 5 : 6) : STAGE_BYTES == 80 * 1024 ? 7 : (STAGES == 4 ? 4 : 8);
+    constexpr int ring_id = STAGE_BYTES == 64 * 1024 ? 0 : STAGE_BYTES == 48 * 1024 ? 3 : (STAGES == 4 ? 1 : 2);
     const unsigned bit = 1u << (ring_id * 2 + (sizeof(T) == 1 ? 1 : 0));
     auto kernel = spoke_mask_tma_kernel<T, STAGE_BYTES, STAGES>;
     if (!(ctx->attr_spoke_mask & bit)) {
@@ -800,15 +802,10 @@ int spoke_to_points_impl(rb_ctx* ctx, const T* echo, const float* cos_tab, const
     if (vec && variant != 1) {
         const ThrArg thr = make_thr(threshold);
         switch (ctx->opt_spoke_ring) {
+            case 0: RB_TRY((launch_mask_tma<T, 64 * 1024, 3>(ctx, echo, g, thr, mask, tile_count, ticket, stream))); break;
             case 1: RB_TRY((launch_mask_tma<T, 32 * 1024, 4>(ctx, echo, g, thr, mask, tile_count, ticket, stream))); break;
-            case 2: RB_TRY((launch_mask_tma<T, 32 * 1024, 3>(ctx, echo, g, thr, mask, tile_count, ticket, stream))); break;
-            case 3: RB_TRY((launch_mask_tma<T, 64 * 1024, 2>(ctx, echo, g, thr, mask, tile_count, ticket, stream))); break;
-            case 4: RB_TRY((launch_mask_tma<T, 16 * 1024, 4>(ctx, echo, g, thr, mask, tile_count, ticket, stream))); break;
-            case 5: RB_TRY((launch_mask_tma<T, 48 * 1024, 3>(ctx, echo, g, thr, mask, tile_count, ticket, stream))); break;
-            case 6: RB_TRY((launch_mask_tma<T, 48 * 1024, 2>(ctx, echo, g, thr, mask, tile_count, ticket, stream))); break;
-            case 7: RB_TRY((launch_mask_tma<T, 80 * 1024, 2>(ctx, echo, g, thr, mask, tile_count, ticket, stream))); break;
-            case 8: RB_TRY((launch_mask_tma<T, 16 * 1024, 6>(ctx, echo, g, thr, mask, tile_count, ticket, stream))); break;
-            default: RB_TRY((launch_mask_tma<T, 64 * 1024, 3>(ctx, echo, g, thr, mask, tile_count, ticket, stream))); break;
+            case 3: RB_TRY((launch_mask_tma<T, 48 * 1024, 2>(ctx, echo, g, thr, mask, tile_count, ticket, stream))); break;
+            default: RB_TRY((launch_mask_tma<T, 32 * 1024, 3>(ctx, echo, g, thr, mask, tile_count, ticket, stream))); break;
         }
         ctx->spoke_last_variant = 2;
     } else {
