@@ -60,7 +60,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--shard-in-flight", type=int, default=4, help="N>1: blocks interleaved per rank (one host thread, one communicator)")
+    ap.add_argument("--shard-in-flight", type=int, default=6, help="N>1: blocks interleaved per rank (one host thread, one communicator)")
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS), help="BASELINE.json configuration (default: config 3, the "
                     "one the metric is quoted on)")
     ap.add_argument("--frames-per-step", type=int, default=0, help="frames per rank and step (device-resident `value`); 0 = the workload's default")

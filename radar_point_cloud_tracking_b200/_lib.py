@@ -184,27 +184,35 @@ class Context:
             pass
 
 
-_contexts: Dict[int, Context] = {}
+# A ctx is not thread safe and holds per-call state (scratch, the ST-DBSCAN plan, a communicator): one per device, host
+# thread and block slot (several blocks interleaved by one thread, sharded.ShardedDetection.run_blocks). The contexts of
+# a thread live in ITS thread-local storage: when the thread ends they are released (rb_destroy frees scratch, pinned
+# staging and the communicator) instead of piling up under recycled thread ids; `_all_contexts` only observes them.
+import weakref
+
+_tls = threading.local()
+_all_contexts: "weakref.WeakSet[Context]" = weakref.WeakSet()
 
 
 def context(device: Optional[int] = None) -> Context:
-    """Context of ``device`` (default: torch's current CUDA device). Raises without a GPU."""
+    """Context of ``device`` (default: torch's current CUDA device) for the calling thread and block slot.
+    Raises without a GPU."""
     import torch
 
     if not torch.cuda.is_available():
         raise RadarB200Error("no CUDA device: the radar-b200 detection path is GPU only (no CPU fallback)")
     if device is None:
         device = torch.cuda.current_device()
-    # a ctx is not thread safe and holds per-call state (scratch, the ST-DBSCAN plan): one per device, host thread and
-    # block slot (several blocks interleaved by one thread, sharded.ShardedDetection.run_blocks)
-    key = (device, threading.get_ident(), getattr(_tls, "slot", 0))
-    ctx = _contexts.get(key)
+    mine = getattr(_tls, "contexts", None)
+    if mine is None:
+        mine = _tls.contexts = {}
+    key = (device, getattr(_tls, "slot", 0))
+    ctx = mine.get(key)
     if ctx is None:
-        ctx = _contexts[key] = Context(device)
+        ctx = mine[key] = Context(device)
+        with _lock:
+            _all_contexts.add(ctx)
     return ctx
-
-
-_tls = threading.local()
 
 
 def set_slot(slot: int) -> int:
@@ -215,8 +223,10 @@ def set_slot(slot: int) -> int:
 
 
 def launch_count_all() -> int:
-    """Kernel launches of every context of this process (all devices, threads and block slots)."""
-    return sum(c.launch_count() for c in list(_contexts.values()))
+    """Kernel launches of every live context of this process (all devices, threads and block slots)."""
+    with _lock:
+        live = list(_all_contexts)
+    return sum(c.launch_count() for c in live if c.handle)
 
 
 def get_slot() -> int:

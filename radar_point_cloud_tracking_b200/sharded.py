@@ -564,10 +564,14 @@ class ShardedDetection:
                 if keep or i == len(blocks) - 1:
                     results[i] = res
                 del res
-            if not ordered and not progressed and active:      # nothing was ready: wait for the oldest block's read-back
+            if not ordered and not progressed and active:      # nothing was ready: poll until some block's read-back arrives
                 pend = [e[4] for e in active if e[4] is not None]
-                if pend:
-                    pend[0].synchronize()
+                spins = 0
+                while pend and not any(ev.query() for ev in pend):
+                    spins += 1
+                    if spins > 20000:                          # (a long GPU phase: stop burning the core, sleep on the oldest)
+                        pend[0].synchronize()
+                        break
         return [r for r in results if r is not None]
 
     def run_device(self, echo, cos_tab, sin_tab, range_res, frame_ids: Sequence[int], cluster: bool = True) -> ShardResult:
