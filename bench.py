@@ -39,18 +39,18 @@ UNIT = "frames/s"
 # density: SURVEY 8(d) "a documented subset ... and/or an angular sector").
 WORKLOADS = {
     "config3": dict(desc="config3-shard: gain-fused 40/50/75, 2048x1024 sweeps, land filter, ST-DBSCAN eps 8/2/15 (thr 10, stride 4)",
-                    gains=(40, 50, 75), cfg={}, frames=1024, e2e_frames=128, cpu_frames=64, cpu_sector=1),
+                    gains=(40, 50, 75), cfg={}, frames=1024, e2e_frames=128, cpu_frames=64, cpu_sector=1, streams=4),
     "config2": dict(desc="config2: single-gain (50) stacked cloud of 500 sweeps, 3-D ST-DBSCAN on (x, y, intensity) with time = frame "
                          "index, eps 5/1/10, no land filter (3_stdbscan_point_clouds.py:177-182), thr 10 / stride 4",
                     gains=(50,), cfg=dict(land_filter=False, eps_space=5.0, eps_time=1.0, min_samples=10, cluster_3d=True),
-                    frames=500, e2e_frames=250, cpu_frames=32, cpu_sector=1),
+                    frames=500, e2e_frames=250, cpu_frames=32, cpu_sector=1, streams=3),
     "config4": dict(desc="config4: dense clutter stress, gain-fused 40/50/75, thr 2 / stride 2 / eps 12 (~2.2 M points per frame), "
                          "land filter, ST-DBSCAN eps 12/2/15",
                     gains=(40, 50, 75), cfg=dict(intensity_threshold=2.0, point_stride=2, eps_space=12.0),
-                    frames=64, e2e_frames=32, cpu_frames=11, cpu_sector=1024),
+                    frames=64, e2e_frames=32, cpu_frames=11, cpu_sector=1024, streams=2),
     "config5": dict(desc="config5: long horizon, gain-fused 40/50/75, land filter, ST-DBSCAN eps 8/5/15 (eps_time 5: an 11-frame window, "
                          "5-frame halo between time shards), thr 10 / stride 4",
-                    gains=(40, 50, 75), cfg=dict(eps_time=5.0), frames=1024, e2e_frames=128, cpu_frames=64, cpu_sector=1),
+                    gains=(40, 50, 75), cfg=dict(eps_time=5.0), frames=1024, e2e_frames=128, cpu_frames=64, cpu_sector=1, streams=4),
 }
 
 
@@ -72,8 +72,8 @@ def parse_args():
     ap.add_argument("--clutter-p", type=float, default=0.003)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--streams", type=int, default=4, help="N=1: blocks in flight (host threads x CUDA streams x library contexts) "
-                    "for `value`; the time-sharded path (N>1) always has one block in flight per rank")
+    ap.add_argument("--streams", type=int, default=0, help="N=1: blocks in flight (host threads x CUDA streams x library contexts) "
+                    "for `value`; 0 = the workload's default")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames per CPU worker in the reference/cpu_baseline sample; 0 = the workload's default")
     ap.add_argument("--shard-profile", action="store_true", help="N>1: print per-stage wall-clock of the sharded driver to stderr")
     args = ap.parse_args()
@@ -81,6 +81,7 @@ def parse_args():
     args.frames_per_step = args.frames_per_step or w["frames"]
     args.e2e_frames = args.e2e_frames or w["e2e_frames"]
     args.cpu_frames = args.cpu_frames or w["cpu_frames"]
+    args.streams = args.streams or w["streams"]          # blocks in flight: 4 where the HBM-bound mask kernel dominates, 2 for the dense stress
     return args
 
 

@@ -139,10 +139,13 @@ __device__ __forceinline__ int cell_index(const DbGrid& g, float x, float y, flo
 }
 
 // cell id per point + slot of the point inside its cell (the atomic's return value)
+// (The slot reservation is pooled per warp: in dense data the 32 consecutive points of a warp fall into a handful of
+// buckets and one atomic per point on the same few counters serialises - 7 ms for the 140 M points of a config-4 block.)
 __global__ void __launch_bounds__(DB_THREADS) db_cell_kernel(DbPoints p, DbGrid g, int64_t n, int* __restrict__ cell_id,
                                                             int* __restrict__ slot, int* __restrict__ cell_count,
                                                             int* __restrict__ outside /* NULL: bounds were measured */) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned live = __ballot_sync(0xffffffffu, i < n);
     if (i >= n) return;
     float x = p.x[i * p.stride];
     float y = g.dim > 1 ? p.y[i * p.stride] : 0.f;
@@ -155,7 +158,12 @@ __global__ void __launch_bounds__(DB_THREADS) db_cell_kernel(DbPoints p, DbGrid 
     }
     int c = cell_index(g, x, y, z, t);
     cell_id[i] = c;
-    slot[i] = atomicAdd(cell_count + c, 1);
+    const unsigned same = __match_any_sync(live, c);
+    const int leader = __ffs(same) - 1;
+    int base = 0;
+    if ((int)rb_lane() == leader) base = atomicAdd(cell_count + c, __popc(same));
+    base = __shfl_sync(same, base, leader);
+    slot[i] = base + __popc(same & rb_lanemask_lt());
 }
 
 __global__ void __launch_bounds__(DB_THREADS) db_scatter_kernel(DbPoints p, int dim, int64_t n, const int* __restrict__ cell_id,
@@ -490,14 +498,39 @@ __global__ void __launch_bounds__(DB_THREADS) dbt_bucket_init_kernel(int64_t n_c
     if (b == n_cells) b_ncore[b] = 0;                                        // scan sentinel
 }
 
+// The points are SORTED by bucket, so the lanes of a warp that share a bucket are contiguous: a segmented reduction by
+// shuffles leaves every run's result in its first lane, and only that lane touches the bucket's words. One atomic per
+// core point on the same bucket serialises in dense data (thousands of points per bucket in config 4: 23 + 26 ms of a
+// 70 ms block went into the two kernels below before this).
+template <typename T, typename Op>
+__device__ __forceinline__ T seg_reduce_sorted(T v, int key, Op op) {
+    const unsigned lane = rb_lane();
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const T ov = __shfl_down_sync(0xffffffffu, v, d);
+        const int ok = __shfl_down_sync(0xffffffffu, key, d);
+        if (lane + d < 32 && ok == key) v = op(v, ov);
+    }
+    return v;                                              // valid in the first lane of every run of equal keys
+}
+__device__ __forceinline__ bool seg_head(int key) {
+    const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+    return rb_lane() == 0 || prev != key;
+}
+
 __global__ void __launch_bounds__(DB_THREADS) dbt_bucket_stats_kernel(int n, const uint8_t* __restrict__ core, const int* __restrict__ scell,
                                                                      const int* __restrict__ sidx, const long long* __restrict__ gidx,
                                                                      int* __restrict__ b_ncore, long long* __restrict__ b_minkey) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n || core[p] != 1) return;
-    const int b = scell[p];
-    atomicAdd(b_ncore + b, 1);
-    atomicMin(b_minkey + b, point_key(gidx, sidx[p]));
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool is_core = p < n && core[p] == 1;
+    const int b = p < n ? scell[p] : -1;
+    const int cnt = seg_reduce_sorted<int>(is_core ? 1 : 0, b, [](int a, int c) { return a + c; });
+    const long long key = seg_reduce_sorted<long long>(is_core ? point_key(gidx, sidx[p]) : KEY_NONE, b,
+                                                       [](long long a, long long c) { return a < c ? a : c; });
+    if (seg_head(b) && cnt > 0) {
+        atomicAdd(b_ncore + b, cnt);
+        atomicMin(b_minkey + b, key);
+    }
 }
 
 // list of the buckets that hold core points; b_label[b] temporarily holds the bucket's slot in the list.
@@ -560,13 +593,26 @@ __global__ void __launch_bounds__(DB_THREADS) dbt_bucket_list_kernel(int64_t n_c
 template <int DIM>
 __global__ void __launch_bounds__(DB_THREADS) dbt_bucket_bbox_kernel(Sorted s, int n, const uint8_t* __restrict__ core,
                                                                     const int* __restrict__ cb_slot, int* __restrict__ cb_bbox) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n || core[p] != 1) return;
-    int* bb = cb_bbox + (size_t)cb_slot[s.cell[p]] * 6;
-    const int ox = f2ord(s.x[p]);
-    atomicMin(bb + 0, ox); atomicMax(bb + 3, ox);
-    if (DIM > 1) { const int oy = f2ord(s.y[p]); atomicMin(bb + 1, oy); atomicMax(bb + 4, oy); }
-    if (DIM > 2) { const int oz = f2ord(s.z[p]); atomicMin(bb + 2, oz); atomicMax(bb + 5, oz); }
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool is_core = p < n && core[p] == 1;
+    const int b = p < n ? s.cell[p] : -1;
+    int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+    if (is_core) {
+        lo[0] = hi[0] = f2ord(s.x[p]);
+        if (DIM > 1) lo[1] = hi[1] = f2ord(s.y[p]);
+        if (DIM > 2) lo[2] = hi[2] = f2ord(s.z[p]);
+    }
+    const int any = seg_reduce_sorted<int>(is_core ? 1 : 0, b, [](int a, int c) { return a | c; });
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+        lo[k] = seg_reduce_sorted<int>(lo[k], b, [](int a, int c) { return a < c ? a : c; });
+        hi[k] = seg_reduce_sorted<int>(hi[k], b, [](int a, int c) { return a > c ? a : c; });
+    }
+    if (seg_head(b) && any) {                             // the first lane of the bucket's run in this warp
+        int* bb = cb_bbox + (size_t)cb_slot[b] * 6;
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) { atomicMin(bb + k, lo[k]); atomicMax(bb + 3 + k, hi[k]); }
+    }
 }
 
 struct BBox { float lo[3], hi[3]; };

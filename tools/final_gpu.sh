@@ -1,10 +1,25 @@
-# Round-end verification on one B200 (run through gpurun): tests, smoke, both bench arms, then the ncu evidence.
-cd /root/repo
+#!/bin/bash
+# Round-end check on one B200: GPU test suite, smoke(), the default bench line, the reference arm, the other workloads.
+cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -x -q -m gpu --timeout=600 --timeout-method=thread > gpurun_out/final_pytest.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/final_pytest.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/final_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/final_smoke.log
-timeout 600 python bench.py > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err; echo "bench rc=$?"; cut -c1-260 gpurun_out/final_bench.json
-timeout 600 python bench.py --impl reference > gpurun_out/final_bench_ref.json 2> gpurun_out/final_bench_ref.err; echo "ref rc=$?"; cut -c1-260 gpurun_out/final_bench_ref.json
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/final_launches.csv python bench.py --steps 2 --warmup 1 > gpurun_out/final_ncu_bench.log 2>&1; echo "ncu list rc=$?"
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:spoke_mask_tma_kernel -s 3 -c 1 -o gpurun_out/r01_ncu_spoke_final python tools/run_spoke.py 32 6 > gpurun_out/final_ncu_spoke.log 2>&1; echo "ncu spoke rc=$?"
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:"dbt_union_kernel|dbt_count_kernel|dbt_border_kernel" -s 6 -c 3 -o gpurun_out/r01_ncu_dbscan_final python tools/run_block.py 512 3 > gpurun_out/final_ncu_db.log 2>&1; echo "ncu dbscan rc=$?"
+( time timeout 2000 python -m pytest tests -m gpu -q --durations=5 ) > gpurun_out/final_pytest.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/final_pytest.log
+grep -E "passed|failed|FAILED|ERROR|rc=" gpurun_out/final_pytest.log | tail -8
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/final_smoke.log 2>&1; tail -2 gpurun_out/final_smoke.log
+timeout 900 python bench.py > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err
+timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/final_bench_ref.json 2> gpurun_out/final_bench_ref.err
+for w in config5 config4 config2; do
+  timeout 900 python bench.py --workload $w --steps 12 > gpurun_out/final_bench_$w.json 2> gpurun_out/final_bench_$w.err
+done
+python - <<'PY'
+import json
+for n in ("final_bench", "final_bench_ref", "final_bench_config5", "final_bench_config4", "final_bench_config2"):
+    try:
+        d = json.loads(open(f"gpurun_out/{n}.json").read().strip().splitlines()[-1])
+        e = d.get("e2e", {})
+        print(n, "value", round(d["value"], 1), "ms/step", round(d["ms_per_step"], 3), "e2e", round(e.get("value", 0), 1), "u8", round(d.get("e2e_uint8_echoes", {}).get("value", 0), 1),
+              "cpu", round(d.get("cpu_baseline", {}).get("value", 0), 4), "cores", d.get("cpu_baseline", {}).get("cores"), "roof", d.get("roofline", {}).get("frac"),
+              "copy-only", e.get("h2d_copy_only", {}).get("frames_per_s"), "launches", d.get("gpu_launches"), "clocks", d.get("clocks", {}).get("sm_mhz"), d.get("clocks", {}).get("reasons"))
+    except Exception as ex:
+        print(n, "FAILED", ex)
+PY
