@@ -47,7 +47,7 @@ WORKLOADS = {
     "config4": dict(desc="config4: dense clutter stress, gain-fused 40/50/75, thr 2 / stride 2 / eps 12 (~2.2 M points per frame), "
                          "land filter, ST-DBSCAN eps 12/2/15",
                     gains=(40, 50, 75), cfg=dict(intensity_threshold=2.0, point_stride=2, eps_space=12.0),
-                    frames=64, e2e_frames=32, cpu_frames=11, cpu_sector=1024, streams=2),
+                    frames=64, e2e_frames=32, cpu_frames=11, cpu_sector=1024, streams=2, shard_in_flight=2),
     "config5": dict(desc="config5: long horizon, gain-fused 40/50/75, land filter, ST-DBSCAN eps 8/5/15 (eps_time 5: an 11-frame window, "
                          "5-frame halo between time shards), thr 10 / stride 4",
                     gains=(40, 50, 75), cfg=dict(eps_time=5.0), frames=1024, e2e_frames=128, cpu_frames=64, cpu_sector=1, streams=4),
@@ -60,7 +60,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--shard-in-flight", type=int, default=6, help="N>1: blocks interleaved per rank (one host thread, one communicator)")
+    ap.add_argument("--shard-in-flight", type=int, default=0, help="N>1: blocks interleaved per rank (one host thread, one communicator)")
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS), help="BASELINE.json configuration (default: config 3, the "
                     "one the metric is quoted on)")
     ap.add_argument("--frames-per-step", type=int, default=0, help="frames per rank and step (device-resident `value`); 0 = the workload's default")
@@ -81,6 +81,7 @@ def parse_args():
     args.frames_per_step = args.frames_per_step or w["frames"]
     args.e2e_frames = args.e2e_frames or w["e2e_frames"]
     args.cpu_frames = args.cpu_frames or w["cpu_frames"]
+    args.shard_in_flight = args.shard_in_flight or w.get("shard_in_flight", 6)
     args.streams = args.streams or w["streams"]          # blocks in flight: 4 where the HBM-bound mask kernel dominates, 2 for the dense stress
     return args
 
