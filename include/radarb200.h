@@ -235,6 +235,10 @@ typedef struct rb_stdbscan_hint {
 int rb_stdbscan_plan(rb_ctx* ctx, const float* x, const float* y, const float* z, int64_t stride,
                      const float* times, int64_t n, double eps_space, float eps_time, int min_samples,
                      void* stream);
+/* A hint that does NOT contain every point / time would put points into wrong buckets: the plan flags it on the device;
+ * rb_stdbscan / rb_detect_block fail with RB_ERR_ARG at their final read-back, and a caller that drives the phases itself
+ * asks with rb_stdbscan_check (syncs; also refreshes rb_stdbscan_last_stats). */
+int rb_stdbscan_check(rb_ctx* ctx, void* stream);
 int rb_stdbscan_plan_hinted(rb_ctx* ctx, const float* x, const float* y, const float* z, int64_t stride,
                             const float* times, int64_t n, double eps_space, float eps_time, int min_samples,
                             const rb_stdbscan_hint* hint /* host, may be NULL */, void* stream);

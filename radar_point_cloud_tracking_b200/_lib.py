@@ -85,6 +85,7 @@ SIGNATURES = {
     "rb_stdbscan_last_stats": (c_i32, [c_vp, C.POINTER(DbscanStats)]),
     "rb_stdbscan_plan": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_f64, c_f32, c_i32, c_vp]),
     "rb_stdbscan_plan_hinted": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_f64, c_f32, c_i32, C.POINTER(StdbscanHint), c_vp]),
+    "rb_stdbscan_check": (c_i32, [c_vp, c_vp]),
     "rb_stdbscan_cores": (c_i32, [c_vp, c_vp, c_vp]),
     "rb_stdbscan_set_cores": (c_i32, [c_vp, c_vp, c_vp]),
     "rb_stdbscan_components": (c_i32, [c_vp, c_vp, c_vp, c_vp]),

@@ -1522,6 +1522,13 @@ extern "C" int rb_stdbscan_wf(rb_ctx* ctx, const float* x, const float* y, const
     return rb_stdbscan_fetch_stats(ctx, n_clusters, stream_);
 }
 
+// After phases driven by the caller (rb_stdbscan_plan_hinted ... rb_stdbscan_assign): syncs the stream, refreshes the
+// counters of rb_stdbscan_last_stats and fails if the plan's hint box did not contain every point and time.
+extern "C" int rb_stdbscan_check(rb_ctx* ctx, void* stream_) {
+    RB_REQUIRE(ctx && ctx->db_plan && ctx->db_plan->valid, "rb_stdbscan_check: no plan");
+    return fetch_stats(ctx, *ctx->db_plan, nullptr, (cudaStream_t)stream_);
+}
+
 extern "C" int rb_stdbscan_last_stats(rb_ctx* ctx, rb_dbscan_stats* out) {
     RB_REQUIRE(ctx && out, "NULL argument");
     *out = ctx->last_stats;

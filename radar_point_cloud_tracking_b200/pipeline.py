@@ -66,9 +66,8 @@ class DetectionResult:
         n = self.points.n
         p = self.points
         packed = torch.stack([p.x[:n], p.y[:n], p.inten[:n]], dim=1)
-        return dict(points=packed.cpu().numpy(), gains=p.gain[:n].cpu().numpy(),
-                    frame_off=p.frame_off.cpu().numpy(), labels=self.labels[:n].cpu().numpy(),
-                    frame_ids=self.frame_ids)
+        points, gains, frame_off, labels = dev.to_pinned_host(packed, p.gain[:n], p.frame_off, self.labels[:n])
+        return dict(points=points, gains=gains, frame_off=frame_off, labels=labels, frame_ids=self.frame_ids)
 
     def to_frames(self, host: Optional[dict] = None, frame_cls=None) -> list:
         """``RadarFrame`` objects as the reference's ``build_frame`` + land filter would hold them.

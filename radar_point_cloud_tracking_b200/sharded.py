@@ -416,8 +416,9 @@ class ShardResult:
     def to_host(self) -> dict:
         n, p = self.points.n, self.points
         packed = torch.stack([p.x[:n], p.y[:n], p.inten[:n]], dim=1)
-        return dict(points=packed.cpu().numpy(), gains=p.gain[:n].cpu().numpy(), frame_off=p.frame_off.cpu().numpy(),
-                    labels=self.labels[:n].cpu().numpy(), frame_ids=self.frame_ids)
+        from .device import to_pinned_host
+        points, gains, frame_off, labels = to_pinned_host(packed, p.gain[:n], p.frame_off, self.labels[:n])
+        return dict(points=points, gains=gains, frame_off=frame_off, labels=labels, frame_ids=self.frame_ids)
 
 
 # ------------------------------------------------------------------------------------------ driver

@@ -380,6 +380,48 @@ def test_stdbscan_phases_and_global_keys(gpu, db_mode):
     assert np.array_equal(key2 >= 0, mod_core)
 
 
+def test_stdbscan_wrong_hint_is_an_error_not_a_wrong_answer(gpu):
+    """A hint box that does not contain every point would clamp points into edge buckets ("same tight cell => neighbour"
+    would then be false): the plan flags it on the device and the check fails loudly."""
+    from radar_point_cloud_tracking_b200 import RadarB200Error
+    rng = np.random.default_rng(2)
+    n = 20000
+    d = torch.device("cuda:0")
+    x = torch.from_numpy((rng.random(n) * 200 - 100).astype(np.float32)).to(d)
+    y = torch.from_numpy((rng.random(n) * 200 - 100).astype(np.float32)).to(d)
+    t = torch.from_numpy(rng.integers(0, 8, n).astype(np.float32)).to(d)
+    good = gpu.StDbscanPhases(x, y, None, t, 5.0, 1.0, 5, n=n, hint=(-100.0, 100.0, -100.0, 100.0, 0.0, 7.0))
+    good.cores()
+    good.check()                                                      # a box that holds everything: fine
+    for bad_hint in ((-100.0, 50.0, -100.0, 100.0, 0.0, 7.0), (-100.0, 100.0, -100.0, 100.0, 0.0, 5.0)):      # x cut / time cut
+        bad = gpu.StDbscanPhases(x, y, None, t, 5.0, 1.0, 5, n=n, hint=bad_hint)
+        bad.cores()
+        with pytest.raises(RadarB200Error, match="hinted box"):
+            bad.check()
+
+
+def test_block_driver_clusters_in_3d_like_t3(gpu):
+    """DetectionConfig(cluster_3d=True): rb_detect_block clusters on (x, y, z = intensity), the coordinates
+    3_stdbscan_point_clouds.py builds (T3:177-182) - labels against the C oracle on the block's own points."""
+    from radar_point_cloud_tracking_b200.pipeline import DetectionConfig, DetectionPipeline
+    spec = syn.SweepSpec(seed=36, frames=20, spokes=512, bins=1024, gains=(50,), clutter_p=0.004)
+    cfg = DetectionConfig(gains=(50,), land_filter=False, eps_space=5.0, eps_time=1.0, min_samples=10, cluster_3d=True)
+    pipe = DetectionPipeline(cfg, 0)
+    echo = gpu.synth_echo(spec)
+    c, s, r = pipe.spoke_tables(spec.angle_units(), spec.scale(), spec.frames, spec.bins)
+    tabs = [torch.from_numpy(t).to(echo.device) for t in (c, s, r)]
+    res = pipe.run_device(echo, *tabs)
+    staged = pipe.run_device_staged(echo, *tabs)
+    p = res.points
+    coords = torch.stack([p.x[:p.n], p.y[:p.n], p.inten[:p.n]], 1).cpu().numpy()
+    times = np.repeat(np.arange(spec.frames), np.diff(p.frame_off.cpu().numpy())).astype(np.float32)
+    want, _ = st_dbscan_c(coords, times, 5.0, 1.0, 10)
+    assert p.n > 20000 and want.max() > 5
+    assert np.array_equal(res.labels.cpu().numpy(), want) and torch.equal(res.labels, staged.labels)
+    flat, _ = st_dbscan_c(coords[:, :2], times, 5.0, 1.0, 10)
+    assert not np.array_equal(flat, want)                             # the third coordinate really takes part
+
+
 def test_stdbscan_sparse_frame_ids_and_coarsening(gpu, db_mode):
     """Frame ids with huge gaps and a tiny eps over a wide extent force the grid to coarsen."""
     from radar_point_cloud_tracking_b200.clustering import st_dbscan
