@@ -66,6 +66,7 @@ def parse_args():
     ap.add_argument("--frames-per-step", type=int, default=0, help="frames per rank and step (device-resident `value`); 0 = the workload's default")
     ap.add_argument("--e2e-frames", type=int, default=0, help="frames per rank and step of the end-to-end measurement (bounds the "
                     "pinned host buffers: 3.2 GB float32 per rank at 128); 0 = the workload's default")
+    ap.add_argument("--e2e-in-flight", type=int, default=2, help="blocks in flight of the end-to-end measurement")
     ap.add_argument("--spokes", type=int, default=2048)
     ap.add_argument("--bins", type=int, default=1024)
     ap.add_argument("--seed", type=int, default=2025)
@@ -485,14 +486,14 @@ def run_ours(args):
         ov2 = None
         if world == 1:
             from radar_point_cloud_tracking_b200.pipeline import OverlappedPipeline
-            ov2 = OverlappedPipeline(cfg, device.index, workers=2)
+            ov2 = OverlappedPipeline(cfg, device.index, workers=args.e2e_in_flight)
 
         def e2e_run(host_t):
             if world == 1:
                 run = lambda k: ov2.map_host([((None, spec.angle_units(), spec.scale(), e_ids), {"pinned": host_t})] * k)
             else:
-                run = lambda k: pipe.run_host_blocks([(host_t, spec.angle_units(), spec.scale(), e_ids)] * k, in_flight=2)
-            run(2)                                                           # warm-up: both slots, their buffers and contexts
+                run = lambda k: pipe.run_host_blocks([(host_t, spec.angle_units(), spec.scale(), e_ids)] * k, in_flight=args.e2e_in_flight)
+            run(args.e2e_in_flight)                                          # warm-up: every slot, its buffers and context
             barrier()
             t0 = time.perf_counter()
             outs = run(e_steps)
@@ -526,7 +527,7 @@ def run_ours(args):
         e2e = {"value": Be * world * e_steps / (ms_e * 1e-3), "unit": UNIT, "frames_per_step_per_gpu": Be, "steps": e_steps,
                "h2d_bytes_per_step": int(out_f["h2d_bytes"]), "d2h_bytes_per_step": int(out_f["d2h_bytes"]),
                "ms_per_step": ms_e / e_steps, "host_buffers": "float32 echoes (the reference's in-memory type), pinned",
-               "blocks_in_flight": 2, "timing": "wall clock between device synchronisations, max over ranks",
+               "blocks_in_flight": args.e2e_in_flight, "timing": "wall clock between device synchronisations, max over ranks",
                "h2d_copy_only": {"ms_per_step": copy_s * 1e3, "gb_per_s_per_gpu": host_echo.numel() * 4 / copy_s / 1e9,
                                  "frames_per_s": Be * world / copy_s,
                                  "note": "the pinned echo buffer copied to the device and nothing else, all ranks at once: the "

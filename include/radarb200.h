@@ -46,6 +46,10 @@ const char* rb_last_error(void);                    /* thread-local text of the 
 int rb_create(int device, rb_ctx** out);            /* fails without a usable CUDA device */
 void rb_destroy(rb_ctx* ctx);
 int rb_device_info(rb_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_bytes);
+/* Scratch grows on demand; a buffer that was outgrown is kept until rb_destroy, because freeing device memory synchronises
+ * the whole device. rb_trim frees those buffers: call it only when no work of this context is in flight and no collective of
+ * the process waits for a peer (rb_detect_block does so itself after its final read-back). */
+int rb_trim(rb_ctx* ctx);
 
 /* ---- a1 + a2: spoke-to-point with threshold, stride and multi-gain concat fusion ------------
  * Replaces the numeric part of load_radar_csv (T4:200-232; twins PKG/core/transforms.py:13-79,

@@ -60,6 +60,7 @@ SIGNATURES = {
     "rb_last_error": (C.c_char_p, []),
     "rb_create": (c_i32, [c_i32, C.POINTER(c_vp)]),
     "rb_destroy": (None, [c_vp]),
+    "rb_trim": (c_i32, [c_vp]),
     "rb_device_info": (c_i32, [c_vp, C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i64)]),
     "rb_spoke_to_points": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_f32, c_i32,
                                    c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),

@@ -149,6 +149,16 @@ extern "C" int64_t rb_get_info(rb_ctx* ctx, const char* name) {
 
 extern "C" int64_t rb_launch_count(rb_ctx* ctx) { return ctx ? ctx->launches : -1; }
 
+// Frees the scratch buffers this context has outgrown. Only for moments when NO work of the context is in flight (the
+// caller has just synchronised its stream) and no collective of the process is waiting for a peer: cudaFree synchronises
+// the whole device. rb_detect_block calls it after its final read-back; the time-sharded path never does.
+extern "C" int rb_trim(rb_ctx* ctx) {
+    RB_REQUIRE(ctx, "ctx is NULL");
+    for (void* p : ctx->retired) cudaFree(p);
+    ctx->retired.clear();
+    return RB_OK;
+}
+
 int rb_scratch_get(rb_ctx* ctx, rb_slot slot, size_t bytes, void** out) {
     rb_scratch& s = ctx->slots[slot];
     if (bytes == 0) bytes = 16;

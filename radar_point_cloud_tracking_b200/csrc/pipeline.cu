@@ -240,5 +240,6 @@ extern "C" int rb_detect_block(rb_ctx* ctx, const float* echo, const float* cos_
     } else {
         RB_CUDA(cudaStreamSynchronize(stream));
     }
+    if (!ctx->retired.empty()) rb_trim(ctx);               // scratch outgrown during this block: nothing of ours is in flight now
     return RB_OK;
 }
