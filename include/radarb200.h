@@ -382,10 +382,13 @@ int rb_comm_exchange(rb_ctx* ctx, int n_parts, const void* const* to_left, const
  *                         [left halo (nl) | owned (n_own) | right halo (nr)]; head / ids: HOST arrays describing its
  *                         frames (head[f] = first local point of frame f, head[n_local_frames] = n_loc); the three parts
  *                         start at the global indices lbase / gbase / rbase
- *   rb_shard_pack_keys    vec int64[5 + cap_keys]: the component keys (rb_stdbscan_components) of the core points of four
- *                         zones [a, b) of the local problem (zones8: HOST int64[8]) followed by the keys that are their
- *                         own global index (one per local component), compacted in order; vec[0..5) = number of keys up to
- *                         the end of each of the five groups (they exceed cap_keys when the vector was too small) */
+ *   rb_shard_pack_keys    vec int64[9 + 2 cap_keys] = [5 running entry counts | 4 zone lengths | keys[cap_keys] | starts[cap_keys]]:
+ *                         the component keys (rb_stdbscan_components) of four zones [a, b) of the local problem (zones8: HOST
+ *                         int64[8]) RUN-LENGTH ENCODED over all their points - an entry is a key (-1 = not a core point) and the
+ *                         position in the zone from which it holds; two ranks' encodings of the same boundary points are
+ *                         merged by position on the host, at a cost that follows the number of runs, not of points - followed
+ *                         by the keys that are their own global index (one per local component). Entries beyond cap_keys are
+ *                         dropped; the counts stay true (the caller repeats with a larger vector) */
 int rb_shard_pack_stats(rb_ctx* ctx, const int64_t* frame_off, int64_t n_frames, const float* bounds4, int64_t cap, double* out7,
                         void* stream);
 int rb_shard_pack_layout(rb_ctx* ctx, const int64_t* frame_off, int64_t n_frames, const int64_t* frame_ids_host, int hh, int64_t* out,

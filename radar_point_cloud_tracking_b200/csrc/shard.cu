@@ -7,8 +7,8 @@
 //                           point counts of the first h and the last h frames]                  -> all-gather 2
 //   rb_shard_local_index   float32 time and int64 GLOBAL index of every point of the local problem
 //                          [left halo | owned | right halo]
-//   rb_shard_pack_keys     the component keys the stitch needs, compacted: core points of the four boundary zones and
-//                          the rank's distinct component keys, with the five running counts in front     -> all-gather 3
+//   rb_shard_pack_keys     the component keys the stitch needs: the four boundary zones run-length encoded (a dense zone of
+//                          one component is a single entry) and the rank's distinct component keys      -> all-gather 3
 #include "common.cuh"
 
 namespace {
@@ -59,14 +59,18 @@ struct KeySegs {
     int64_t end[5];        // cumulative length up to and including the segment
 };
 
-// virtual candidate vector = the four boundary zones, then all points; take = core (key >= 0) in the zones, root
-// (key == own global index) in the last segment
-__device__ __forceinline__ int64_t key_source(const KeySegs& sg, int64_t v, int* seg) {
+// virtual candidate vector = the four boundary zones, then all points. An ENTRY starts
+//   in a zone: where the key differs from the key of the point before it (and at the zone's first point) - the zones are
+//              run-length encoded over ALL their points, -1 = not a core point: a dense zone of millions of core points of
+//              one component is ONE entry, and the entries of two ranks for the same zone are merged by position on the host;
+//   in the last segment: at every point that is its component's smallest core (key == own global index).
+__device__ __forceinline__ int64_t key_source(const KeySegs& sg, int64_t v, int* seg, int64_t* pos_in_seg) {
     int j = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) j += v >= sg.end[k];
     *seg = j;
-    return sg.src[j] + (v - (j ? sg.end[j - 1] : 0));
+    *pos_in_seg = v - (j ? sg.end[j - 1] : 0);
+    return sg.src[j] + *pos_in_seg;
 }
 
 __global__ void __launch_bounds__(SH_THREADS) shard_key_flag_kernel(const int64_t* __restrict__ key, const int64_t* __restrict__ gidx, KeySegs sg,
@@ -74,23 +78,33 @@ __global__ void __launch_bounds__(SH_THREADS) shard_key_flag_kernel(const int64_
     const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= sg.end[4]) return;
     int seg;
-    const int64_t i = key_source(sg, v, &seg);
+    int64_t pos;
+    const int64_t i = key_source(sg, v, &seg, &pos);
     const int64_t k = key[i];
-    flag[v] = seg < 4 ? (k >= 0) : (k == gidx[i]);
+    flag[v] = seg < 4 ? (pos == 0 || key[i - 1] != k) : (k == gidx[i]);
 }
 
+// vec = [5 running entry counts | 4 zone lengths | keys[cap] | starts[cap]]
 __global__ void __launch_bounds__(SH_THREADS) shard_key_scatter_kernel(const int64_t* __restrict__ key, KeySegs sg, const int32_t* __restrict__ flag,
                                                                       const int32_t* __restrict__ pos, int64_t cap, int64_t* __restrict__ vec) {
     const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= sg.end[4]) return;
     int seg;
-    const int64_t i = key_source(sg, v, &seg);
+    int64_t in_seg;
+    const int64_t i = key_source(sg, v, &seg, &in_seg);
     const int take = flag[v];
     const int64_t p = pos[v];
-    if (take && p < cap) vec[5 + p] = key[i];
+    if (take && p < cap) {
+        vec[9 + p] = key[i];
+        vec[9 + cap + p] = seg < 4 ? in_seg : 0;
+    }
 #pragma unroll
     for (int j = 0; j < 5; ++j)
-        if (sg.end[j] - 1 == v) vec[j] = p + take;                   // keys taken up to the end of segment j
+        if (sg.end[j] - 1 == v) vec[j] = p + take;                   // entries up to the end of segment j
+    if (v == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) vec[5 + j] = sg.end[j] - (j ? sg.end[j - 1] : 0);
+    }
 }
 
 // pinned staging: [0, 1 KiB) belongs to the read-backs of other entry points; the regions below are rewritten only by
@@ -162,7 +176,7 @@ extern "C" int rb_shard_pack_keys(rb_ctx* ctx, const int64_t* key, const int64_t
                                   int64_t* vec, void* stream_) {
     RB_REQUIRE(ctx && vec && zones8_host && n_loc >= 0 && cap_keys >= 0, "bad arguments");
     cudaStream_t stream = (cudaStream_t)stream_;
-    RB_CUDA(cudaMemsetAsync(vec, 0, sizeof(int64_t) * (size_t)(5 + cap_keys), stream));
+    RB_CUDA(cudaMemsetAsync(vec, 0, sizeof(int64_t) * (size_t)(9 + 2 * cap_keys), stream));
     if (n_loc == 0) return RB_OK;
     RB_REQUIRE(key && gidx, "NULL keys");
     KeySegs sg;

@@ -83,6 +83,30 @@ def stitch_components(seg_keys: Sequence[Sequence[np.ndarray]], keys: Sequence[n
     return table_keys[:m], table_ids[:m], int(ncl.value)
 
 
+def pair_zone_runs(keys_a: np.ndarray, starts_a: np.ndarray, keys_b: np.ndarray, starts_b: np.ndarray
+                   ) -> Tuple[np.ndarray, np.ndarray]:
+    """Two ranks hold the SAME boundary points (rank r's own last frames = rank r+1's left halo, ...) with the same core
+    flags, each under its own component keys, and ship them run-length encoded: ``keys[j]`` holds from position
+    ``starts[j]`` of the zone to the next start (-1 = not a core point). Returns the distinct ``(key_a, key_b)`` pairs under
+    which one core point is known to the two ranks - what ties their local components together. The cost follows the
+    number of RUNS, not of points: a dense boundary zone of millions of core points of one component is a single run."""
+    e = np.zeros(0, np.int64)
+    if len(keys_a) == 0 or len(keys_b) == 0:
+        if len(keys_a) != len(keys_b):
+            raise RadarB200Error("stitch: boundary zones of neighbouring ranks do not match")
+        return e, e
+    cuts = np.union1d(starts_a, starts_b)
+    ka = keys_a[np.searchsorted(starts_a, cuts, side="right") - 1]
+    kb = keys_b[np.searchsorted(starts_b, cuts, side="right") - 1]
+    core = ka >= 0
+    if not np.array_equal(core, kb >= 0):
+        raise RadarB200Error("stitch: neighbouring ranks disagree on the core points of a boundary zone")
+    if not core.any():
+        return e, e
+    pairs = np.unique(np.stack([ka[core], kb[core]], axis=1), axis=0)
+    return np.ascontiguousarray(pairs[:, 0]), np.ascontiguousarray(pairs[:, 1])
+
+
 # ------------------------------------------------------------------------------------------ engines
 class TorchEngineBase:
     """Bookkeeping and collectives of the protocol with torch ops over ``torch.distributed`` (any backend, any device).
@@ -116,18 +140,32 @@ class TorchEngineBase:
         return torch.cat([off_d[F:F + 1], off_d[F - hh:F - hh + 1], ids_d[:hh], per[:hh], ids_d[F - hh:], per[F - hh:]])
 
     def pack_keys(self, key, gidx, zones, n_loc: int, cap_k: int) -> torch.Tensor:
+        """``[5 running entry counts | 4 zone lengths | keys[cap_k] | starts[cap_k]]`` (int64): the component keys of the
+        four boundary zones RUN-LENGTH ENCODED over all their points (an entry = a key and the position in the zone where
+        it starts to hold; -1 = not a core point), then the rank's distinct component keys (the points that are their
+        component's smallest core). Entries beyond ``cap_k`` are dropped; the counts stay true."""
+        buf = torch.zeros(9 + 2 * cap_k, dtype=torch.int64, device=self.device)
         if n_loc == 0:
-            return torch.zeros(5 + cap_k, dtype=torch.int64, device=self.device)
-        seg_end = np.cumsum([b - a for a, b in zones] + [n_loc])        # ends of the five segments in the candidate vector
-        is_core, is_root = key >= 0, key == gidx
-        cand = torch.cat([key[a:b] for a, b in zones] + [key])
-        take = torch.cat([is_core[a:b] for a, b in zones] + [is_root])
-        pos = torch.cumsum(take, 0) - 1
-        buf = torch.zeros(5 + cap_k + 1, dtype=torch.int64, device=self.device)
-        # head of the vector: how many keys were taken up to the end of each segment (0 for a leading empty one)
-        buf[:5] = torch.where(self.upload(seg_end > 0), pos[self.upload(np.maximum(seg_end - 1, 0))] + 1, 0)
-        buf[torch.where(take & (pos < cap_k), pos + 5, 5 + cap_k)] = cand          # the last slot takes the rest
-        return buf[:5 + cap_k]
+            return buf
+        ent_k, ent_s = [], []
+        for a, b in zones:
+            k = key[a:b]
+            if b > a:
+                flag = torch.ones(b - a, dtype=torch.bool, device=self.device)
+                flag[1:] = k[1:] != k[:-1]
+                idx = torch.nonzero(flag)[:, 0]
+            else:
+                idx = torch.zeros(0, dtype=torch.int64, device=self.device)
+            ent_k.append(k[idx]); ent_s.append(idx)
+        roots = key[key == gidx]
+        ent_k.append(roots); ent_s.append(torch.zeros_like(roots))
+        lens = np.array([len(t) for t in ent_k], dtype=np.int64)
+        buf[:5] = self.upload(np.cumsum(lens))
+        buf[5:9] = self.upload(np.array([b - a for a, b in zones], dtype=np.int64))
+        allk, alls = torch.cat(ent_k)[:cap_k], torch.cat(ent_s)[:cap_k]
+        buf[9:9 + len(allk)] = allk
+        buf[9 + cap_k:9 + cap_k + len(alls)] = alls
+        return buf
 
     # -- collectives
     def all_gather(self, mine: torch.Tensor) -> torch.Tensor:
@@ -341,7 +379,7 @@ class CudaEngine(TorchEngineBase):
     def pack_keys(self, key, gidx, zones, n_loc: int, cap_k: int) -> torch.Tensor:
         from ._lib import check, ptr, stream_ptr
         ctx = self._ctx()
-        vec = torch.empty(5 + cap_k, dtype=torch.int64, device=self.device)
+        vec = torch.empty(9 + 2 * cap_k, dtype=torch.int64, device=self.device)
         z = np.ascontiguousarray(np.array(zones, dtype=np.int64).reshape(-1))
         check(ctx.lib.rb_shard_pack_keys(ctx.handle, ptr(key) if n_loc else None, ptr(gidx) if n_loc else None, int(n_loc), z.ctypes.data,
                                          int(cap_k), ptr(vec), stream_ptr()), "rb_shard_pack_keys")
@@ -715,10 +753,10 @@ class ShardedDetection:
             key = torch.zeros(0, dtype=torch.int64, device=self.device)
 
         # ---- stitch (on every rank) -----------------------------------------------------------------------------
-        # what the stitch needs from me: the local key of every CORE point of my four boundary zones (left halo, own
-        # first frames, own last frames, right halo - they pair up with the neighbours' zones by position) and my
-        # distinct component keys (= keys of the points that ARE their component's smallest core). The engine compacts
-        # them on the device into a fixed-capacity vector [5 counts | keys ...]; collective 4 all-gathers it.
+        # what the stitch needs from me: the local keys of my four boundary zones (left halo, own first frames, own last
+        # frames, right halo - the same points, in the same order, as the neighbours' zones), run-length encoded over the
+        # zone's points, and my distinct component keys (= keys of the points that ARE their component's smallest core).
+        # The engine builds the fixed-capacity vector on the device; collective 3 all-gathers it.
         zones = ((0, nl), (nl, nl + lo_end), (nl + hi_start, nl + n_own), (nl + n_own, n_loc))
         while True:
             cap_k = self._key_cap
@@ -735,10 +773,23 @@ class ShardedDetection:
             if need <= cap_k:
                 break
             self._key_cap = int(need * 1.5) + 1024             # too small somewhere: everybody repeats with more room
-        all_segs, all_keys = [], []
+        # every rank's zones as runs (key, start) and its distinct component keys
+        runs, all_keys = [], []
         for r in range(self.world):
-            pieces = np.split(got[r, 5:5 + int(sizes[r].sum())], np.cumsum(sizes[r])[:-1])
-            all_segs.append(pieces[:4]); all_keys.append(pieces[4])
+            tot = int(sizes[r].sum())
+            cuts = np.cumsum(sizes[r])[:-1]
+            k_parts = np.split(got[r, 9:9 + tot], cuts)
+            s_parts = np.split(got[r, 9 + cap_k:9 + cap_k + tot], cuts)
+            runs.append([(k_parts[z], s_parts[z]) for z in range(4)])
+            all_keys.append(k_parts[4])
+        # the same boundary points under two ranks' keys: own last frames | left halo, right halo | own first frames
+        e = np.zeros(0, np.int64)
+        all_segs = [[e, e, e, e] for _ in range(self.world)]
+        for r in range(self.world - 1):
+            for za, zb in ((2, 0), (3, 1)):
+                if got[r, 5 + za] != got[r + 1, 5 + zb]:
+                    raise RadarB200Error("stitch: boundary zones of neighbouring ranks do not match")
+                all_segs[r][za], all_segs[r + 1][zb] = pair_zone_runs(*runs[r][za], *runs[r + 1][zb])
         tk, ti, ncl = stitch_components(all_segs, all_keys)
         self._tick("stitch")
 

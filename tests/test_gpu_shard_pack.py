@@ -83,6 +83,7 @@ def test_local_index_and_pack_keys(engines):
         for cap_k in (8192, 37, 0):
             got = cuda.pack_keys(key, gidx, zones, n_loc, cap_k)
             want = ref.pack_keys(key, gidx, zones, n_loc, cap_k)
-            assert torch.equal(got[:5], want[:5])                           # the five running counts (true sizes)
+            assert torch.equal(got[:9], want[:9])                           # the five running counts (true sizes), zone lengths
             n_fit = min(int(want[4]), cap_k)
-            assert torch.equal(got[5:5 + n_fit], want[5:5 + n_fit])
+            assert torch.equal(got[9:9 + n_fit], want[9:9 + n_fit])                              # run keys, then root keys
+            assert torch.equal(got[9 + cap_k:9 + cap_k + n_fit], want[9 + cap_k:9 + cap_k + n_fit])  # where each run starts
