@@ -18,16 +18,12 @@ except Exception as e:
     print(f"{label:44s} FAILED: {e}: {line[:200]}", flush=True)
 PY
 }
-run "64Kx3 (197 KB), 3 in flight"   RB_OPT_SPOKE_RING=0
-run "48Kx3 (148 KB), 3 in flight"   RB_OPT_SPOKE_RING=5
-run "64Kx2 (131 KB), 3 in flight"   RB_OPT_SPOKE_RING=3
-run "48Kx2 ( 98 KB), 3 in flight"   RB_OPT_SPOKE_RING=6
-run "32Kx3 ( 98 KB), 3 in flight"   RB_OPT_SPOKE_RING=2
-run "16Kx6 ( 98 KB), 3 in flight"   RB_OPT_SPOKE_RING=8
-run "16Kx4 ( 66 KB), 3 in flight"   RB_OPT_SPOKE_RING=4
-run "32Kx4 (131 KB), 3 in flight"   RB_OPT_SPOKE_RING=1
-EXTRA="--streams 2" run "32Kx3, 2 in flight"  RB_OPT_SPOKE_RING=2
-EXTRA="--streams 4" run "32Kx3, 4 in flight"  RB_OPT_SPOKE_RING=2
-EXTRA="--streams 4" run "16Kx6, 4 in flight"  RB_OPT_SPOKE_RING=8
-EXTRA="--streams 4" run "48Kx2, 4 in flight"  RB_OPT_SPOKE_RING=6
-run "32Kx3 + l2 hint, 3 in flight"  RB_OPT_SPOKE_RING=2 RB_OPT_SPOKE_L2_HINT=1
+run "32Kx3 ( 98 KB, default)"        RB_OPT_SPOKE_RING=2
+run "48Kx2 ( 98 KB)"                 RB_OPT_SPOKE_RING=3
+run "32Kx4 (131 KB)"                 RB_OPT_SPOKE_RING=1
+run "64Kx3 (197 KB, round 1)"        RB_OPT_SPOKE_RING=0
+run "32Kx3, no L2 evict-first hint"  RB_OPT_SPOKE_RING=2 RB_OPT_SPOKE_L2_HINT=0
+run "32Kx3, no mask gate"            RB_OPT_SPOKE_RING=2 RB_OPT_MASK_GATE=0
+run "32Kx3, no launch priority"      RB_OPT_SPOKE_RING=2 RB_OPT_MASK_PRIORITY=0
+run "32Kx3 + carveout 44 everywhere" RB_OPT_SPOKE_RING=2 RB_OPT_CARVEOUT=44
+for k in 1 2 3 4 6; do EXTRA="--streams $k" run "32Kx3, $k block(s) in flight" RB_OPT_SPOKE_RING=2; done
