@@ -161,3 +161,81 @@ def test_stitch_components_matches_a_plain_union_find():
         want = {k: roots.index(find(k)) for k in parent}
         assert list(tk) == sorted(parent) and ncl == len(roots)
         assert [want[int(k)] for k in tk] == list(ti)
+
+
+def test_pair_zone_runs_equals_positional_pairing():
+    """The run-length encoded boundary zones of two neighbouring ranks (sharded.pair_zone_runs) give exactly the distinct
+    key pairs of the position-by-position pairing of the decoded arrays."""
+    from radar_point_cloud_tracking_b200.sharded import pair_zone_runs
+
+    rng = np.random.default_rng(21)
+
+    def encode(keys):
+        if len(keys) == 0:
+            return np.zeros(0, np.int64), np.zeros(0, np.int64)
+        start = np.flatnonzero(np.concatenate([[True], keys[1:] != keys[:-1]]))
+        return keys[start], start.astype(np.int64)
+
+    for n in (0, 1, 7, 500, 20000):
+        core = rng.random(n) < 0.7
+        # two labelings of the same points: components of A are unions of runs, B's are a different coarsening
+        a = np.where(core, 1000 + rng.integers(0, 6, n) * 3, -1).astype(np.int64)
+        b = np.where(core, 5000 + (rng.integers(0, 4, n) + np.arange(n) // max(n // 3, 1)) * 7, -1).astype(np.int64)
+        if n > 50:
+            a[10:40] = np.where(core[10:40], 1000, -1)                     # a long run
+        pa, pb = pair_zone_runs(*encode(a), *encode(b))
+        want = np.unique(np.stack([a[core], b[core]], axis=1), axis=0) if core.any() else np.zeros((0, 2), np.int64)
+        assert np.array_equal(np.stack([pa, pb], axis=1), want)
+    with pytest.raises(Exception):
+        pair_zone_runs(np.array([5, -1]), np.array([0, 3]), np.array([-1, 9]), np.array([0, 3]))      # core sets disagree
+
+
+def test_clusters_from_records_replays_set_order():
+    """device.clusters_from_records (host logic): from a segment table in (frame, label) order with first-occurrence
+    indices it rebuilds {frame: [Cluster]} in the iteration order of set(frame_labels) - labels far beyond the set's
+    table size, so hash collisions and table growth matter - with member arrays as views of the grouped arrays."""
+    from radar_point_cloud_tracking_b200.device import clusters_from_records
+    from radar_point_cloud_tracking_b200.tracker import Cluster
+
+    rng = np.random.default_rng(23)
+    sizes = [0, 900, 3, 2500, 0, 40]
+    K = 700
+    pts, labels = [], []
+    for n in sizes:
+        pts.append(np.column_stack([rng.normal(0, 50, n), rng.normal(0, 50, n), rng.random(n) * 255]).astype(np.float32))
+        labels.append((rng.integers(-1, K, n) * (rng.random(n) < 0.8) - (rng.random(n) < 0.1)).clip(-1, K - 1).astype(np.int32))
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    frame_ids = [11, 12, 13, 14, 15, 16]
+    # the table the device would produce, built here with numpy: segments by frame, then label; grouped points stable
+    rec = {k: [] for k in ("frame", "label", "first", "count", "start", "cx", "cy", "mean_intensity")}
+    gx, gy, gi = [], [], []
+    pos = 0
+    for f, (p, lab) in enumerate(zip(pts, labels)):
+        for l in np.unique(lab):
+            m = np.flatnonzero(lab == l)
+            rec["frame"].append(f); rec["label"].append(l); rec["first"].append(m[0]); rec["count"].append(len(m))
+            if l < 0:
+                rec["start"].append(-1); rec["cx"].append(0); rec["cy"].append(0); rec["mean_intensity"].append(0)
+                continue
+            cen, mi = O.cluster_means_f32(p[m, :2], p[m, 2])
+            rec["start"].append(pos); rec["cx"].append(cen[0]); rec["cy"].append(cen[1]); rec["mean_intensity"].append(mi)
+            gx.append(p[m, 0]); gy.append(p[m, 1]); gi.append(p[m, 2]); pos += len(m)
+    rec = {k: np.array(v, dtype=np.int64 if k == "start" else np.float32 if k in ("cx", "cy", "mean_intensity") else np.int32)
+           for k, v in rec.items()}
+    rec.update(gx=np.concatenate(gx), gy=np.concatenate(gy), gi=np.concatenate(gi))
+    got = clusters_from_records(rec, frame_ids, Cluster)
+    want_frames = []
+    for f, (p, lab) in enumerate(zip(pts, labels)):
+        ids = set(lab)                                                 # the reference's loop, T4:518-534
+        ids.discard(-1)
+        if not ids:
+            continue
+        want_frames.append(frame_ids[f])
+        g = got[frame_ids[f]]
+        assert [c.cluster_id for c in g] == [int(c) for c in ids]      # the set's own iteration order
+        for c, cid in zip(g, ids):
+            m = lab == cid
+            assert np.array_equal(c.points, p[m, :2]) and np.array_equal(c.intensities, p[m, 2])
+            assert np.array_equal(c.centroid, np.mean(p[m, :2], axis=0)) and c.mean_intensity == float(np.mean(p[m, 2]))
+            assert c.points.base is not None                           # a view into the grouped arrays, not a copy
+    assert list(got) == want_frames

@@ -196,3 +196,16 @@ def test_wf_variant_oracles_vs_reference_golden():
         if k < 6:                                                 # the Python restatements are slow: a few cases
             assert np.array_equal(O.st_dbscan_wf_canonical(c, tm, float(eps_s), float(eps_t), int(ms), int(mf))[0], want), k
             assert np.array_equal(O.st_dbscan_wf_sequential(c, tm, float(eps_s), float(eps_t), int(ms), int(mf)), want), k
+
+
+def test_cluster_mean_reduction_orders_are_numpys():
+    """The float32 reduction orders the device cluster records reproduce (csrc/clusters.cu), pinned against numpy itself:
+    np.mean over the rows of an [n, 2] array is sequential per column; np.mean of a 1-D array is numpy's pairwise sum."""
+    rng = np.random.default_rng(17)
+    for n in list(range(1, 40)) + [127, 128, 129, 255, 256, 257, 1000, 4097, 20001]:
+        pts = (rng.random((n, 2)) * 400 - 200).astype(np.float32)
+        inten = (rng.random(n) * 255).astype(np.float32)
+        cen, mi = O.cluster_means_f32(pts, inten)
+        assert np.array_equal(cen, np.mean(pts, axis=0)), n
+        assert mi == np.mean(inten) and mi.dtype == np.float32, n
+        assert O.pairwise_sum_f32(inten) == np.add.reduce(inten), n
