@@ -1,5 +1,6 @@
-"""Time-sharded multi-GPU driver of the detection path (SURVEY.md section 8 e): one process per GPU,
-``torch.distributed`` (NCCL over NVLink/NVSwitch; gloo in the CPU tests) for the few small exchanges.
+"""Time-sharded multi-GPU driver of the detection path (SURVEY.md section 8 e): one process per GPU, a few small
+exchanges per block over NCCL (NVLink/NVSwitch) issued by ``libradarb200.so`` itself; gloo through ``torch.distributed``
+in the CPU tests.
 
 Rank r owns a contiguous block of frames. Spoke-to-point is embarrassingly parallel; the land filter
 needs two tiny reductions; ST-DBSCAN couples frame f only to frames within ``eps_time``, so every rank
@@ -11,15 +12,17 @@ stitched from the ranks' component keys. Per block (details and measurements: DE
 3. ``all_gather`` of the ranks' halo layouts (points owned, ids and per-frame counts of the boundary frames)
 4. neighbour send/recv of the boundary frames' filtered points (x, y)   -> exact core flags of OWNED points
 5. neighbour send/recv of those points' core flags (1 B/point)          -> exact core flags of HALO points
-6. components over owned + halo cores, keyed by GLOBAL point index; ``all_gather`` of the local component key of
-   every boundary-zone core point and of every rank's distinct keys; EVERY rank unions the keys that share a point
-   and numbers the components by their smallest core index - exactly the reference's numbering
-   (``rb_stitch_components``)
+6. components over owned + halo cores, keyed by GLOBAL point index; ``all_gather`` of the local component keys of the
+   boundary zones (run-length encoded over the zones' points: a dense zone of one component is a single entry) and of
+   every rank's distinct keys; EVERY rank merges the neighbours' encodings of the same points by position
+   (:func:`pair_zone_runs`), unions the keys that share a point and numbers the components by their smallest core index
+   - exactly the reference's numbering (``rb_stitch_components``)
 7. ``rb_relabel`` + border assignment (all neighbours of an owned point are present locally)
 
-What the collectives carry is assembled on the device; a block reads back to the host three times. A block is a
-generator that yields before each read-back, so one host thread can interleave several blocks over one
-communicator (:meth:`ShardedDetection.run_blocks`).
+What the collectives carry is assembled on the device; a block reads back to the host three times, asynchronously into
+pinned memory. A block is a generator that yields before each read-back, so one host thread keeps several blocks going,
+each in its own block slot - CUDA stream, library context and communicator - and steps whichever block's read-back has
+arrived (:meth:`ShardedDetection.run_blocks`).
 
 The result equals the single-GPU labels of the concatenated recording, id for id.
 
