@@ -610,6 +610,15 @@ def run_reference(args):
     if rank != 0:
         return
     workers = max(1, min(os.cpu_count() or 1, 32))
+    # every worker keeps its block of float32 sweeps in memory (input generation stays outside the timed region): leave
+    # at least half of the available RAM alone
+    try:
+        import psutil
+        w = WORKLOADS[args.workload]
+        per_worker = args.cpu_frames * len(w["gains"]) * max(1, args.spokes // int(w["cpu_sector"])) * args.bins * 4 * 1.5 + 1.5e9
+        workers = max(1, min(workers, int(psutil.virtual_memory().available * 0.5 / per_worker)))
+    except Exception:
+        pass
     steps = max(1, min(args.steps, 2))
     warm = min(args.warmup, 1)
     cb = run_cpu_reference(args, steps=steps, warmup=warm, workers=workers, frames=args.cpu_frames)
