@@ -239,3 +239,27 @@ def test_clusters_from_records_replays_set_order():
             assert np.array_equal(c.centroid, np.mean(p[m, :2], axis=0)) and c.mean_intensity == float(np.mean(p[m, 2]))
             assert c.points.base is not None                           # a view into the grouped arrays, not a copy
     assert list(got) == want_frames
+
+
+def test_read_back_staging_views_and_copies():
+    """The result read-back goes through one reusable staging buffer per thread (device.to_pinned_host): views at aligned
+    offsets with the tensors' dtypes and shapes, arrays handed out as copies, the buffer reused until it is too small."""
+    import torch
+
+    from radar_point_cloud_tracking_b200 import device as dv
+    ts = [torch.randn(1000, 3), torch.arange(7, dtype=torch.int32), torch.zeros(0, 3),
+          torch.randint(0, 255, (513,), dtype=torch.uint8), torch.arange(5, dtype=torch.int64)]
+    total = sum((t.numel() * t.element_size() + 255) & ~255 for t in ts)
+    buf = dv._staging_buffer(total, False)
+    views = dv._staging_views(buf, ts)
+    for v, t in zip(views, ts):
+        assert v.dtype == t.dtype and v.shape == t.shape and (t.numel() == 0 or v.data_ptr() % 256 == buf.data_ptr() % 256)
+        v.copy_(t)
+    for v, t in zip(views, ts):
+        assert np.array_equal(v.numpy(), t.numpy())
+    assert dv._staging_buffer(16, False) is buf
+    bigger = dv._staging_buffer(buf.numel() + 1, False)
+    assert bigger is not buf and bigger.numel() > buf.numel()
+    out = dv.to_pinned_host(*ts)                                    # host tensors: plain copies
+    ts[1][0] = 99
+    assert out[1][0] == 0 and all(np.array_equal(o[1:] if i == 1 else o, (t.numpy()[1:] if i == 1 else t.numpy())) for i, (o, t) in enumerate(zip(out, ts)))

@@ -791,3 +791,27 @@ def test_stdbscan_partition_is_permutation_invariant_at_scale(gpu):
     assert np.array_equal(a < 0, b < 0)                          # same noise set
     pairs = np.unique(np.stack([a[cm], b[cm]]), axis=1)          # label map between the two runs on core points
     assert pairs.shape[1] == ncl1 and len(np.unique(pairs[0])) == ncl1 and len(np.unique(pairs[1])) == ncl1
+
+
+def test_result_read_back_modes_agree_and_results_stay_valid(gpu, monkeypatch):
+    dev = gpu
+    """device.to_pinned_host: the staging path (default), fresh pinned tensors and plain .cpu() hand out the same arrays;
+    arrays of an earlier call are not touched by later calls (the staging buffer is reused, the results are copies)."""
+    import torch
+    d = torch.device("cuda", 0)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    ts = [torch.randn(70001, 3, generator=g).to(d), torch.arange(333, dtype=torch.int32, device=d), torch.zeros(0, dtype=torch.int32, device=d),
+          torch.randint(0, 255, (1025,), dtype=torch.uint8, generator=g).to(d), torch.arange(129, dtype=torch.int64, device=d)]
+    want = [t.cpu().numpy() for t in ts]
+    kept = {}
+    for mode in ("staging", "pinned", "pageable"):
+        monkeypatch.setattr(dev, "HOST_READBACK_MODE", mode)
+        kept[mode] = dev.to_pinned_host(*ts)
+        for a, b in zip(kept[mode], want):
+            assert a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b)
+    monkeypatch.setattr(dev, "HOST_READBACK_MODE", "staging")
+    dev.to_pinned_host(*[t * 0 for t in ts])                          # overwrites the staging buffer
+    dev.to_pinned_host(torch.ones(4_000_000, device=d))               # grows it
+    for mode in kept:
+        for a, b in zip(kept[mode], want):
+            assert np.array_equal(a, b)
