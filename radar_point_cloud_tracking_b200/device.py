@@ -79,8 +79,8 @@ def to_pinned_host(*tensors):
     read-back (config 4: 1.4 GB of points and labels per 32 frames) is made of. The pinned memory is a per-thread
     staging buffer that is reused from call to call and the arrays handed out are ordinary numpy copies of it: allocating
     page-locked memory is an implicit device-wide synchronisation point, and a caller that keeps its results (so that
-    torch's host cache can never recycle the blocks) would pay for it on every block - measured, two blocks in flight:
-    152 ms per 128-frame block instead of 64."""
+    torch's host cache can never recycle the blocks) would pay for it on every block - seen once on one box, two blocks in flight:
+    152 ms per 128-frame block instead of 62 (profiles/r02_e2e_readback_modes.txt)."""
     if not tensors:
         return []
     if not tensors[0].is_cuda:
