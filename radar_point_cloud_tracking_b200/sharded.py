@@ -817,7 +817,10 @@ class ShardedDetection:
         n, p = res.points.n, res.points
         pause = self._pause(0, p.x[:n], p.y[:n], p.inten[:n], p.gain[:n], p.frame_off, res.labels[:n])
         yield pause
-        x, y, inten, gain, off, labels = (t.numpy() for t in pause[2])
+        # copies, not views: the page-locked blocks go back to torch's host cache with this generator, so a caller that
+        # keeps its results does not make every later block allocate page-locked memory (device.to_pinned_host)
+        x, y, inten, gain, off, labels = (np.array(t.numpy()) for t in pause[2])
+        del pause
         out = dict(points=np.stack([x, y, inten], axis=1), gains=gain, frame_off=off, labels=labels, frame_ids=res.frame_ids,
                    n_clusters=res.n_clusters)
         out["h2d_bytes"] = t_echo.numel() * t_echo.element_size() + 3 * c.nbytes
