@@ -198,6 +198,31 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------ CPU (oracle port)
 _CPU_CACHE = {}
+_REF_T4 = []
+
+
+def reference_t4():
+    """The UNMODIFIED reference script ``4_temporal_object_tracker.py`` as a module, if ``__graft_entry__.build()`` has
+    installed it under ``baseline/_ref/`` (it travels to the GPU box with the snapshot), else ``None``."""
+    if not _REF_T4:
+        import importlib.util
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "baseline", "_ref", "PointCloudWork", "4_temporal_object_tracker.py")
+        mod = None
+        if os.path.exists(path):
+            try:
+                os.environ.setdefault("MPLBACKEND", "Agg")
+                spec = importlib.util.spec_from_file_location("reference_t4_unmodified", path)
+                mod = importlib.util.module_from_spec(spec)
+                sys.modules["reference_t4_unmodified"] = mod
+                spec.loader.exec_module(mod)
+                if not getattr(mod, "HAS_SKLEARN", False):
+                    mod = None
+            except Exception as e:                                       # a missing plotting dependency, say: the port takes over
+                sys.stderr.write(f"reference T4 not importable ({e!r}); timing the oracle port instead\n")
+                mod = None
+        _REF_T4.append(mod)
+    return _REF_T4[0]
+
 
 
 def cpu_block_sample(args_tuple):
@@ -222,6 +247,7 @@ def cpu_block_sample(args_tuple):
                             for g in range(len(spec.gains))] for f in range(frames)]
         O._query_radius(np.zeros((4, 2), np.float32), 1.0)               # import scikit-learn before the clock starts
     echo = _CPU_CACHE[key]
+    T4 = None if prm["cluster_3d"] else reference_t4()                     # imported before the clock starts
     ang, scale = spec.angle_units()[:keep_spokes], spec.scale()[:keep_spokes]
     t0 = time.perf_counter()
     pts = []
@@ -231,6 +257,25 @@ def cpu_block_sample(args_tuple):
         fused = O.fuse_concat(per_gain)
         pts.append(fused[0] if fused is not None else np.zeros((0, 3), np.float32))
     t1 = time.perf_counter()
+    if T4 is not None:
+        # land filter and ST-DBSCAN (incl. its per-frame Cluster records) by the reference's OWN functions, called the way
+        # its run_pipeline does (T4:936-975) with its own land-filter constants (the workloads do not change those)
+        import contextlib
+        import datetime
+        import io
+        t_stamp = datetime.datetime(2025, 1, 1)
+        with contextlib.redirect_stdout(io.StringIO()):
+            frs = [T4.RadarFrame(timestamp=t_stamp, timestamp_ms=f, frame_id=f, points=p, gains=np.zeros(len(p), np.int32))
+                   for f, p in enumerate(pts) if len(p)]
+            if prm["land_filter"] and len(frs) > 10:
+                count, isum, edges = T4.build_occupancy_grid(frs, T4.LAND_GRID_RESOLUTION)
+                land = T4.identify_land_cells(count, isum, len(frs))
+                frs = [T4.filter_land_from_frame(fr, land, edges) for fr in frs]
+            t2 = time.perf_counter()
+            by_frame = T4.st_dbscan(frs, prm["eps_space"], prm["eps_time"], prm["min_samples"])
+        t3 = time.perf_counter()
+        ids = {c.cluster_id for cl in by_frame.values() for c in cl}
+        return (t1 - t0, t2 - t1, t3 - t2, int(sum(fr.num_points for fr in frs)), len(ids), True)
     built = [p for p in pts if len(p)]
     if prm["land_filter"] and len(built) > 10:
         count, isum, edges = O.occupancy_grid(built)
@@ -244,7 +289,7 @@ def cpu_block_sample(args_tuple):
     else:
         labels, _ = O.st_dbscan_frames(list(enumerate(pts)), prm["eps_space"], prm["eps_time"], prm["min_samples"], sequential=True)
     t3 = time.perf_counter()
-    return (t1 - t0, t2 - t1, t3 - t2, int(sum(len(p) for p in pts)), int(labels.max() + 1 if len(labels) else 0))
+    return (t1 - t0, t2 - t1, t3 - t2, int(sum(len(p) for p in pts)), int(labels.max() + 1 if len(labels) else 0), False)
 
 
 def run_cpu_reference(args, steps: int, warmup: int, workers: int, frames: int = 64):
@@ -274,13 +319,20 @@ def run_cpu_reference(args, steps: int, warmup: int, workers: int, frames: int =
             f"consecutive frames cut to an angular sector of 1/{sector} of the spokes ({max(1, args.spokes // sector)}x{args.bins} x "
             f"{len(w['gains'])} gains, at the recording's true density; value = frames x 1/{sector} per second, which FAVOURS the CPU: "
             f"its cost grows faster than the sector)")
+    real = all(r[5] for r in detail)
+    how = ("land filter, ST-DBSCAN and Cluster records by the functions of the UNMODIFIED reference script (baseline/_ref/PointCloudWork/"
+           "4_temporal_object_tracker.py: build_occupancy_grid, identify_land_cells, filter_land_from_frame, st_dbscan), spoke-to-point "
+           "(T4:200-232, which the reference only has inside its CSV reader) by the numpy port pinned to it"
+           if real else
+           "numpy/scikit-learn oracle port of the reference incl. its sequential ST-DBSCAN expansion")
     return {"value": frames * workers / sector / mean_t, "ms_per_step": mean_t * 1e3, "cores": workers,
+            "kind": "reference" if real else "port",
             "sample": f"{workers} worker(s) x {frames} {what} of the same "
-                      f"synthetic recording, numpy/scikit-learn oracle port of T4 incl. the reference's sequential ST-DBSCAN "
-                      f"expansion; input generation untimed; the reference's cost per frame grows with the block length "
-                      f"(spatial-only BallTree over all frames, T4:474-475)",
+                      f"synthetic recording; {how}; input generation untimed; the reference's cost per frame grows with the "
+                      f"block length (spatial-only BallTree over all frames, T4:474-475)",
             "stage_seconds": [float(sum(r[i] for r in detail) / len(detail)) for i in range(3)],
-            "points_per_sample": int(sum(r[3] for r in detail) / len(detail))}
+            "points_per_sample": int(sum(r[3] for r in detail) / len(detail)),
+            "clusters_per_sample": int(sum(r[4] for r in detail) / len(detail))}
 
 
 # ------------------------------------------------------------------------------------ ours
@@ -597,7 +649,7 @@ def run_ours(args):
         line["e2e_uint8_echoes"] = e2e_u8
     if not args.no_cpu_baseline:
         cb = run_cpu_reference(args, steps=1, warmup=0, workers=1, frames=args.cpu_frames)
-        line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "port",
+        line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"],
                                 "sample": cb["sample"], "stage_seconds": cb["stage_seconds"],
                                 "host_cpus": os.cpu_count()}
     print(json.dumps(line))
@@ -627,7 +679,7 @@ def run_reference(args):
         "steps": steps, "warmup": warm, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 (numpy, scikit-learn)", "data": "synthetic",
         "config": workload_config(args),
-        "cpu_baseline": {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "port", "sample": cb["sample"],
+        "cpu_baseline": {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"],
                          "stage_seconds": cb["stage_seconds"], "host_cpus": os.cpu_count()},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
